@@ -1,0 +1,238 @@
+/*
+ * cygym_b200.h -- C-ABI of the B200-native CyGym step path.
+ *
+ * The reference (Lan131/CyGym) has no FFI: its boundary is the Python attribute
+ * surface of Volt_Typhoon_CyberDefenseEnv.  This header
+ * is the C-ABI a maintainer would bind from Python (ctypes)
+ * to replace that path.  Each entry point cites the reference member it
+ * replaces.  Plain pointers and sizes only; no torch types.  Device memory is
+ * owned by the caller (torch tensors on the Python side); the library only
+ * launches kernels on the caller's stream.
+ *
+ * Conventions: every function returns 0 on success and a negative CYG_E_* code
+ * otherwise; cyg_last_error() returns a thread-local message.  All launches are
+ * asynchronous on the given stream.  One host thread per handle.
+ */
+#ifndef CYGYM_B200_H
+#define CYGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYG_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define CYG_OK 0
+#define CYG_E_INVAL (-22)   /* bad argument / unsupported configuration */
+#define CYG_E_NOMEM (-12)
+#define CYG_E_CUDA (-5)     /* a CUDA runtime call failed; see cyg_last_error() */
+#define CYG_E_STATE (-71)   /* sticky per-env error flag raised by a kernel */
+
+/* ---- canonical per-device word: dev[B][M] uint32 ------------------------
+ * Flattening of the dynamic Device fields (CDSimulatorComponents.py:219-242)
+ * and Workload (CDSimulatorComponents.py:18-26).                            */
+#define CYG_DEV_COMP 0x00000001u      /* isCompromised */
+#define CYG_DEV_KNOWN 0x00000002u     /* Known_to_attacker */
+#define CYG_DEV_NYA 0x00000004u       /* Not_yet_added */
+#define CYG_DEV_OWNED 0x00000008u     /* attacker_owned */
+#define CYG_DEV_REMOVED 0x00000010u   /* removed_before */
+#define CYG_DEV_HASWL 0x00000020u     /* workload is not None */
+#define CYG_DEV_BUSYSET 0x00000040u   /* member of env._busy_devices (volt_typhoon_env.py:1330) */
+#define CYG_DEV_ACTSET 0x00000080u    /* member of env._active_ids (CyberDefenseEnv.py:654-659) */
+#define CYG_DEV_PT_SHIFT 8            /* workload.processing_time, 3 bits */
+#define CYG_DEV_PT_MASK 0x7u
+#define CYG_DEV_BUSY_SHIFT 12         /* busy_time, 8 bits canonical (kernels keep 4: 0..15) */
+#define CYG_DEV_BUSY_MASK 0xFFu
+#define CYG_DEV_CBY_SHIFT 20          /* compromised_by as a mask over exploit slots, 6 bits */
+#define CYG_DEV_CBY_MASK 0x3Fu
+#define CYG_BUSY_MAX 15
+
+/* ---- per-device checkpoint word: ckpt[B][M] uint32 ----------------------
+ * The 7 fields of _device_state (volt_typhoon_env.py:419-428).              */
+#define CYG_CK_COMP 0x00000001u
+#define CYG_CK_KNOWN 0x00000002u
+#define CYG_CK_NYA 0x00000004u
+#define CYG_CK_REACH 0x00000008u
+#define CYG_CK_HASWL 0x00000020u
+#define CYG_CK_VALID 0x80000000u
+/* pt / busy / cby use the CYG_DEV_* shifts */
+
+/* ---- static per-device word: dev_static[M] uint32 (shared by all envs) -- */
+#define CYG_ST_DC 0x00000001u         /* device_type == "DomainController" */
+#define CYG_ST_SERVER 0x00000002u     /* wtype == 'server' */
+#define CYG_ST_REACH 0x00000004u      /* reachable_by_attacker (set once at init) */
+#define CYG_ST_NAPPS_SHIFT 8          /* len(device.apps), 8 bits */
+#define CYG_ST_VULN_SHIFT 16          /* bit e: an app vulnerability id is in exploits[e].target */
+
+/* ---- per-env scalars: scal[B][16] uint32 -------------------------------- */
+enum {
+  CYG_S_STEP = 0,       /* step_num */
+  CYG_S_EPOCH = 1,      /* draw epoch (bumped by every step / randomize / sample_action) */
+  CYG_S_FLAGS = 2,      /* CYG_FL_* */
+  CYG_S_PREV_X = 3,     /* low16: n_comp behind _prev_att_potential (0xFFFF = None); high16: #extra edges */
+  CYG_S_DEF_STEP = 4,   /* defender_step */
+  CYG_S_ATT_STEP = 5,   /* attacker_step */
+  CYG_S_LOGS = 6,       /* len(simulator.logger.logs) */
+  CYG_S_COMPCNT = 7,    /* compromised_devices_cnt */
+  CYG_S_WORK = 8,       /* work_done */
+  CYG_S_DEFCOST = 9,    /* defensive_cost (float bits) */
+  CYG_S_CLEANCOST = 10, /* clearning_cost (float bits) */
+  CYG_S_SCAN = 11,      /* scan_cnt */
+  CYG_S_REVERT = 12,    /* revert_count */
+  CYG_S_CKPT = 13,      /* checkpoint_count */
+  CYG_S_EBLK = 14,      /* edges_blocked */
+  CYG_S_EADD = 15,      /* edges_added */
+  CYG_NSCAL = 16
+};
+#define CYG_FL_HAS_CKPT 0x00000001u     /* env.checkpoint is not None */
+#define CYG_FL_SETS_INIT 0x00000002u    /* env._active_ids exists */
+#define CYG_FL_DET_TRAINED 0x00000004u  /* action 10 ran with a non-empty log: sklearn territory */
+#define CYG_FL_ERR_BUSY 0x00000010u     /* busy_time exceeded CYG_BUSY_MAX (kernel saturated it) */
+#define CYG_FL_ERR_XCAP 0x00000020u     /* more attacker-star edges than xcap */
+#define CYG_FL_ERR_DETECTOR 0x00000040u /* scan requested after the detector was trained */
+#define CYG_FL_ERR_MASK 0x000000F0u
+#define CYG_FL_DISC_SHIFT 8             /* bit e: exploits[e].discovered */
+
+/* ---- extra (per-env) edges: extra[B][xcap] uint32 -----------------------
+ * Attacker hub-star edges added by evolve_network (CyberDefenseEnv.py:738-774). */
+#define CYG_X_V_SHIFT 12
+#define CYG_X_BLOCKED 0x01000000u
+#define CYG_X_IDMASK 0xFFFu
+
+/* ---- actions -------------------------------------------------------------
+ * One action = (action_type, exploit_indices, device_indices, app_index)
+ * (volt_typhoon_env.py:876).  hdr[B][4] uint32 + dev_mask[B][W] uint32,
+ * W = ceil(M/32).  device_indices is the ascending list of the mask's bits
+ * unless an explicit order array is given (then order[b][0..n_dev) is used).  */
+#define CYG_ATYPE_NONE 0x80u  /* action is None: filled from base_line (volt_typhoon_env.py:847-874) */
+/* hdr[0]: atype (bits 0-7, signed) | mode<<8 (0 defender, 1 attacker) | n_ex<<16 (0..4) */
+/* hdr[1]: exploit_indices[0..3], one signed byte each */
+/* hdr[2]: n_dev (len(device_indices)) */
+/* hdr[3]: app_index (int32) */
+#define CYG_MODE_DEFENDER 0
+#define CYG_MODE_ATTACKER 1
+
+/* step flags */
+#define CYG_STEP_GROUPED 0x1u   /* step_grouped semantics (volt_typhoon_env.py:694-779) */
+#define CYG_STEP_SKIP_WORK 0x2u /* step(action, agent_cnt != len(net)) (volt_typhoon_env.py:1207,1307) */
+
+/* base_line (volt_typhoon_env.py:849-873, :913, :1130, :1187) */
+enum { CYG_BL_NASH = 0, CYG_BL_NO_DEFENSE = 1, CYG_BL_PRESET = 2, CYG_BL_NO_ATTACK = 3, CYG_BL_OTHER = 4 };
+
+/* ---- configuration (attributes of the env; volt_typhoon_env.py:32-120,
+ * CyberDefenseEnv.py:19-62) ------------------------------------------------ */
+typedef struct cyg_config {
+  int32_t M;                 /* Max_network_size == len(subnet.net) (device slots) */
+  int32_t E;                 /* unique directed pairs in the base graph */
+  int32_t X;                 /* MaxExploits */
+  int32_t n_exploits;        /* len(simulator.exploits) */
+  int32_t xcap;              /* capacity of the per-env extra-edge list */
+  int32_t num_of_device;     /* numOfDevice */
+  int32_t min_network_size;  /* Min_network_size */
+  int32_t evolve_period;     /* _evolve_period (volt_typhoon_env.py:66) */
+  int32_t wl_period_base;    /* workload_period_base */
+  int32_t wl_period_max;     /* workload_period_max */
+  int32_t wl_cap;            /* workload_cap, -1 = None */
+  int32_t scaling_vulnerability;
+  int32_t turbo;
+  int32_t zero_day;
+  uint32_t zero_day_mask;    /* common_exploit_indices | private_exploit_indices */
+  int32_t att_space_n;       /* attacker_action_space.n = n_exploits + 3 */
+  int32_t def_space_n;       /* defender_action_space.n = 14 */
+  int32_t default_high;      /* default_high = 3 */
+  int32_t n_app_ids;         /* get_num_app_indices() */
+  int32_t base_line;         /* CYG_BL_* */
+  int32_t tri_high;          /* `high` of np.random.triangular(0, mode, high) (CDSimulator.py:308) */
+  int32_t reserved0;
+  float work_scale, comp_scale, def_scale, gamma;
+  uint64_t thr_p_add;        /* random() < p_add      <=> x < thr (CyberDefenseEnv.py:679) */
+  uint64_t thr_p_attacker;   /* random() < p_attacker <=> x < thr (CyberDefenseEnv.py:690) */
+  uint32_t poisson_tab[16];  /* np.random.poisson(lambda_events): #{j: x >= tab[j]} (CyberDefenseEnv.py:668) */
+  uint32_t tri_tab[8];       /* ceil(triangular): min(tri_high, 1 + #{v: x >= tab[v]}) */
+  uint64_t seed;             /* Philox key */
+} cyg_config;
+
+/* ---- shared network tables (device pointers for the CUDA library) ------- */
+typedef struct cyg_network {
+  const int32_t* row_ptr;      /* [M+1] CSR over unique out-pairs, ascending neighbour id (_outnbrs, volt:456-473) */
+  const int32_t* col;          /* [E] */
+  const uint8_t* mult;         /* [E] multiplicity of the pair in the igraph multigraph */
+  const uint32_t* dev_static;  /* [M] CYG_ST_* */
+  const float* os_val;         /* [M] os_to_float(d.OS) (CyberDefenseEnv.py:125-144) */
+  const float* ver_val;        /* [M] float(d.version) */
+} cyg_network;
+
+/* ---- per-env state buffers (device pointers, canonical layout) ---------- */
+typedef struct cyg_state {
+  uint32_t* dev;      /* [B][M] */
+  uint32_t* ckpt;     /* [B][M] */
+  uint32_t* blocked;  /* [B][ceil(E/32)] bit e: base pair e is in env._blocked (volt:73) */
+  uint32_t* extra;    /* [B][xcap] */
+  uint32_t* scal;     /* [B][16] */
+} cyg_state;
+
+typedef struct cyg_actions {
+  const uint32_t* hdr;    /* [G][B][4] */
+  const uint32_t* mask;   /* [G][B][W] */
+  const uint16_t* order;  /* optional [G][B][order_stride] explicit device_indices order, or NULL */
+  int32_t order_stride;
+  int32_t n_groups;       /* G: 1 for step(), len(groups) for step_grouped() */
+} cyg_actions;
+
+typedef struct cyg_step_out {
+  float* raw_reward;     /* [B]   (volt_typhoon_env.py:1291,1303) */
+  float* shaped_reward;  /* [B]   (volt_typhoon_env.py:1292,1304) */
+  int32_t* done;         /* [B]   _check_done: step_num > 1000 (CyberDefenseEnv.py:547-552) */
+  uint32_t* pre_masks;   /* optional [B][3][W]: compromised / known / not_yet_added BEFORE evolve_network,
+                            i.e. the content of the `state` step() returns (volt_typhoon_env.py:1306) */
+  float* obs;            /* optional [B][obs_dim] post-evolve view of `obs_mode` */
+  int32_t obs_mode;      /* 0 none, 1 _get_defender_state (6M), 2 _get_attacker_state (4M+X), 3 _get_state (6M) */
+} cyg_step_out;
+
+typedef struct cyg_env_s* cyg_handle;
+
+int cyg_version(void);
+const char* cyg_last_error(void);
+
+/* Replaces Volt_Typhoon_CyberDefenseEnv.__init__ + attribute configuration. The
+ * network tables are copied to the device by the library (they are tiny). All
+ * pointers in `net` are HOST pointers here. `device` is the CUDA ordinal.      */
+int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_net, int32_t B,
+               int32_t env_id0, int32_t device);
+int cyg_destroy(cyg_handle h);
+int cyg_set_base_line(cyg_handle h, int32_t base_line);
+
+/* Sizes the caller must allocate (in uint32 words per env) for the kernels' internal
+ * bit-plane state: state words per env. */
+int cyg_internal_words(cyg_handle h, int64_t* words_per_env);
+
+/* Bind the internal state buffer (device pointer, B * words_per_env uint32, 16-byte aligned). */
+int cyg_bind(cyg_handle h, uint32_t* internal_state);
+
+/* canonical <-> internal conversion (import = reset()/snapshot load, volt_typhoon_env.py:1904-1925). */
+int cyg_import_state(cyg_handle h, const cyg_state* canonical, void* stream);
+int cyg_export_state(cyg_handle h, const cyg_state* canonical, void* stream);
+
+/* Replaces step() / step_grouped() (volt_typhoon_env.py:818-1333, :694-779). */
+int cyg_step(cyg_handle h, const cyg_actions* actions, uint32_t step_flags, const cyg_step_out* out,
+             void* stream);
+
+/* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
+int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
+
+/* Replaces sample_action() (CyberDefenseEnv.py:555-578) for every env; writes hdr[B][4], mask[B][W]. */
+int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream);
+
+/* Replaces _get_defender_state / _get_attacker_state / _get_state (CyberDefenseEnv.py:241/194/146). */
+int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t cyg_launch_count(cyg_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYGYM_B200_H */
