@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused CyGym step kernel on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the CPU arm (oracle port on the host cores)
+
+Workload (config.workload "C3"): 65 536 envs x 100 device slots / 8 subnets per GPU, synthetic network
+(cygym_b200.network.synthetic_network), uniformly random sample_action()-style defender / attacker
+actions on alternating turns, detector untrained (defender action 10 rewritten to the no-op 8).
+A "step" is ONE launch of cyg_step over one batch of B envs.  Envs shard across GPUs with no
+data-path collective (weak scaling: B envs per GPU); NCCL only carries the timing reduction.
+
+L2 policy: the bench rotates over `--sets` independent env sets (default 3 x 57 MB of state
+> 126 MB L2) and a ring of pre-generated action batches, so a launch never finds its records
+in L2 from the previous launch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec at 64K envs x 100 devices"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--devices", type=int, default=100)
+    ap.add_argument("--subnets", type=int, default=8)
+    ap.add_argument("--sets", type=int, default=3, help="independent env sets rotated to defeat L2 residency")
+    ap.add_argument("--ring", type=int, default=8, help="pre-generated action batches per mode")
+    ap.add_argument("--obs", type=int, default=0, help="fused observation mode inside the step (0 none, 1 defender, 2 attacker)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"C3: {a.envs} envs x {a.devices} device slots / {a.subnets} subnets per GPU, random sample_action defender/attacker turns"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_arm(a, seconds, threads=None):
+    """The oracle port (oracle/cyg_oracle.c, OpenMP over envs) timed on the host cores on a bounded
+    sample of the same workload.  Returns (env-steps/s, cores, description)."""
+    import numpy as np
+    from cygym_b200 import synthetic_network
+    from oracle import cyg_oracle as O
+    from tests.common import oracle_for, oracle_state_from_template, sanitize_actions
+    net = synthetic_network(a.devices, n_subnets=a.subnets, seed=a.seed)
+    cores = threads or os.cpu_count() or 1
+    cores = min(cores, O.lib().cyo_max_threads()) if O.lib().cyo_max_threads() > 0 else 1
+    Bc = max(cores * 256, 1024)
+    orc, _ = oracle_for(net, seed=a.seed, xcap=16)
+    st = oracle_state_from_template(orc, net, Bc)
+    acts = []
+    for mode in (0, 1):
+        h, m = orc.sample_actions(st, mode)
+        h = sanitize_actions(h, np.ones(Bc, np.uint32), mode)
+        acts.append((h, m))
+    for t in range(4):
+        orc.step(st, *acts[t & 1], n_threads=cores)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        orc.step(st, *acts[n & 1], n_threads=cores)
+        n += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or n >= 100000:
+            break
+    return Bc * n / el, cores, f"{Bc} envs x {n} steps of the same workload, {cores} OpenMP threads, {el:.1f}s"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(0.5, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+    # each "step" of this arm is one bounded CPU sample
+    vals = []
+    for i in range(a.warmup + a.steps):
+        v, cores, sample = cpu_arm(a, per_step)
+        if i >= a.warmup:
+            vals.append(v)
+    val = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "l2_policy": "n/a (CPU arm)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" per step, {a.steps} steps"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import ActionBatch, VectorCyberDefenseEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, Wm = a.envs, a.steps, max(3, a.warmup)
+
+    net = synthetic_network(a.devices, n_subnets=a.subnets, seed=a.seed)
+    # one env set per rotation slot; env ids are globally unique across ranks and sets
+    sets = [VectorCyberDefenseEnv(net, B, device=dev, seed=a.seed, env_id0=(rank * a.sets + s) * B, xcap=16)
+            for s in range(a.sets)]
+    # ring of pre-generated action batches (inputs resident in HBM before the timed region)
+    ring = {0: [], 1: []}
+    for mode in (0, 1):
+        for r in range(a.ring):
+            ab = sets[r % a.sets].sample_actions(mode)
+            if mode == 0:  # detector untrained: defender 10 -> no-op 8
+                ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == 10, (ab.hdr[:, 0] & ~0xFF) | 8, ab.hdr[:, 0])
+            ring[mode].append(ActionBatch(ab.hdr.clone(), ab.mask.clone()))
+    torch.cuda.synchronize()
+
+    def one_step(i):
+        env = sets[i % a.sets]
+        turn = (i // a.sets) & 1  # every set alternates defender / attacker turns
+        env.step(ring[turn][(i // (2 * a.sets)) % a.ring], obs_mode=a.obs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = sum(s.launch_count for s in sets)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(K):
+        one_step(Wm + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(s.launch_count for s in sets) - l0
+    clocks = sampler.stop()
+    errs = int(max(int(s.error_flags().max().item()) for s in sets))
+
+    # ---- e2e: through VectorCyberDefenseEnv with HOST buffers (pinned), H2D + step + D2H every step ----
+    e2e = None
+    if not a.no_e2e:
+        Ke = max(10, min(K, 100))
+        host = []
+        for mode in (0, 1):
+            ab = ring[mode][0]
+            host.append((ab.hdr.cpu().pin_memory(), ab.mask.cpu().pin_memory()))
+        d_hdr = torch.empty_like(ring[0][0].hdr)
+        d_mask = torch.empty_like(ring[0][0].mask)
+        out_host = torch.empty(3, B, dtype=torch.float32).pin_memory()
+        env = sets[0]
+
+        def e2e_step(i):
+            h, m = host[i & 1]
+            d_hdr.copy_(h, non_blocking=True)
+            d_mask.copy_(m, non_blocking=True)
+            raw, shaped, done = env.step(ActionBatch(d_hdr, d_mask))
+            out_host[0].copy_(raw, non_blocking=True)
+            out_host[1].copy_(shaped, non_blocking=True)
+            out_host[2].copy_(done.view(torch.float32), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads rewards / done before the next action
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(Ke):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        e2e = (ems, Ke, host[0][0].numel() * 4 + host[0][1].numel() * 4, 3 * B * 4)
+
+    # ---- max over ranks ----
+    t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ems = float(t[0]), float(t[1])
+    if rank == 0:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f) if os.path.getsize(f.name) else {}
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
+        alg = net.algorithmic_bytes_per_step(obs=bool(a.obs))
+        launch_s = ms * 1e-3 / K
+        achieved = alg * B / launch_s / 1e9
+        value = world * B * K / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
+                       "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4,
+                       "l2_policy": f"rotating {a.sets} env sets ({a.sets * B * (sets[0].S + net.M) * 4 / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
+                       "parallelism": f"env-sharded x{world}, no per-step collective", "error_flags": errs},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
+                         "launch_us": launch_s * 1e6, "peak_source": peak_src,
+                         "actual_bytes_per_env_step": 2 * sets[0].S * 4 + 4 * (4 + net.W) + 12},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = {"value": world * B * e2e[1] / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[2],
+                           "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1]}
+        if not a.no_cpu_baseline and world == 1:
+            v, cores, sample = cpu_arm(a, a.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,601 @@
+/*
+ * cyg_kernels.cu -- sm_100a kernels + the C-ABI of include/cygym_b200.h.
+ *
+ * cyg_step_kernel<W>: ONE launch per env step (volt_typhoon_env.py:818-1333 / :694-779).
+ *   A CTA owns a block of NB consecutive envs.  Their internal records (cyg_core.cuh) are one
+ *   contiguous span of HBM, so the CTA moves them with a single TMA bulk copy into shared
+ *   memory (cp.async.bulk + mbarrier), steps them there, and writes them back with a single
+ *   bulk store: HBM sees exactly one full-sector read and one write of the state per step.
+ *   The hot network tables (adjacency bit rows, device masks, CSR) ride in on the same mbarrier.
+ *   Work mapping is thread-per-env over bit-planes (32 devices per integer op), in three phases
+ *   separated by __syncthreads():
+ *     1. prologue  thread t -> env t      : epoch, executed action type, busy tick
+ *     2. action    thread t -> env perm[t]: envs are counting-sorted by (mode, action type) inside
+ *                                           the CTA so that a warp runs one action type and the 14
+ *                                           defender / 3+X attacker branches do not serialise
+ *     3. epilogue  thread t -> env t      : work, arrivals, reward, counters, evolve_network,
+ *                                           coalesced outputs, optional fused observation rows
+ * No tensor cores: the path has no dense contraction.  No CPU fallback anywhere in this file.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "cyg_core.cuh"
+#include "cyg_tables.h"
+
+using namespace cyg;
+
+/* ---- small PTX wrappers (mbarrier + 1-D TMA bulk copies) ------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* ---- kernel parameters ---------------------------------------------------- */
+struct StepParams {
+  Net net;              /* pointers into the device copy of the table blob */
+  uint32_t* recs;       /* [B][S] internal records */
+  uint32_t* ckpt;       /* [B][M] canonical checkpoint words */
+  const uint32_t* hdr;  /* [G][B][4] */
+  const uint32_t* mask; /* [G][B][W] */
+  const uint16_t* order;
+  float* raw;
+  float* shaped;
+  int32_t* done;
+  uint32_t* pre_masks;
+  float* obs;
+  int B, env_id0, G, order_stride, obs_mode;
+  uint32_t flags;
+};
+
+#define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
+
+__host__ __device__ inline int act_stride(int W) { int a = 4 + W; return (a & 1) ? a : a + 1; }
+
+/* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned) */
+struct SmemPlan {
+  size_t off_tables, off_recs, off_act, off_cost, off_meta, off_perm, off_cnt, off_net, off_bar, total;
+};
+__host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int W, int NB) {
+  SmemPlan p;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
+  p.off_tables = take((size_t)hot_words * 4);
+  p.off_recs = take((size_t)NB * S * 4);
+  p.off_act = take((size_t)NB * act_stride(W) * 4);
+  p.off_cost = take((size_t)NB * 8);
+  p.off_meta = take((size_t)NB * 4);
+  p.off_perm = take((size_t)NB * 2);
+  p.off_cnt = take((size_t)(CYG_NKEYS + 1) * 4);
+  p.off_net = take(sizeof(Net));
+  p.off_bar = take(8);
+  p.total = o;
+  return p;
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int NB = blockDim.x, tid = threadIdx.x;
+  const int S = p.net.S, M = p.net.M;
+  const int env0 = blockIdx.x * NB;
+  const int nb = min(NB, p.B - env0);
+  const SmemPlan sp = smem_plan(p.net.hot_words, S, W, NB);
+  uint32_t* s_tab = (uint32_t*)(smem + sp.off_tables);
+  uint32_t* s_rec = (uint32_t*)(smem + sp.off_recs);
+  uint32_t* s_act = (uint32_t*)(smem + sp.off_act);
+  double* s_cost = (double*)(smem + sp.off_cost);
+  uint32_t* s_meta = (uint32_t*)(smem + sp.off_meta);
+  uint16_t* s_perm = (uint16_t*)(smem + sp.off_perm);
+  uint32_t* s_cnt = (uint32_t*)(smem + sp.off_cnt);
+  Net* s_net = (Net*)(smem + sp.off_net);
+  uint64_t* bar = (uint64_t*)(smem + sp.off_bar);
+  const int AS = act_stride(W);
+  const bool grouped = (p.flags & CYG_STEP_GROUPED) != 0;
+
+  uint32_t* g_rec = p.recs + (size_t)env0 * S;
+  const uint32_t rec_bytes = (uint32_t)nb * S * 4u;
+  const uint32_t tab_bytes = p.net.hot_words * 4u;
+  const bool bulk_ok = (rec_bytes & 15u) == 0 && ((((size_t)g_rec) & 15) == 0);
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, tab_bytes + (bulk_ok ? rec_bytes : 0u));
+    bulk_g2s(s_tab, p.net.blob, tab_bytes, bar);
+    if (bulk_ok) bulk_g2s(s_rec, g_rec, rec_bytes, bar);
+    /* CTA-local copy of the Net whose hot tables point into shared memory */
+    Net n = p.net;
+    auto hot = [&](const void* g) { return (const uint32_t*)((const unsigned char*)s_tab + ((const unsigned char*)g - (const unsigned char*)p.net.blob)); };
+    n.adj = hot(n.adj); n.m_dc = hot(n.m_dc); n.m_server = hot(n.m_server); n.m_reach = hot(n.m_reach);
+    n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_vuln = hot(n.m_vuln);
+    n.mlo = hot(n.mlo); n.mhi = hot(n.mhi);
+    n.row_ptr = (const int32_t*)hot(n.row_ptr); n.col = (const uint16_t*)hot(n.col);
+    *s_net = n;
+  }
+  if (tid < CYG_NKEYS + 1) s_cnt[tid] = 0;
+  /* stage this block's actions (group 0) while the bulk copies fly: coalesced 16-byte loads */
+  if (tid < nb) {
+    const uint32_t* h = p.hdr + (size_t)(env0 + tid) * 4;
+    const uint32_t* m = p.mask + (size_t)(env0 + tid) * W;
+    uint32_t* a = s_act + tid * AS;
+    uint4 hv = *reinterpret_cast<const uint4*>(h);
+    a[0] = hv.x; a[1] = hv.y; a[2] = hv.z; a[3] = hv.w;
+#pragma unroll
+    for (int w = 0; w < W; w++) a[4 + w] = m[w];
+  }
+  __syncthreads(); /* mbarrier initialised; s_net visible */
+  if (!bulk_ok) {
+    for (int i = tid; i < nb * S; i += NB) s_rec[i] = g_rec[i];
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+
+  const uint16_t* order_t = p.order ? p.order + (size_t)(env0 + tid) * p.order_stride : nullptr;
+
+  /* ---- phase 1: prologue, thread t -> env t ---- */
+  int key = 0;
+  if (tid < nb) {
+    Env<W> e(s_net, s_rec + tid * S, p.ckpt + (size_t)(env0 + tid) * M, (uint32_t)(p.env_id0 + env0 + tid));
+    const uint32_t* a = s_act + tid * AS;
+    int atype = e.prologue(a, a + 4, order_t, p.flags);
+    int mode = (int)((a[0] >> 8) & 1u);
+    key = grouped ? 0 : ((mode << 4) | (atype & 15));
+    s_meta[tid] = (uint32_t)(atype & 0xFF);
+    atomicAdd(&s_cnt[key + 1], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) { /* exclusive prefix over the 32 keys */
+    uint32_t run = 0;
+    for (int k = 1; k <= CYG_NKEYS; k++) { uint32_t c = s_cnt[k]; s_cnt[k] = run; run += c; }
+  }
+  __syncthreads();
+  if (tid < nb) {
+    uint32_t pos = atomicAdd(&s_cnt[key + 1], 1u);
+    s_perm[pos] = (uint16_t)tid;
+  }
+  __syncthreads();
+
+  /* ---- phase 2: the action, thread t -> env perm[t] (a warp sees one action type) ---- */
+  if (tid < nb) {
+    const int el = s_perm[tid];
+    const int env = env0 + el;
+    Env<W> e(s_net, s_rec + el * S, p.ckpt + (size_t)env * M, (uint32_t)(p.env_id0 + env));
+    e.resume_epoch();
+    typename Env<W>::Carry cy;
+    const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
+    if (!grouped) {
+      const uint32_t* a = s_act + el * AS;
+      e.act(a, a + 4, ord, 0, 0, 0, 1, p.flags, (int)(int8_t)s_meta[el], cy);
+    } else {
+      e.act(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
+            (size_t)p.B * p.order_stride, p.G, p.flags, 0, cy);
+    }
+    s_cost[el] = cy.cost;
+    s_meta[el] = (uint32_t)(cy.atype & 0xFF) | ((uint32_t)cy.mode << 8) | ((uint32_t)cy.dirty << 9);
+  }
+  __syncthreads();
+
+  /* ---- phase 3: epilogue, thread t -> env t (coalesced outputs) ---- */
+  if (tid < nb) {
+    const int env = env0 + tid;
+    Env<W> e(s_net, s_rec + tid * S, p.ckpt + (size_t)env * M, (uint32_t)(p.env_id0 + env));
+    e.resume_epoch();
+    typename Env<W>::Carry cy;
+    uint32_t mt = s_meta[tid];
+    cy.cost = s_cost[tid];
+    cy.atype = (int)(int8_t)(mt & 0xFF);
+    cy.mode = (int)((mt >> 8) & 1u);
+    cy.dirty = (int)((mt >> 9) & 1u);
+    float raw, shaped;
+    int32_t done;
+    e.epilogue(cy, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
+    p.raw[env] = raw;
+    p.shaped[env] = shaped;
+    p.done[env] = done;
+  }
+  __syncthreads();
+
+  /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
+  if (p.obs && p.obs_mode) {
+    const int dim = p.obs_mode == 2 ? 4 * M + p.net.cfg.X : 6 * M;
+    float* o = p.obs + (size_t)env0 * dim;
+    for (int i = tid; i < nb * dim; i += NB) {
+      int el = i / dim;
+      o[i] = observe_elem<W>(s_net, s_rec + el * S, p.obs_mode, i - el * dim);
+    }
+  }
+
+  /* ---- write the block's records back: one bulk store ---- */
+  if (bulk_ok) {
+    fence_proxy_async(); /* generic-proxy writes to smem -> visible to the async proxy */
+    __syncthreads();
+    if (tid == 0) {
+      bulk_s2g(g_rec, s_rec, rec_bytes);
+      bulk_commit_wait_read();
+    }
+  } else {
+    for (int i = tid; i < nb * S; i += NB) g_rec[i] = s_rec[i];
+  }
+}
+
+/* ---- randomize_compromise_and_ownership: thread per env on the global record ---- */
+struct SimpleParams {
+  Net net;
+  uint32_t* recs;
+  const uint8_t* env_mask;
+  uint32_t* hdr;
+  uint32_t* mask;
+  int B, env_id0, mode;
+};
+
+template <int W>
+__global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  if (p.env_mask && !p.env_mask[env]) return;
+  uint32_t rec[CYG_REC_PLANES + 21 * W]; /* scalars + planes are all randomize touches */
+  uint32_t* g = p.recs + (size_t)env * p.net.S;
+  const int nw = CYG_REC_PLANES + p.net.NP * W;
+  for (int i = 0; i < nw; i++) rec[i] = g[i];
+  Env<W> e(&p.net, rec, nullptr, (uint32_t)(p.env_id0 + env));
+  e.randomize();
+  for (int i = 0; i < nw; i++) g[i] = rec[i];
+}
+
+template <int W>
+__global__ void cyg_sample_kernel(const __grid_constant__ SimpleParams p) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  uint32_t rec[CYG_NSCAL];
+  uint32_t* g = p.recs + (size_t)env * p.net.S;
+  for (int i = 0; i < CYG_NSCAL; i++) rec[i] = g[i];
+  Env<W> e(&p.net, rec, nullptr, (uint32_t)(p.env_id0 + env));
+  uint32_t h[4], m[W];
+  e.sample_action(p.mode, h, m);
+  g[CYG_S_EPOCH] = rec[CYG_S_EPOCH];
+  for (int i = 0; i < 4; i++) p.hdr[(size_t)env * 4 + i] = h[i];
+  for (int w = 0; w < W; w++) p.mask[(size_t)env * W + w] = m[w];
+}
+
+/* ---- canonical <-> internal conversion: one warp per env, ballots build the planes ---- */
+struct ConvParams {
+  Net net;
+  uint32_t* recs;
+  uint32_t* ckpt_int;
+  uint32_t *dev, *ckpt, *blocked, *extra, *scal;
+  int B;
+};
+
+template <int W>
+__global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B) return;
+  const Net& n = p.net;
+  uint32_t* rec = p.recs + (size_t)warp * n.S;
+  const int M = n.M;
+  uint32_t err = 0;
+  for (int w = 0; w < W; w++) {
+    int d = w * 32 + lane;
+    uint32_t x = d < M ? p.dev[(size_t)warp * M + d] : 0u;
+    uint32_t b = (x >> CYG_DEV_BUSY_SHIFT) & CYG_DEV_BUSY_MASK;
+    if (b > CYG_BUSY_MAX) { b = CYG_BUSY_MAX; err = CYG_FL_ERR_BUSY; }
+    uint32_t flags8 = x & 0xFFu; /* COMP KNOWN NYA OWNED REMOVED HASWL BUSYSET ACTSET are bits 0..7 == planes 0..7 */
+    for (int pnum = 0; pnum < 8; pnum++) {
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (flags8 >> pnum) & 1u);
+      if (lane == 0) rec[CYG_REC_PLANES + pnum * W + w] = m;
+    }
+    uint32_t pt = (x >> CYG_DEV_PT_SHIFT) & CYG_DEV_PT_MASK;
+    for (int k = 0; k < 3; k++) {
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (pt >> k) & 1u);
+      if (lane == 0) rec[CYG_REC_PLANES + (P_PT0 + k) * W + w] = m;
+    }
+    for (int k = 0; k < 4; k++) {
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (b >> k) & 1u);
+      if (lane == 0) rec[CYG_REC_PLANES + (P_BUSY0 + k) * W + w] = m;
+    }
+    uint32_t cb = (x >> CYG_DEV_CBY_SHIFT) & CYG_DEV_CBY_MASK;
+    for (int k = 0; k < n.ncby; k++) {
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (cb >> k) & 1u);
+      if (lane == 0) rec[CYG_REC_PLANES + (P_CBY0 + k) * W + w] = m;
+    }
+    if (d < M) p.ckpt_int[(size_t)warp * M + d] = p.ckpt ? p.ckpt[(size_t)warp * M + d] : 0u;
+  }
+  err = __reduce_or_sync(0xFFFFFFFFu, err);
+  if (lane < CYG_NSCAL) {
+    uint32_t v = p.scal[(size_t)warp * CYG_NSCAL + lane];
+    if (lane == CYG_S_FLAGS) v |= err;
+    rec[lane] = v;
+  }
+  for (int i = lane; i < n.EW; i += 32) rec[n.off_blocked + i] = p.blocked[(size_t)warp * n.EW + i];
+  for (int i = lane; i < n.cfg.xcap; i += 32) rec[n.off_extra + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
+  for (int i = n.off_extra + n.cfg.xcap + lane; i < n.S; i += 32) rec[i] = 0u;
+}
+
+template <int W>
+__global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= p.B) return;
+  const Net& n = p.net;
+  const uint32_t* rec = p.recs + (size_t)warp * n.S;
+  const int M = n.M;
+  for (int w = 0; w < W; w++) {
+    int d = w * 32 + lane;
+    if (d >= M) continue;
+    p.dev[(size_t)warp * M + d] = export_device<W>(&n, rec, d);
+    if (p.ckpt) p.ckpt[(size_t)warp * M + d] = p.ckpt_int[(size_t)warp * M + d];
+  }
+  if (lane < CYG_NSCAL) p.scal[(size_t)warp * CYG_NSCAL + lane] = rec[lane];
+  for (int i = lane; i < n.EW; i += 32) p.blocked[(size_t)warp * n.EW + i] = rec[n.off_blocked + i];
+  for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = rec[n.off_extra + i];
+}
+
+struct ObsParams {
+  Net net;
+  const uint32_t* recs;
+  float* obs;
+  int B, obs_mode;
+};
+template <int W>
+__global__ void cyg_observe_kernel(const __grid_constant__ ObsParams p) {
+  const int dim = p.obs_mode == 2 ? 4 * p.net.M + p.net.cfg.X : 6 * p.net.M;
+  const size_t total = (size_t)p.B * dim;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t env = i / dim;
+    p.obs[i] = observe_elem<W>(&p.net, p.recs + env * p.net.S, p.obs_mode, (int)(i - env * dim));
+  }
+}
+
+/* ===========================================================================
+ * C-ABI (include/cygym_b200.h)
+ * ======================================================================== */
+struct cyg_env_s {
+  TableBlob blob;
+  Net net;           /* device pointers */
+  uint32_t* d_blob;
+  uint32_t* state;   /* bound internal buffer: [B][S] records then [B][M] checkpoint words */
+  int B, env_id0, device, W, NB;
+  size_t smem_bytes;
+  int64_t launches;
+};
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(CYG_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t _e = (call);                             \
+    if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev;
+  bool ok;
+  explicit DeviceGuard(int dev) : prev(-1), ok(false) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define DISPATCH_W(W_, STMT)                     \
+  switch (W_) {                                  \
+    case 1: { constexpr int KW = 1; STMT; } break; \
+    case 2: { constexpr int KW = 2; STMT; } break; \
+    case 3: { constexpr int KW = 3; STMT; } break; \
+    default: { constexpr int KW = 4; STMT; } break; \
+  }
+
+static int pick_block_envs(const cyg_env_s* h, int requested) {
+  /* envs (= threads) per CTA: as many as keeps >= 3 CTAs resident per SM, capped at 256 */
+  if (requested > 0) return requested;
+  const size_t budget = 72 * 1024;
+  int nb = 256;
+  while (nb > 32 && smem_plan(h->net.hot_words, h->net.S, h->W, nb).total > budget) nb -= 32;
+  return nb;
+}
+
+template <int W>
+static int configure_step(cyg_env_s* h) {
+  SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, W, h->NB);
+  h->smem_bytes = sp.total;
+  if (sp.total > 227 * 1024) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
+  CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
+  return CYG_OK;
+}
+
+extern "C" {
+
+int cyg_version(void) { return CYG_ABI_VERSION; }
+const char* cyg_last_error(void) { return g_last_error.c_str(); }
+
+int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_net, int32_t B, int32_t env_id0, int32_t device) {
+  if (!out || !cfg || !host_net || !host_net->row_ptr || !host_net->col || !host_net->dev_static)
+    return fail(CYG_E_INVAL, "null argument");
+  if (B < 1) return fail(CYG_E_INVAL, "B must be >= 1");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(CYG_E_INVAL, "bad CUDA device ordinal");
+  cyg_env_s* h = new (std::nothrow) cyg_env_s();
+  if (!h) return fail(CYG_E_NOMEM, "out of host memory");
+  std::string err = build_tables(*cfg, *host_net, h->blob);
+  if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
+  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0;
+  h->W = h->blob.net.W;
+  DeviceGuard g(device);
+  if (!g.ok) { delete h; return fail(CYG_E_CUDA, "cudaSetDevice failed"); }
+  size_t bytes = h->blob.words.size() * 4;
+  cudaError_t e = cudaMalloc((void**)&h->d_blob, bytes);
+  if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(tables)"); }
+  e = cudaMemcpy(h->d_blob, h->blob.words.data(), bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(h->d_blob); delete h; return cuda_fail(e, "cudaMemcpy(tables)"); }
+  relocate(h->blob, h->d_blob, h->net);
+  const char* nb_env = getenv("CYG_BLOCK_ENVS");
+  h->NB = pick_block_envs(h, nb_env ? atoi(nb_env) : 0);
+  if (h->NB < 1 || h->NB > 256) { cudaFree(h->d_blob); delete h; return fail(CYG_E_INVAL, "CYG_BLOCK_ENVS must be in 1..256"); }
+  int rc = CYG_OK;
+  DISPATCH_W(h->W, rc = configure_step<KW>(h));
+  if (rc != CYG_OK) { cudaFree(h->d_blob); delete h; return rc; }
+  *out = h;
+  return CYG_OK;
+}
+
+int cyg_destroy(cyg_handle h) {
+  if (!h) return CYG_OK;
+  DeviceGuard g(h->device);
+  cudaFree(h->d_blob);
+  delete h;
+  return CYG_OK;
+}
+
+int cyg_set_base_line(cyg_handle h, int32_t base_line) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  h->net.cfg.base_line = base_line;
+  return CYG_OK;
+}
+
+int cyg_internal_words(cyg_handle h, int64_t* words_per_env) {
+  if (!h || !words_per_env) return fail(CYG_E_INVAL, "null argument");
+  *words_per_env = (int64_t)h->net.S + h->net.M;
+  return CYG_OK;
+}
+
+int cyg_bind(cyg_handle h, uint32_t* internal_state) {
+  if (!h || !internal_state) return fail(CYG_E_INVAL, "null argument");
+  if (((uintptr_t)internal_state) & 15) return fail(CYG_E_INVAL, "internal state must be 16-byte aligned");
+  h->state = internal_state;
+  return CYG_OK;
+}
+
+static uint32_t* ckpt_of(cyg_handle h) { return h->state + (size_t)h->B * h->net.S; }
+
+int cyg_import_state(cyg_handle h, const cyg_state* c, void* stream) {
+  if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  DeviceGuard g(h->device);
+  ConvParams p = {h->net, h->state, ckpt_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
+  DISPATCH_W(h->W, (cyg_import_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_export_state(cyg_handle h, const cyg_state* c, void* stream) {
+  if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  DeviceGuard g(h->device);
+  ConvParams p = {h->net, h->state, ckpt_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
+  DISPATCH_W(h->W, (cyg_export_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_step_out* out, void* stream) {
+  if (!h || !a || !out || !a->hdr || !a->mask || !out->raw_reward || !out->shaped_reward || !out->done)
+    return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  const bool grouped = (step_flags & CYG_STEP_GROUPED) != 0;
+  if (a->n_groups < 1 || (!grouped && a->n_groups != 1)) return fail(CYG_E_INVAL, "n_groups must be 1 unless CYG_STEP_GROUPED");
+  if (a->order && a->order_stride < 1) return fail(CYG_E_INVAL, "order_stride must be >= 1 with an order array");
+  if (out->obs && (out->obs_mode < 1 || out->obs_mode > 3)) return fail(CYG_E_INVAL, "obs_mode must be 1..3 when obs is given");
+  if (((uintptr_t)a->hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
+  DeviceGuard g(h->device);
+  StepParams p;
+  p.net = h->net;
+  p.recs = h->state; p.ckpt = ckpt_of(h);
+  p.hdr = a->hdr; p.mask = a->mask; p.order = a->order;
+  p.raw = out->raw_reward; p.shaped = out->shaped_reward; p.done = out->done;
+  p.pre_masks = out->pre_masks; p.obs = out->obs;
+  p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
+  p.obs_mode = out->obs ? out->obs_mode : 0;
+  p.flags = step_flags;
+  int blocks = (h->B + h->NB - 1) / h->NB;
+  DISPATCH_W(h->W, (cyg_step_kernel<KW><<<blocks, h->NB, h->smem_bytes, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  DeviceGuard g(h->device);
+  SimpleParams p = {h->net, h->state, env_mask, nullptr, nullptr, h->B, h->env_id0, 0};
+  int threads = 128, blocks = (h->B + threads - 1) / threads;
+  DISPATCH_W(h->W, (cyg_randomize_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream) {
+  if (!h || !hdr || !mask) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  if (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER) return fail(CYG_E_INVAL, "mode must be 0 or 1");
+  DeviceGuard g(h->device);
+  SimpleParams p = {h->net, h->state, nullptr, hdr, mask, h->B, h->env_id0, mode};
+  int threads = 128, blocks = (h->B + threads - 1) / threads;
+  DISPATCH_W(h->W, (cyg_sample_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream) {
+  if (!h || !obs) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  if (obs_mode < 1 || obs_mode > 3) return fail(CYG_E_INVAL, "obs_mode must be 1..3");
+  DeviceGuard g(h->device);
+  ObsParams p = {h->net, h->state, obs, h->B, obs_mode};
+  int threads = 256;
+  size_t total = (size_t)h->B * (obs_mode == 2 ? 4 * h->net.M + h->net.cfg.X : 6 * h->net.M);
+  int blocks = (int)((total + threads - 1) / threads);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  DISPATCH_W(h->W, (cyg_observe_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int64_t cyg_launch_count(cyg_handle h) { return h ? h->launches : 0; }
+
+} /* extern "C" */

@@ -1,0 +1,252 @@
+"""VectorCyberDefenseEnv: B independent CyGym envs stepped by one fused CUDA launch.
+
+The batched counterpart of Volt_Typhoon_CyberDefenseEnv (volt_typhoon_env.py:30): same
+transition, same reset()/step() vocabulary, tensors instead of Python objects.  torch provides
+device memory and streams only; every state transition is a kernel of libcygym_b200.so reached
+through the C-ABI of include/cygym_b200.h.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as K
+from .network import Network
+
+
+class ActionBatch:
+    """One action per env: (action_type, exploit_indices, device_indices, app_index)
+    (volt_typhoon_env.py:876) packed as hdr[B,4] + device mask[B,W] (+ optional explicit order)."""
+
+    def __init__(self, hdr, mask, order=None):
+        self.hdr, self.mask, self.order = hdr, mask, order
+
+    @staticmethod
+    def pack(actions, mode, M, order_form=False):
+        """Host-side packing of a list of reference-style action tuples (or None) -> numpy arrays."""
+        W = (M + 31) // 32
+        B = len(actions)
+        hdr = np.zeros((B, 4), np.uint32)
+        mask = np.zeros((B, W), np.uint32)
+        order = np.zeros((B, M), np.uint16) if order_form else None
+        modes = mode if isinstance(mode, (list, tuple, np.ndarray)) else [mode] * B
+        for b, a in enumerate(actions):
+            m = 1 if modes[b] in (1, "attacker") else 0
+            if a is None:
+                hdr[b, 0] = K.ATYPE_NONE | (m << 8)
+                continue
+            atype, ex, devs, app = a
+            ex = [int(x) for x in np.atleast_1d(ex)][:4]
+            devs = [int(d) for d in devs]
+            at = max(-127, min(127, int(atype)))
+            hdr[b, 0] = (at & 0xFF) | (m << 8) | (len(ex) << 16)
+            w1 = 0
+            for i, x in enumerate(ex):
+                w1 |= (max(-128, min(127, x)) & 0xFF) << (8 * i)
+            hdr[b, 1] = w1
+            hdr[b, 2] = len(devs)
+            hdr[b, 3] = np.uint32(int(app) & 0xFFFFFFFF)
+            for d in devs:
+                if not 0 <= d < M:
+                    raise IndexError(f"device index {d} out of range")
+                mask[b, d >> 5] |= np.uint32(1 << (d & 31))
+            if order_form:
+                if len(devs) > M:
+                    raise ValueError("more device indices than device slots")
+                order[b, :len(devs)] = devs
+            elif devs != sorted(set(devs)):
+                raise ValueError("mask form needs an ascending duplicate-free device list; use order_form=True")
+        return hdr, mask, order
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VectorCyberDefenseEnv:
+    def __init__(self, network: Network, num_envs, device="cuda:0", seed=0, env_id0=0, base_line="Nash", xcap=16,
+                 stream=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("VectorCyberDefenseEnv needs a CUDA device (no CPU fallback)")
+        self.L = K.lib()
+        self.net = network
+        self.B = int(num_envs)
+        self.M, self.W, self.E, self.EW, self.X = network.M, network.W, network.E, network.EW, network.X
+        self.device = torch.device(device)
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.xcap = max(int(xcap), len(network.template.get("extra", ())))
+        self.env_id0 = int(env_id0)
+        self.base_line = base_line
+        self.cfg = K.make_config(network.cfg, network.E, seed=seed, xcap=self.xcap, base_line=base_line)
+        hn = K.CygNetwork(network.row_ptr.ctypes.data, network.col.ctypes.data, network.mult.ctypes.data,
+                          network.dev_static.ctypes.data, network.os_val.ctypes.data, network.ver_val.ctypes.data)
+        self.h = C.c_void_p()
+        K.check(self.L.cyg_create(C.byref(self.h), C.byref(self.cfg), C.byref(hn), self.B, self.env_id0, self.dev_index))
+        words = C.c_int64()
+        K.check(self.L.cyg_internal_words(self.h, C.byref(words)))
+        self.S = int(words.value) - self.M
+        i32 = dict(dtype=torch.int32, device=self.device)
+        self._state = torch.zeros(self.B * int(words.value), **i32)
+        K.check(self.L.cyg_bind(self.h, _ptr(self._state)))
+        self.records = self._state[: self.B * self.S].view(self.B, self.S)
+        self.scalars = self.records[:, : K.NSCAL]  # live view of the 16 CYG_S_* scalars of every env
+        self.raw = torch.zeros(self.B, dtype=torch.float32, device=self.device)
+        self.shaped = torch.zeros(self.B, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(self.B, **i32)
+        self._stream = stream
+        self._obs = {}
+        self._pre = None
+        self.reset()
+
+    # ---- plumbing ----
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.cyg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _s(self):
+        s = self._stream if self._stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    @property
+    def launch_count(self):
+        return int(self.L.cyg_launch_count(self.h))
+
+    def set_base_line(self, name):
+        self.base_line = name
+        K.check(self.L.cyg_set_base_line(self.h, K.BASE_LINES.get(name, 4)))
+
+    def _canon_alloc(self):
+        u = dict(dtype=torch.int32, device=self.device)
+        return dict(dev=torch.zeros(self.B, self.M, **u), ckpt=torch.zeros(self.B, self.M, **u),
+                    blocked=torch.zeros(self.B, self.EW, **u), extra=torch.zeros(self.B, max(1, self.xcap), **u),
+                    scal=torch.zeros(self.B, K.NSCAL, **u))
+
+    def _cstate(self, c):
+        return K.CygState(*[c[k].data_ptr() for k in ("dev", "ckpt", "blocked", "extra", "scal")])
+
+    # ---- state in / out (reset(from_init=True) / snapshot load, volt:1904-1925) ----
+    def import_state(self, canon):
+        """canon: dict of [B,*] int32/uint32 tensors or numpy arrays in the canonical layout."""
+        c = {}
+        for k, width in (("dev", self.M), ("ckpt", self.M), ("blocked", self.EW), ("extra", max(1, self.xcap)), ("scal", K.NSCAL)):
+            a = canon[k]
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a).view(np.int32).reshape(self.B, -1))
+            a = a.to(self.device, torch.int32)
+            if a.shape[1] < width:
+                a = torch.nn.functional.pad(a, (0, width - a.shape[1]))
+            c[k] = a.contiguous()
+        cs = self._cstate(c)
+        K.check(self.L.cyg_import_state(self.h, C.byref(cs), self._s()))
+        self._keep = c
+        return self
+
+    def export_state(self):
+        c = self._canon_alloc()
+        cs = self._cstate(c)
+        K.check(self.L.cyg_export_state(self.h, C.byref(cs), self._s()))
+        return c
+
+    def reset(self, env_epoch0=0):
+        """Every env <- the network's template state (what reset(from_init=True) reloads)."""
+        t = self.net.template
+        canon = {}
+        for k, width in (("dev", self.M), ("ckpt", self.M), ("blocked", self.EW), ("extra", max(1, self.xcap)), ("scal", K.NSCAL)):
+            row = np.zeros(width, np.uint32)
+            src = np.asarray(t[k], np.uint32)
+            row[: len(src)] = src
+            canon[k] = np.broadcast_to(row, (self.B, width)).copy()
+        return self.import_state(canon)
+
+    # ---- the hot path ----
+    def step(self, actions: ActionBatch, flags=0, obs_mode=0, want_pre=False):
+        """One step() of every env (volt_typhoon_env.py:818).  Returns (raw, shaped, done) device tensors
+        that are overwritten by the next call."""
+        return self._step([actions], flags, obs_mode, want_pre)
+
+    def step_grouped(self, groups, obs_mode=0, want_pre=False):
+        """step_grouped() of every env (volt_typhoon_env.py:694): groups = list of ActionBatch."""
+        return self._step(list(groups), K.STEP_GROUPED, obs_mode, want_pre)
+
+    def _step(self, groups, flags, obs_mode, want_pre):
+        G = len(groups)
+        if G == 1:
+            hdr, mask, order = groups[0].hdr, groups[0].mask, groups[0].order
+        else:
+            hdr = torch.stack([g.hdr for g in groups]).contiguous()
+            mask = torch.stack([g.mask for g in groups]).contiguous()
+            order = torch.stack([g.order for g in groups]).contiguous() if groups[0].order is not None else None
+        a = K.CygActions(hdr.data_ptr(), mask.data_ptr(), order.data_ptr() if order is not None else None,
+                         order.shape[-1] if order is not None else 0, G)
+        obs = None
+        if obs_mode:
+            obs = self._obs_buf(obs_mode)
+        pre = None
+        if want_pre:
+            if self._pre is None:
+                self._pre = torch.zeros(self.B, 3, self.W, dtype=torch.int32, device=self.device)
+            pre = self._pre
+        o = K.CygStepOut(self.raw.data_ptr(), self.shaped.data_ptr(), self.done.data_ptr(),
+                         pre.data_ptr() if pre is not None else None, obs.data_ptr() if obs is not None else None, obs_mode)
+        K.check(self.L.cyg_step(self.h, C.byref(a), flags, C.byref(o), self._s()))
+        self._hold = (hdr, mask, order)
+        return self.raw, self.shaped, self.done
+
+    def _obs_buf(self, mode):
+        if mode not in self._obs:
+            dim = 4 * self.M + self.X if mode == 2 else 6 * self.M
+            self._obs[mode] = torch.zeros(self.B, dim, dtype=torch.float32, device=self.device)
+        return self._obs[mode]
+
+    def last_obs(self, mode):
+        return self._obs[mode]
+
+    def pre_masks(self):
+        return self._pre
+
+    def observe(self, mode):
+        """1: _get_defender_state, 2: _get_attacker_state, 3: _get_state (CyberDefenseEnv.py:241/194/146)."""
+        obs = self._obs_buf(mode)
+        K.check(self.L.cyg_observe(self.h, mode, _ptr(obs), self._s()))
+        return obs
+
+    def randomize_compromise_and_ownership(self, env_mask=None):
+        if env_mask is not None:
+            env_mask = env_mask.to(self.device, torch.uint8).contiguous()
+            self._hold_mask = env_mask
+        K.check(self.L.cyg_randomize(self.h, _ptr(env_mask), self._s()))
+
+    def sample_actions(self, mode, out: ActionBatch = None):
+        """sample_action() of every env (CyberDefenseEnv.py:555-578) as an ActionBatch on the device."""
+        m = 1 if mode in (1, "attacker") else 0
+        if out is None:
+            out = ActionBatch(torch.zeros(self.B, 4, dtype=torch.int32, device=self.device),
+                              torch.zeros(self.B, self.W, dtype=torch.int32, device=self.device))
+        K.check(self.L.cyg_sample_actions(self.h, m, _ptr(out.hdr), _ptr(out.mask), self._s()))
+        return out
+
+    def to_device(self, hdr, mask, order=None):
+        f = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a).view(dt)).to(self.device)
+        return ActionBatch(f(hdr, np.int32), f(mask, np.int32), f(order, np.int16))
+
+    # ---- counters (the `info` dict of volt:1272-1285, per env) ----
+    def info(self):
+        s = self.scalars
+        f = lambda i: s[:, i].contiguous().view(torch.float32)
+        return {
+            "step_count": s[:, K.S_STEP], "revert_count": s[:, K.S_REVERT], "checkpoint_count": s[:, K.S_CKPT],
+            "defensive_cost": f(K.S_DEFCOST), "clearning_cost": f(K.S_CLEANCOST), "Scan_count": s[:, K.S_SCAN],
+            "work_done": s[:, K.S_WORK], "Compromised_devices": s[:, K.S_COMPCNT], "Edges Blocked": s[:, K.S_EBLK],
+            "Edges Added": s[:, K.S_EADD], "defender_step": s[:, K.S_DEF_STEP], "attacker_step": s[:, K.S_ATT_STEP],
+        }
+
+    def error_flags(self):
+        """Sticky per-env CYG_FL_ERR_* bits (0 everywhere on a healthy run)."""
+        return self.scalars[:, K.S_FLAGS] & K.FL_ERR_MASK

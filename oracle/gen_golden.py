@@ -1,0 +1,48 @@
+"""Regenerate tests/golden/*.npz from the live reference (build container only).
+
+    python -m oracle.gen_golden
+
+Each file is one trajectory of the UNMODIFIED reference under replayed draws
+(oracle/ref_harness.py), recorded by oracle/trajectory.py:record().  The cases
+follow BASELINE.json's configs: C1 = init_experiments.py defaults (numOfDevice=10,
+Max_network_size=20, seed 1), then the ~50- and 100-device shapes.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+CASES = {
+    # name: record() kwargs
+    "c1_m20_plain": dict(numOfDevice=10, M=20, seed=1, T=260),
+    "c1_m20_order": dict(numOfDevice=10, M=20, seed=2, T=200, order_form=True),
+    "c1_m20_baselines": dict(numOfDevice=10, M=20, seed=3, T=160, baseline_every=17),
+    "c2_m50_plain": dict(numOfDevice=40, M=50, seed=4, T=160),
+    "c2_m60_padd": dict(numOfDevice=50, M=60, seed=5, T=140, xcap=128, env_attrs=dict(p_add=0.5, p_attacker=0.3, lambda_events=1.5)),
+    "c3_m100_plain": dict(numOfDevice=90, M=100, seed=6, T=130),
+    "c3_m100_scales": dict(numOfDevice=90, M=100, seed=7, T=100, order_form=True,
+                           env_attrs=dict(comp_scale=30, work_scale=2.0, def_scale=0.5)),
+    "m33_odd": dict(numOfDevice=25, M=33, seed=8, T=150, randomize_every=11),
+}
+
+
+def main(names=None):
+    warnings.filterwarnings("ignore")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out_dir = os.path.join(os.path.dirname(here), "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    from . import trajectory as TR
+    for name, kw in CASES.items():
+        if names and name not in names:
+            continue
+        g = TR.record(**kw)
+        # self-check against the C restatement before writing
+        n = TR.replay(g, TR.OracleImpl(g), label=f"oracle[{name}]")
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **g)
+        print(f"{name}: {n} ops, {os.path.getsize(path)} bytes", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

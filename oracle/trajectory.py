@@ -1,0 +1,245 @@
+"""Golden trajectories: record from the live reference, replay against a checker (TEST INFRASTRUCTURE).
+
+record()  -- needs /root/reference (build container only).  Drives the unmodified
+             reference with replayed draws and stores, after every operation, the
+             canonical state it is in.
+replay()  -- needs nothing but numpy: feeds the recorded operations to any
+             implementation exposing step/randomize/set_base_line on the canonical
+             layout (the C oracle on CPU, the CUDA library on GPU) and compares.
+"""
+import json
+
+import numpy as np
+
+OP_STEP, OP_GROUPED, OP_RANDOMIZE, OP_BASELINE = 0, 1, 2, 3
+BASELINES = ["Nash", "No Defense", "Preset", "No Attack"]
+G_MAX = 4
+
+
+def _policy_ops(rng, T, M, n_logs_fn, grouped_every=9, randomize_every=41, baseline_every=0, none_every=13,
+                order_form=False):
+    """Yield abstract ops; concrete actions are drawn when executed (they depend on live state)."""
+    for t in range(T):
+        if randomize_every and t % randomize_every == randomize_every - 1:
+            yield ("randomize",)
+        if baseline_every and t % baseline_every == baseline_every - 1:
+            yield ("baseline", BASELINES[int(rng.integers(len(BASELINES)))])
+        mode = "defender" if t % 2 == 0 else "attacker"
+        if grouped_every and t % grouped_every == grouped_every - 1:
+            yield ("grouped", mode)
+        elif none_every and t % none_every == none_every - 1:
+            yield ("none", mode)
+        else:
+            yield ("step", mode)
+
+
+def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, grouped_every=9,
+           randomize_every=41, baseline_every=0, none_every=13, env_attrs=None, env_id=0):
+    from . import cyg_oracle as O
+    from . import ref_harness as H
+
+    env = H.build_env(numOfDevice=numOfDevice, Max_network_size=M, seed=seed, **(env_attrs or {}))
+    netw = H.extract_network(env)
+    ctx = H.context()
+    ctx.seed, ctx.env_id, ctx.epoch = draw_seed, env_id, 0
+    W = (M + 31) // 32
+    E = len(netw["col"])
+    EW = max(1, (E + 31) // 32)
+    rng = np.random.default_rng(seed * 7919 + 17)
+    init = H.extract_state(env, netw, ctx.epoch)
+    rec = dict(kind=[], mode=[], n_groups=[], hdr=[], mask=[], order=[], baseline=[],
+               dev=[], ckpt=[], blocked=[], scal=[], extra=[], n_extra=[], raw=[], shaped=[], done=[], exec_atype=[],
+               pre=[], obs_def=[], obs_att=[])
+
+    def snap(raw=0.0, shaped=0.0, done=False, ex=0, state=None):
+        st = H.extract_state(env, netw, ctx.epoch)
+        rec["dev"].append(st["dev"]); rec["ckpt"].append(st["ckpt"])
+        b = np.zeros(EW, np.uint32); b[:len(st["blocked"])] = st["blocked"]
+        rec["blocked"].append(b); rec["scal"].append(st["scal"])
+        x = np.zeros(xcap, np.uint32); x[:len(st["extra"])] = st["extra"]
+        rec["extra"].append(x); rec["n_extra"].append(len(st["extra"]))
+        rec["raw"].append(raw); rec["shaped"].append(shaped); rec["done"].append(int(done)); rec["exec_atype"].append(ex)
+        pre = np.zeros((3, W), np.uint32)
+        if state is not None:
+            s6 = np.asarray(state).reshape(M, 6)
+            for row, col in enumerate((2, 4, 5)):
+                for i in range(M):
+                    if s6[i, col] > 0.5:
+                        pre[row, i >> 5] |= np.uint32(1 << (i & 31))
+        rec["pre"].append(pre)
+        rec["obs_def"].append(np.asarray(env._get_defender_state(), np.float32))
+        rec["obs_att"].append(np.asarray(env._get_attacker_state(), np.float32))
+
+    def push_op(kind, mode, groups, baseline=0):
+        hdr = np.zeros((G_MAX, 4), np.uint32); mask = np.zeros((G_MAX, W), np.uint32); order = np.zeros((G_MAX, M), np.uint16)
+        for g, a in enumerate(groups):
+            h, m, o = O.pack_action(a, mode, M, order_form)
+            hdr[g], mask[g] = h, m
+            if o is not None:
+                order[g] = o
+        rec["kind"].append(kind); rec["mode"].append(1 if mode == "attacker" else 0); rec["n_groups"].append(len(groups))
+        rec["hdr"].append(hdr); rec["mask"].append(mask); rec["order"].append(order); rec["baseline"].append(baseline)
+
+    def fix(a, mode):
+        at, ex, devs, app = a
+        if mode == "defender" and at == 10 and len(env.simulator.logger.logs) > 0:
+            at = 8  # trained-IsolationForest branch is out of the kernel's scope
+        if not order_form:
+            devs = sorted(devs)
+        return (at, ex, devs, app)
+
+    for op in _policy_ops(rng, T, M, None, grouped_every, randomize_every, baseline_every, none_every, order_form):
+        if op[0] == "randomize":
+            H.ref_randomize(env)
+            push_op(OP_RANDOMIZE, "defender", [])
+            snap()
+        elif op[0] == "baseline":
+            env.base_line = op[1]
+            push_op(OP_BASELINE, "defender", [], baseline=BASELINES.index(op[1]))
+            snap()
+        elif op[0] == "none":
+            raw, shaped, done, info, state = H.ref_step(env, op[1], None)
+            push_op(OP_STEP, op[1], [None])
+            snap(raw, shaped, done, info["executed_atype"], state)
+        elif op[0] == "step":
+            a = fix(H.ref_sample_action(env, op[1]), op[1])
+            push_op_args = (OP_STEP, op[1], [a])
+            # sample_action consumed an epoch on the reference side: record it as an explicit epoch bump
+            raw, shaped, done, info, state = H.ref_step(env, op[1], a)
+            push_op(*push_op_args)
+            snap(raw, shaped, done, info["executed_atype"], state)
+        else:  # grouped
+            mode = op[1]
+            ng = int(rng.integers(1, G_MAX + 1))
+            groups = []
+            for _ in range(ng):
+                a = fix(H.ref_sample_action(env, mode), mode)
+                at = a[0]
+                if mode == "defender":
+                    at = int(rng.choice([0, 1, 1, 2, 3, 8, 10, 11, 1, 5]))
+                    if at == 10 and len(env.simulator.logger.logs) > 0:
+                        at = 1
+                groups.append((at, a[1], a[2], a[3]))
+            env.mode = mode
+            with ctx.window():
+                state, raw, shaped, done, info, _ = env.step(list(groups))
+            push_op(OP_GROUPED, mode, groups)
+            snap(float(raw), float(shaped), bool(done), -1, state)
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out["n_sample_epochs"] = np.asarray(0)
+    for k in ("row_ptr", "col", "mult", "dev_static", "os_val", "ver_val"):
+        out["net_" + k] = netw[k]
+    for k in ("dev", "ckpt", "blocked", "extra", "scal"):
+        out["init_" + k] = init[k]
+    meta = dict(cfg=netw["cfg"], draw_seed=draw_seed, env_id=env_id, xcap=xcap, order_form=bool(order_form),
+                numOfDevice=numOfDevice, M=M, seed=seed, T=T)
+    out["meta"] = np.asarray(json.dumps(meta))
+    return out
+
+
+class Mismatch(AssertionError):
+    pass
+
+
+def replay(g, impl, check_obs=True, rtol=1e-5, label="impl"):
+    """Feed golden trajectory `g` (dict / NpzFile) to `impl` and compare after every op.
+
+    impl protocol (canonical numpy arrays in, canonical out):
+      impl.load(init: dict(dev, ckpt, blocked, extra, scal))        # B = 1
+      impl.step(hdr[G,1,4], mask[G,1,W], order[G,1,M] | None, flags) -> dict(raw, shaped, done[, exec_atype, pre_masks])
+      impl.randomize();  impl.set_base_line(name);  impl.bump_epoch(n)
+      impl.state() -> dict(dev[M], ckpt[M], blocked[EW], extra[xcap], scal[16])
+      impl.observe(mode) -> float32[dim]
+    """
+    meta = json.loads(str(g["meta"]))
+    M = meta["M"]
+    order_form = meta["order_form"]
+    impl.load({k: np.array(g["init_" + k]) for k in ("dev", "ckpt", "blocked", "extra", "scal")})
+    T = len(g["kind"])
+    for t in range(T):
+        kind = int(g["kind"][t])
+        if kind == OP_RANDOMIZE:
+            impl.randomize()
+        elif kind == OP_BASELINE:
+            impl.set_base_line(BASELINES[int(g["baseline"][t])])
+        else:
+            G = int(g["n_groups"][t])
+            hdr = np.array(g["hdr"][t][:G])[:, None, :]
+            mask = np.array(g["mask"][t][:G])[:, None, :]
+            order = np.array(g["order"][t][:G])[:, None, :] if order_form else None
+            # the reference drew each (non-None) action with sample_action(): one epoch per group
+            n_sampled = sum(1 for gi in range(G) if (int(hdr[gi, 0, 0]) & 0xFF) != 0x80) if True else 0
+            impl.bump_epoch(n_sampled)
+            out = impl.step(hdr, mask, order, 1 if kind == OP_GROUPED else 0)
+            raw, shaped = float(g["raw"][t]), float(g["shaped"][t])
+            tol = rtol * max(1.0, abs(raw))
+            if abs(float(out["raw"][0]) - raw) > tol or abs(float(out["shaped"][0]) - shaped) > tol:
+                raise Mismatch(f"{label}: op {t}: reward {out['raw'][0]}/{out['shaped'][0]} != {raw}/{shaped}")
+            if int(out["done"][0]) != int(g["done"][t]):
+                raise Mismatch(f"{label}: op {t}: done")
+            if kind == OP_STEP and "exec_atype" in out and int(out["exec_atype"][0]) != int(g["exec_atype"][t]):
+                raise Mismatch(f"{label}: op {t}: executed_atype {out['exec_atype'][0]} != {g['exec_atype'][t]}")
+            if "pre_masks" in out and out["pre_masks"] is not None:
+                if not np.array_equal(np.asarray(out["pre_masks"][0]), g["pre"][t]):
+                    raise Mismatch(f"{label}: op {t}: pre-evolve state masks differ")
+        st = impl.state()
+        for k in ("dev", "ckpt", "blocked"):
+            if not np.array_equal(np.asarray(st[k]), g[k][t]):
+                bad = np.nonzero(np.asarray(st[k]) != g[k][t])[0]
+                raise Mismatch(f"{label}: op {t} kind {kind}: {k} differs at {bad[:8]}: "
+                               f"{[hex(int(x)) for x in np.asarray(st[k])[bad[:8]]]} != {[hex(int(x)) for x in g[k][t][bad[:8]]]}")
+        a, r = np.array(st["scal"], np.uint32), np.array(g["scal"][t], np.uint32)
+        fa, fr = a[9:11].view(np.float32), r[9:11].view(np.float32)
+        if not np.allclose(fa, fr, rtol=rtol, atol=1e-6):
+            raise Mismatch(f"{label}: op {t}: cost counters {fa} != {fr}")
+        a[9:11] = 0; r[9:11] = 0
+        if not np.array_equal(a, r):
+            raise Mismatch(f"{label}: op {t} kind {kind}: scalars {a} != {r}")
+        nx = int(g["n_extra"][t])
+        xa = sorted(int(x) & 0x1FFFFFF for x in np.asarray(st["extra"])[:nx])
+        xr = sorted(int(x) for x in g["extra"][t][:nx])
+        if xa != xr:
+            raise Mismatch(f"{label}: op {t}: extra edges {xa} != {xr}")
+        if check_obs:
+            for mode, key in ((1, "obs_def"), (2, "obs_att")):
+                o = np.asarray(impl.observe(mode))
+                if not np.array_equal(o, g[key][t]):
+                    raise Mismatch(f"{label}: op {t}: observation mode {mode} differs")
+    return T
+
+
+class OracleImpl:
+    """The replay() protocol on top of the C oracle (B = 1)."""
+
+    def __init__(self, g, base_line="Nash"):
+        from . import cyg_oracle as O
+        meta = json.loads(str(g["meta"]))
+        self.meta = meta
+        netw = {k: np.array(g["net_" + k]) for k in ("row_ptr", "col", "mult", "dev_static", "os_val", "ver_val")}
+        self.cfg = O.make_config(meta["cfg"], len(netw["col"]), seed=meta["draw_seed"], xcap=meta["xcap"], base_line=base_line)
+        self.orc = O.Oracle(netw, self.cfg, env_id0=meta["env_id"])
+        self.st = self.orc.new_state(1)
+
+    def load(self, init):
+        self.st.dev[0] = init["dev"]; self.st.ckpt[0] = init["ckpt"]
+        self.st.blocked[0] = 0; self.st.blocked[0, :len(init["blocked"])] = init["blocked"]
+        self.st.extra[0] = 0; self.st.extra[0, :len(init["extra"])] = init["extra"]
+        self.st.scal[0] = init["scal"]
+
+    def bump_epoch(self, n):
+        self.st.scal[0, 1] += np.uint32(n)
+
+    def step(self, hdr, mask, order, flags):
+        return self.orc.step(self.st, hdr, mask, order, flags=flags, want_pre=True)
+
+    def randomize(self):
+        self.orc.randomize(self.st)
+
+    def set_base_line(self, name):
+        self.orc.set_base_line(name)
+
+    def state(self):
+        return dict(dev=self.st.dev[0], ckpt=self.st.ckpt[0], blocked=self.st.blocked[0], extra=self.st.extra[0], scal=self.st.scal[0])
+
+    def observe(self, mode):
+        return self.orc.observe(self.st, mode)[0]

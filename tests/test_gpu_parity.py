@@ -1,0 +1,208 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI (run on the B200 box: -m gpu).
+
+ * golden trajectories recorded from the unmodified reference, replayed on the GPU (B = 1);
+ * batched random rollouts at the BASELINE.json shapes vs the C oracle on the same seeded inputs:
+   integer / boolean state bit-exact, rewards within 1e-5 relative (fp32 outputs vs float64);
+ * at the full 65 536 x 100 size: size-independent properties (shard invariance, determinism,
+   export/import round trip) plus an oracle check of a contiguous slice of the big batch.
+"""
+import numpy as np
+import pytest
+
+from oracle import trajectory as TR
+from tests.common import (GOLDEN, GOLDEN_IDS, CudaImpl, compare_rewards, compare_states, load_golden, oracle_for,
+                          oracle_state_from_template, sanitize_actions)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5  # north_star: rewards / payoffs within 1e-5 relative
+
+
+def _np(c):
+    return {k: v.cpu().numpy().view(np.uint32) for k, v in c.items()}
+
+
+def test_library_loaded_is_the_cuda_one():
+    import torch
+    from cygym_b200 import _capi
+    assert torch.cuda.is_available()
+    assert _capi.lib().cyg_version() == 1
+    assert "sm_100" in " ".join(torch.cuda.get_arch_list()) or torch.cuda.get_device_capability()[0] >= 10
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=GOLDEN_IDS)
+def test_cuda_replays_golden(path):
+    g = load_golden(path)
+    n = TR.replay(g, CudaImpl(g), rtol=RTOL, label="cuda")
+    assert n == len(g["kind"])
+
+
+def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, block_envs=None, **kw):
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv, ActionBatch
+    net = synthetic_network(M, n_subnets=subnets, seed=seed, **kw)
+    xcap = 64
+    orc, cfg = oracle_for(net, seed=1234, xcap=xcap, env_id0=env_id0)
+    env = VectorCyberDefenseEnv(net, B, seed=1234, env_id0=env_id0, xcap=xcap)
+    so = oracle_state_from_template(orc, net, B)
+    for t in range(T):
+        mode = t & 1
+        if t % 29 == 28:
+            orc.randomize(so)
+            env.randomize_compromise_and_ownership()
+        ho, mo = orc.sample_actions(so, mode)
+        ab = env.sample_actions(mode)
+        torch.cuda.synchronize()
+        assert np.array_equal(ab.hdr.cpu().numpy().view(np.uint32), ho), f"sample_action hdr t={t}"
+        assert np.array_equal(ab.mask.cpu().numpy().view(np.uint32), mo), f"sample_action mask t={t}"
+        ho = sanitize_actions(ho, so.scal[:, 6], mode)
+        if t % 11 == 10:
+            ho[::3, 0] = 0x80 | (mode << 8)
+        oo = orc.step(so, ho, mo, n_threads=8)
+        om = 1 + (t % 3) if t % obs_every == 0 else 0
+        raw, shaped, done = env.step(env.to_device(ho, mo), obs_mode=om)
+        torch.cuda.synchronize()
+        og = dict(raw=raw.cpu().numpy(), shaped=shaped.cpu().numpy(), done=done.cpu().numpy())
+        compare_rewards(og, oo, f"t={t}", RTOL)
+        if t % 5 == 0 or t == T - 1:
+            compare_states(_np(env.export_state()), dict(dev=so.dev, ckpt=so.ckpt, blocked=so.blocked, extra=so.extra, scal=so.scal), f"t={t}", RTOL)
+        if om:
+            assert np.array_equal(env.last_obs(om).cpu().numpy(), orc.observe(so, om)), f"fused obs mode {om} t={t}"
+            assert np.array_equal(env.observe(om).cpu().numpy(), orc.observe(so, om)), f"observe mode {om} t={t}"
+    assert int(env.error_flags().max().item()) == 0
+    assert env.launch_count > T
+
+
+def test_c1_default_network_rollout():
+    _rollout_vs_oracle(20, 1, 64, 300, num_of_device=10)
+
+
+def test_c2_4096_envs_50_devices():
+    _rollout_vs_oracle(50, 3, 4096, 60)
+
+
+def test_c3_shape_8192_envs_100_devices():
+    _rollout_vs_oracle(100, 8, 8192, 50)
+
+
+def test_ragged_batch_and_odd_sizes():
+    _rollout_vs_oracle(33, 2, 1001, 40)      # B not a multiple of the CTA block; M not a multiple of 32
+    _rollout_vs_oracle(128, 4, 257, 30)      # maximum M of the bit-matrix kernels
+    _rollout_vs_oracle(1, 1, 5, 20, num_of_device=1)
+
+
+def test_evolving_topology_with_attacker_arrivals():
+    _rollout_vs_oracle(60, 3, 512, 80, p_add=0.5, p_attacker=0.4, lambda_events=1.5)
+
+
+def test_zero_day_remap():
+    _rollout_vs_oracle(40, 2, 256, 60, zero_day=1, zero_day_mask=0b10)
+
+
+def test_grouped_and_order_form_steps():
+    """step_grouped (volt:694-779) and explicit device_indices order, vs the oracle."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    rng = np.random.default_rng(0)
+    M, B, G = 50, 300, 4
+    net = synthetic_network(M, n_subnets=3, seed=11)
+    orc, cfg = oracle_for(net, seed=77, xcap=32)
+    env = VectorCyberDefenseEnv(net, B, seed=77, xcap=32)
+    so = oracle_state_from_template(orc, net, B)
+    W = net.W
+    for t in range(40):
+        mode = t & 1
+        hdr = np.zeros((G, B, 4), np.uint32); mask = np.zeros((G, B, W), np.uint32); order = np.zeros((G, B, M), np.uint16)
+        for g in range(G):
+            for b in range(B):
+                n = int(rng.integers(0, M))
+                devs = rng.permutation(M)[:n]
+                at = int(rng.choice([0, 1, 1, 2, 3, 8, 11, 1, 5, 7])) if n > 0 else 8
+                if t % 4 == 3:
+                    at = int(rng.integers(0, 14 if mode == 0 else 5))
+                    if at == 10 and so.scal[b, 6] > 0:
+                        at = 8
+                    if at in (11, 12, 13) and n == 0:
+                        at = 8
+                hdr[g, b] = [(at & 0xFF) | (mode << 8) | (1 << 16), int(rng.integers(0, 6)), n, int(rng.integers(0, 9))]
+                order[g, b, :n] = devs
+                for d in devs:
+                    mask[g, b, d >> 5] |= np.uint32(1 << (d & 31))
+        from cygym_b200.vector_env import ActionBatch
+        if t % 4 == 3:   # plain step with an explicit order
+            oo = orc.step(so, hdr[0], mask[0], order[0])
+            raw, shaped, done = env.step(env.to_device(hdr[0], mask[0], order[0]))
+        else:
+            oo = orc.step(so, hdr, mask, order, flags=1)
+            raw, shaped, done = env.step_grouped([env.to_device(hdr[g], mask[g], order[g]) for g in range(G)])
+        torch.cuda.synchronize()
+        compare_rewards(dict(raw=raw.cpu().numpy(), shaped=shaped.cpu().numpy(), done=done.cpu().numpy()), oo, f"t={t}", RTOL)
+        compare_states(_np(env.export_state()), dict(dev=so.dev, ckpt=so.ckpt, blocked=so.blocked, extra=so.extra, scal=so.scal), f"t={t}", RTOL)
+
+
+def test_full_size_properties_65536_x_100():
+    """BASELINE.json C3 at full size: shard invariance + determinism + round trip + oracle slice."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    net = synthetic_network(100, n_subnets=8, seed=0)
+    B, T, xcap = 65536, 24, 16
+    whole = VectorCyberDefenseEnv(net, B, seed=42, xcap=xcap)
+    halves = [VectorCyberDefenseEnv(net, B // 2, seed=42, env_id0=i * (B // 2), xcap=xcap) for i in range(2)]
+    k0, kn = 40000, 768
+    orc, cfg = oracle_for(net, seed=42, xcap=xcap, env_id0=k0)
+    so = oracle_state_from_template(orc, net, kn)
+    for t in range(T):
+        mode = t & 1
+        ab = whole.sample_actions(mode)
+        hs = [h.sample_actions(mode) for h in halves]
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat([x.hdr for x in hs]), ab.hdr) and torch.equal(torch.cat([x.mask for x in hs]), ab.mask)
+        # the trained-detector branch is out of scope: rewrite defender 10 -> 8 on the device
+        if mode == 0:
+            for a, e in [(ab, whole)] + list(zip(hs, halves)):
+                bad = ((a.hdr[:, 0] & 0xFF) == 10) & (e.scalars[:, 6] > 0)
+                a.hdr[:, 0] = torch.where(bad, (a.hdr[:, 0] & ~0xFF) | 8, a.hdr[:, 0])
+        r = [x.clone() for x in whole.step(ab)]
+        rh = [[x.clone() for x in h.step(a)] for h, a in zip(halves, hs)]
+        torch.cuda.synchronize()
+        for i in range(3):
+            assert torch.equal(torch.cat([rh[0][i], rh[1][i]]), r[i]), f"shard invariance, output {i}, t={t}"
+        ho = ab.hdr[k0:k0 + kn].cpu().numpy().view(np.uint32)
+        mo = ab.mask[k0:k0 + kn].cpu().numpy().view(np.uint32)
+        so.scal[:, 1] += 1  # the sample_action epoch
+        oo = orc.step(so, ho, mo, n_threads=8)
+        compare_rewards(dict(raw=r[0][k0:k0 + kn].cpu().numpy(), shaped=r[1][k0:k0 + kn].cpu().numpy(),
+                             done=r[2][k0:k0 + kn].cpu().numpy()), oo, f"slice t={t}", RTOL)
+    cw = _np(whole.export_state())
+    ch = [_np(h.export_state()) for h in halves]
+    for k in cw:
+        assert np.array_equal(np.concatenate([ch[0][k], ch[1][k]]), cw[k]), f"shard invariance of {k}"
+    compare_states({k: v[k0:k0 + kn] for k, v in cw.items()},
+                   dict(dev=so.dev, ckpt=so.ckpt, blocked=so.blocked, extra=so.extra, scal=so.scal), "slice", RTOL)
+    # export -> import -> export is the identity
+    again = VectorCyberDefenseEnv(net, B, seed=42, xcap=xcap)
+    again.import_state(whole.export_state())
+    ca = _np(again.export_state())
+    for k in cw:
+        assert np.array_equal(ca[k], cw[k]), f"round trip of {k}"
+    # conservation: every env advanced exactly T steps; counters are consistent
+    s = cw["scal"]
+    assert (s[:, 0] == T).all() and (s[:, 4] + s[:, 5] == T).all()
+    assert int(whole.error_flags().max().item()) == 0
+
+
+def test_errors_are_loud():
+    import ctypes as C
+    from cygym_b200 import _capi as K, synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    net = synthetic_network(20, n_subnets=1, seed=1)
+    env = VectorCyberDefenseEnv(net, 4)
+    a = K.CygActions(None, None, None, 0, 1)
+    o = K.CygStepOut(None, None, None, None, None, 0)
+    rc = env.L.cyg_step(env.h, C.byref(a), 0, C.byref(o), None)
+    assert rc == K.E_INVAL and b"null" in env.L.cyg_last_error()
+    with pytest.raises(K.CygError):
+        big = synthetic_network(200, n_subnets=4, seed=1)
+        VectorCyberDefenseEnv(big, 4)
