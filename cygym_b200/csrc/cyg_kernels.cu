@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ S
     auto hot = [&](const void* g) { return (const uint32_t*)((const unsigned char*)s_tab + ((const unsigned char*)g - (const unsigned char*)p.net.blob)); };
     n.adj = hot(n.adj); n.m_dc = hot(n.m_dc); n.m_server = hot(n.m_server); n.m_reach = hot(n.m_reach);
     n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_vuln = hot(n.m_vuln);
-    n.mlo = hot(n.mlo); n.mhi = hot(n.mhi);
+    n.mlo = hot(n.mlo); n.mhi = hot(n.mhi); n.adjT = hot(n.adjT); n.mloT = hot(n.mloT); n.mhiT = hot(n.mhiT);
+    n.in_ptr = (const int32_t*)hot(n.in_ptr); n.in_eid = (const uint16_t*)hot(n.in_eid); n.dev_static = hot(n.dev_static);
     n.row_ptr = (const int32_t*)hot(n.row_ptr); n.col = (const uint16_t*)hot(n.col);
     *s_net = n;
   }

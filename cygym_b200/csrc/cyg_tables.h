@@ -72,14 +72,14 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   b.o_mhi = tb_alloc(b, (size_t)M * W);
   b.o_row_ptr = tb_alloc(b, M + 1);
   b.o_col = tb_alloc(b, (E + 1) / 2 + 1);
-  b.hot_words = b.words.size();
-  /* cold section (read through L1/L2 by the few actions that need it) */
   b.o_adjT = tb_alloc(b, (size_t)M * W);
   b.o_mloT = tb_alloc(b, (size_t)M * W);
   b.o_mhiT = tb_alloc(b, (size_t)M * W);
   b.o_in_ptr = tb_alloc(b, M + 1);
   b.o_in_eid = tb_alloc(b, (E + 1) / 2 + 1);
   b.o_static = tb_alloc(b, M);
+  b.hot_words = b.words.size();
+  /* cold section (observation rows only) */
   b.o_os = tb_alloc(b, M);
   b.o_ver = tb_alloc(b, M);
   uint32_t* w = b.words.data();

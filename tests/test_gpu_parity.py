@@ -36,12 +36,11 @@ def test_cuda_replays_golden(path):
     assert n == len(g["kind"])
 
 
-def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, block_envs=None, **kw):
+def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64, **kw):
     import torch
     from cygym_b200 import synthetic_network
     from cygym_b200.vector_env import VectorCyberDefenseEnv, ActionBatch
     net = synthetic_network(M, n_subnets=subnets, seed=seed, **kw)
-    xcap = 64
     orc, cfg = oracle_for(net, seed=1234, xcap=xcap, env_id0=env_id0)
     env = VectorCyberDefenseEnv(net, B, seed=1234, env_id0=env_id0, xcap=xcap)
     so = oracle_state_from_template(orc, net, B)
@@ -92,7 +91,7 @@ def test_ragged_batch_and_odd_sizes():
 
 
 def test_evolving_topology_with_attacker_arrivals():
-    _rollout_vs_oracle(60, 3, 512, 80, p_add=0.5, p_attacker=0.4, lambda_events=1.5)
+    _rollout_vs_oracle(60, 3, 512, 80, xcap=160, p_add=0.5, p_attacker=0.4, lambda_events=1.5)
 
 
 def test_zero_day_remap():
