@@ -7,7 +7,8 @@
  *   [0, 16)                          the 16 scalars of include/cygym_b200.h (CYG_S_*)
  *   [16 + p*W, 16 + (p+1)*W)         bit-plane p, W = ceil(M/32) words, bit d = device d
  *   [off_blocked, off_blocked + EW)  blocked-edge bitset over base CSR edge ids
- *   [off_extra,  off_extra + xcap)   per-env extra (attacker hub-star) edges
+ * (the rarely used per-env extra attacker hub-star edges and the per-device checkpoint words
+ * live in side arrays in global memory and are touched only by the actions that need them)
  *
  * Bit-planes turn every O(M) loop of the reference (busy tick volt_typhoon_env.py:904-908,
  * workload advance :1242-1261, _count_comp :563-572, candidate lists of
@@ -60,7 +61,7 @@ enum {
 /* ---- shared network tables + derived sizes (device pointers on the GPU) ---- */
 struct Net {
   cyg_config cfg;
-  int M, W, E, EW, NP, S, ncby, off_blocked, off_extra;
+  int M, W, E, EW, NP, S, ncby, off_blocked;
   const uint32_t* adj;        /* [M][W] out-neighbour bit rows (unique pairs; _outnbrs, volt:456-473) */
   const uint32_t* adjT;       /* [M][W] in-neighbour bit rows (_innbrs) */
   const uint32_t* mlo;        /* [M][W] bit v of row u: (mult(u,v)-1) & 1 */
@@ -77,6 +78,8 @@ struct Net {
   const uint32_t* m_reach;
   const uint32_t* m_valid;    /* bits < M */
   const uint32_t* m_rowmulti; /* device has an out-pair with multiplicity > 1 */
+  const uint32_t* m_incmulti; /* device has an incident (out or in) pair with multiplicity > 1 */
+  const uint32_t* m_napps;    /* [8][W] bit-planes of len(device.apps) */
   const uint32_t* m_vuln;     /* [X][W] */
   const float* os_val;        /* [M] */
   const float* ver_val;       /* [M] */
@@ -167,6 +170,17 @@ struct Stream {
     k++;
     return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
   }
+  /* continue at draw index k + n (n draws are skipped unread) */
+  CYG_HD void skip(const Rng& r, uint32_t nskip) {
+    if (nskip == 0) return;
+    uint32_t old_blk = (k + 3u) >> 2; /* first block not loaded yet */
+    k += nskip;
+    if ((k & 3u) != 0u && (k >> 2) >= old_blk) {
+      uint32_t o[4];
+      philox4x32_10(r.env, r.epoch, (uint32_t)site, k >> 2, r.k0, r.k1, o);
+      b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+    }
+  }
 };
 
 /* ---- per-env view over an internal record --------------------------------- */
@@ -175,12 +189,13 @@ struct Env {
   const Net* n;
   uint32_t* rec;   /* the record (shared memory on the GPU) */
   uint32_t* ckpt;  /* canonical per-device checkpoint words of this env [M] (global memory) */
+  uint32_t* xtra;  /* extra (attacker hub-star) edges of this env [xcap] (global memory) */
   Rng rng;
   Stream stall;    /* SITE_STALL is shared by every group of a grouped step */
   double defcost, cleancost;
 
-  CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t env_id)
-      : n(net), rec(record), ckpt(ck), stall(SITE_STALL), defcost(0.0), cleancost(0.0) {
+  CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t* xt, uint32_t env_id)
+      : n(net), rec(record), ckpt(ck), xtra(xt), stall(SITE_STALL), defcost(0.0), cleancost(0.0) {
     rng.k0 = (uint32_t)net->cfg.seed;
     rng.k1 = (uint32_t)(net->cfg.seed >> 32);
     rng.env = env_id;
@@ -189,19 +204,13 @@ struct Env {
   CYG_HD uint32_t& scal(int i) { return rec[i]; }
   CYG_HD uint32_t& pl(int p, int w) { return rec[CYG_REC_PLANES + p * W + w]; }
   CYG_HD uint32_t* blocked() { return rec + n->off_blocked; }
-  CYG_HD uint32_t* extra() { return rec + n->off_extra; }
+  CYG_HD uint32_t* extra() { return xtra; }
   CYG_HD int n_extra() { return (int)(rec[CYG_S_PREV_X] >> 16); }
 
   /* open a draw epoch (one per step / randomize / sample_action call) */
   CYG_HD void begin_epoch() {
     rng.epoch = scal(CYG_S_EPOCH);
     scal(CYG_S_EPOCH) = rng.epoch + 1u;
-    stall = Stream(SITE_STALL);
-  }
-
-  /* re-attach to the epoch the prologue opened (the kernel re-maps threads to envs between phases) */
-  CYG_HD void resume_epoch() {
-    rng.epoch = scal(CYG_S_EPOCH) - 1u;
     stall = Stream(SITE_STALL);
   }
 
@@ -481,13 +490,78 @@ struct Env {
   }
 
   /* ---- defender actions ---- */
-  CYG_HD void clean_device(int d, double ds, double& cost) { /* volt:996-1011, :676-690 */
+  /* busy_time = randint(0, high) for every device of mask a[] in ascending id order (one _stall draw each) */
+  CYG_HD void stall_deposit(const uint32_t* a, int low, int high) {
+    uint32_t range = (uint32_t)(high - low + 1);
+    for (int w = 0; w < W; w++) {
+      uint32_t bits = a[w];
+      if (!bits) continue;
+      uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      while (bits) {
+        int s = ctz(bits);
+        bits &= bits - 1;
+        uint32_t v = (uint32_t)low + below(stall.next(rng), range);
+        if (v > CYG_BUSY_MAX) { v = CYG_BUSY_MAX; scal(CYG_S_FLAGS) |= CYG_FL_ERR_BUSY; }
+        r0 |= (v & 1u) << s; r1 |= ((v >> 1) & 1u) << s; r2 |= ((v >> 2) & 1u) << s; r3 |= ((v >> 3) & 1u) << s;
+      }
+      uint32_t keep = ~a[w];
+      pl(P_BUSY0, w) = (pl(P_BUSY0, w) & keep) | r0;
+      pl(P_BUSY0 + 1, w) = (pl(P_BUSY0 + 1, w) & keep) | r1;
+      pl(P_BUSY0 + 2, w) = (pl(P_BUSY0 + 2, w) & keep) | r2;
+      pl(P_BUSY0 + 3, w) = (pl(P_BUSY0 + 3, w) & keep) | r3;
+    }
+  }
+  /* clear isCompromised, compromised_by and the workload of every device in a[] */
+  CYG_HD void wipe(const uint32_t* a, bool comp_too) {
+    for (int w = 0; w < W; w++) {
+      uint32_t keep = ~a[w];
+      if (comp_too) {
+        pl(P_COMP, w) &= keep;
+        for (int k = 0; k < n->ncby; k++) pl(P_CBY0 + k, w) &= keep;
+      }
+      pl(P_HASWL, w) &= keep;
+      pl(P_PT0, w) &= keep; pl(P_PT0 + 1, w) &= keep; pl(P_PT0 + 2, w) &= keep;
+    }
+  }
+  /* device_indices as a set: the first n_dev bits of the mask (what the reference loop visits) */
+  CYG_HD void listed(const Act& a, uint32_t* l) {
+    int nl = 0;
+    for (int w = 0; w < W; w++) { l[w] = a.mask[w] & n->m_valid[w]; nl += popc(l[w]); }
+    if (a.n_dev >= nl) return;
+    int keep = a.n_dev < 0 ? 0 : a.n_dev, seen = 0; /* inconsistent header: fewer entries than mask bits */
+    for (int w = 0; w < W; w++) {
+      uint32_t lm = l[w], out = 0;
+      while (lm) { uint32_t lb = lm & (0u - lm); lm ^= lb; if (seen++ < keep) out |= lb; }
+      l[w] = out;
+    }
+  }
+
+  /* clean every listed device: volt_typhoon_env.py:996-1011 (and :676-690 in the grouped path), set form */
+  CYG_HD void clean_set(const Act& act, double ds, double& cost) {
+    uint32_t a[W];
+    int nc = 0, nu = 0;
+    uint32_t disc = 0;
+    listed(act, a);
+    for (int w = 0; w < W; w++) {
+      a[w] &= ~pl(P_NYA, w) & ~pl(P_OWNED, w);
+      nc += popc(a[w] & pl(P_COMP, w));
+      nu += popc(a[w] & ~pl(P_COMP, w));
+      for (int k = 0; k < n->ncby; k++) if (pl(P_CBY0 + k, w) & a[w]) disc |= 1u << k;
+    }
+    cost += (nc * 0.3 - nu * 0.01) * ds;
+    cleancost += (nc * 0.3 + nu * 0.01) * ds;
+    defcost += (nc * 0.3 + nu * 0.01) * ds;
+    scal(CYG_S_FLAGS) |= disc << CYG_FL_DISC_SHIFT; /* exp.discovered = True */
+    wipe(a, true);
+    stall_deposit(a, 0, n->cfg.default_high);
+  }
+  CYG_HD void clean_device(int d, double ds, double& cost) { /* same, one device (explicit order form) */
     if (bit(P_OWNED, d)) return;
     bool comp = bit(P_COMP, d);
     cost += (comp ? 0.3 : -0.01) * ds;
     cleancost += (comp ? 0.3 : 0.01) * ds;
     defcost += (comp ? 0.3 : 0.01) * ds;
-    scal(CYG_S_FLAGS) |= cby(d) << CYG_FL_DISC_SHIFT; /* exp.discovered = True */
+    scal(CYG_S_FLAGS) |= cby(d) << CYG_FL_DISC_SHIFT;
     clr_cby(d);
     clrb(P_COMP, d);
     set_busy(d, stall_draw(0, n->cfg.default_high));
@@ -508,9 +582,10 @@ struct Env {
       busy_inc(m);
     } else if (atype == 3) {
       scal(CYG_S_REVERT)++;
-      if (scal(CYG_S_FLAGS) & CYG_FL_HAS_CKPT) {
-        int M = n->M;
-        for (int i = 0; i < M; i++) set_busy(i, stall_draw(0, c.default_high));
+      if (scal(CYG_S_FLAGS) & CYG_FL_HAS_CKPT) { /* every device: busy = randint(0, high), workload dropped */
+        uint32_t all[W];
+        for (int w = 0; w < W; w++) all[w] = n->m_valid[w];
+        stall_deposit(all, 0, c.default_high);
         for (int w = 0; w < W; w++) { pl(P_HASWL, w) = 0; pl(P_PT0, w) = 0; pl(P_PT0 + 1, w) = 0; pl(P_PT0 + 2, w) = 0; }
         cost += -1.0 * a.n_dev * ds;
         dirty = true;
@@ -519,7 +594,7 @@ struct Env {
       if (!grouped) { /* volt:946-953; the grouped variant has no busy bump (volt:650-659) */
         if (a.n_dev > 0) {
           int d = first_dev(a);
-          set_busy(d, busy(d) + 1);
+          if (d >= 0 && d < n->M) set_busy(d, busy(d) + 1);
         } else {
           uint32_t m[W];
           for (int w = 0; w < W; w++) m[w] = busy_nz(w);
@@ -559,19 +634,18 @@ struct Env {
   }
 
   /* block / unblock one incident edge of d (volt:1071-1080, :1091-1100, :485-511):
-   * pool = out-edges then in-edges whose blocked flag == want, each repeated `multiplicity` times */
-  CYG_HD bool flip_incident(int d, bool want, int site, Stream& st) {
+   * pool = out-edges then in-edges whose blocked flag == want, each repeated `multiplicity` times.
+   * General form in neighbour-id space (extra edges, multi-edges). */
+  CYG_HD bool flip_incident_general(int d, bool want, Stream& st) {
     bool has_blk = any_blocked();
     if (want && !has_blk) return false;
     uint32_t o[W], in[W];
     out_row(d, has_blk, want, o);
     in_row(d, has_blk, want, in);
-    bool multi = ((n->m_rowmulti[d >> 5] >> (d & 31)) & 1u) != 0;
-    bool multiT = false;
-    for (int w = 0; w < W; w++) multiT = multiT || ((n->mloT[d * W + w] | n->mhiT[d * W + w]) != 0);
+    bool multi = ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u) != 0;
     const uint32_t *lo = n->mlo + d * W, *hi = n->mhi + d * W, *loT = n->mloT + d * W, *hiT = n->mhiT + d * W;
     int to = weight_below(o, lo, hi, multi, 32 * W);
-    int ti = weight_below(in, loT, hiT, multiT, 32 * W);
+    int ti = weight_below(in, loT, hiT, multi, 32 * W);
     int total = to + ti;
     if (total == 0) return false;
     int r = (int)below(st.next(rng), (uint32_t)total);
@@ -579,14 +653,151 @@ struct Env {
       int v = weighted_select(o, lo, hi, multi, r);
       set_edge_blocked(d, v, !want);
     } else {
-      int s = weighted_select(in, loT, hiT, multiT, r - to);
+      int s = weighted_select(in, loT, hiT, multi, r - to);
       set_edge_blocked(s, d, !want);
     }
     return true;
   }
+  /* Same pick in EDGE-ID space, for the common case (no extra edges, no multi-edge at d): the out-edges of d
+   * are the contiguous bits [row_ptr[d], row_ptr[d+1]) of the blocked bitset (ascending neighbour id == pool
+   * order) and its in-edges are in_eid[in_ptr[d] .. in_ptr[d+1]) (ascending source id). */
+  CYG_HD bool flip_incident(int d, bool want, Stream& st) {
+    if (n_extra() > 0 || ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u)) return flip_incident_general(d, want, st);
+    uint32_t* b = blocked();
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
+    int a = n->row_ptr[d], z = n->row_ptr[d + 1];
+    int to = 0;
+    if (a < z) {
+      for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
+        uint32_t x = b[wi] ^ flipw;
+        if (wi == (a >> 5)) x &= ~lowmask(a & 31);
+        if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
+        to += popc(x);
+      }
+    }
+    int c0 = n->in_ptr[d], c1 = n->in_ptr[d + 1];
+    uint32_t inb[CYG_MAX_W]; /* pool membership of the in-edges, by position in the in-list (in-degree <= M-1) */
+    int ti = 0;
+    for (int q = 0; q < CYG_MAX_W; q++) {
+      uint32_t acc = 0;
+      int j0 = c0 + 32 * q;
+      if (j0 < c1) {
+        int lim = c1 - j0 < 32 ? c1 - j0 : 32;
+        for (int j = 0; j < lim; j++) {
+          int e = n->in_eid[j0 + j];
+          acc |= (((b[e >> 5] ^ flipw) >> (e & 31)) & 1u) << j;
+        }
+      }
+      inb[q] = acc;
+      ti += popc(acc);
+    }
+    int total = to + ti;
+    if (total == 0) return false;
+    int r = (int)below(st.next(rng), (uint32_t)total);
+    int e = -1;
+    if (r < to) {
+      for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
+        uint32_t x = b[wi] ^ flipw;
+        if (wi == (a >> 5)) x &= ~lowmask(a & 31);
+        if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
+        int cnt = popc(x);
+        if (r < cnt) { e = wi * 32 + select_in_word(x, r); break; }
+        r -= cnt;
+      }
+    } else {
+      r -= to;
+      for (int q = 0; q < CYG_MAX_W; q++) {
+        int cnt = popc(inb[q]);
+        if (r < cnt) { e = n->in_eid[c0 + 32 * q + select_in_word(inb[q], r)]; break; }
+        r -= cnt;
+      }
+    }
+    if (want) b[e >> 5] &= ~(1u << (e & 31)); else b[e >> 5] |= 1u << (e & 31);
+    return true;
+  }
 
-  /* per-device defender actions in listed order (volt:989-1123) */
-  CYG_HD void defender_per_device(const Act& a, int atype, double& cost, bool& dirty) {
+  /* per-device defender actions when device_indices is a SET (ascending, duplicate-free): the loop of
+   * volt:989-1123 collapses to word-wide operations for every type but block / unblock */
+  CYG_HD void defender_per_device_set(const Act& a, int atype, double& cost, bool& dirty) {
+    const cyg_config& c = n->cfg;
+    double ds = (double)c.def_scale;
+    if (atype == 1) { clean_set(a, ds, cost); return; }
+    uint32_t act[W];
+    int na = 0;
+    listed(a, act);
+    for (int w = 0; w < W; w++) { act[w] &= ~pl(P_NYA, w); na += popc(act[w]); }
+    if (na == 0) return;
+    switch (atype) {
+      case 4: { /* volt:1013-1018 */
+        cost += -1.0 * ds * na;
+        if (a.app_index >= 0 && a.app_index < 256) { /* devices with app_index < len(apps): bit-sliced compare */
+          uint32_t up[W];
+          for (int w = 0; w < W; w++) {
+            uint32_t gt = 0, eq = 0xFFFFFFFFu;
+            for (int bb = 7; bb >= 0; bb--) {
+              uint32_t nb = n->m_napps[bb * W + w], ab = ((a.app_index >> bb) & 1) ? 0xFFFFFFFFu : 0u;
+              gt |= eq & nb & ~ab;
+              eq &= ~(nb ^ ab);
+            }
+            up[w] = act[w] & gt;
+          }
+          stall_deposit(up, 0, c.default_high);
+        }
+      } break;
+      case 5: /* volt:1020-1069 with an untrained detector: every prediction is "D" */
+        scal(CYG_S_SCAN) += (uint32_t)na;
+        if (scal(CYG_S_LOGS) > 0) {
+          if (scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR;
+          cost += -0.5 * ds * na;
+          defcost += 0.5 * ds * na;
+        }
+        break;
+      case 6: case 9: {
+        Stream st(atype == 6 ? SITE_BLOCK : SITE_UNBLOCK);
+        cost += -0.5 * ds * na;
+        defcost += 0.5 * ds * na;
+        uint32_t cnt = 0;
+        for (int w = 0; w < W; w++) {
+          uint32_t bits = act[w];
+          while (bits) {
+            int d = w * 32 + ctz(bits);
+            bits &= bits - 1;
+            if (flip_incident(d, atype == 9, st)) cnt++;
+          }
+        }
+        if (cnt) { scal(atype == 6 ? CYG_S_EBLK : CYG_S_EADD) += cnt; dirty = true; }
+      } break;
+      case 7: /* volt:1082-1089 */
+        cost += -0.5 * ds * na;
+        for (int w = 0; w < W; w++) pl(P_NYA, w) |= act[w];
+        wipe(act, true);
+        dirty = true;
+        break;
+      case 12: { /* acts on device_indices[0] once per listed active device (volt:1102-1109) */
+        int dev0 = first_dev(a);
+        if (ckpt[dev0] & CYG_CK_VALID) {
+          restore_device(dev0);
+          cost += -1.0 * ds * na;
+          defcost += 1.0 * ds * na;
+        }
+      } break;
+      case 13: { /* volt:1111-1123: only the last of the `na` _stall draws survives */
+        int dev0 = first_dev(a);
+        clrb(P_COMP, dev0);
+        clr_cby(dev0);
+        drop_wl(dev0);
+        stall.skip(rng, (uint32_t)(na - 1));
+        set_busy(dev0, stall_draw(3, c.default_high + 3));
+        cost += -3.0 * ds * na;
+        cleancost += 3.0 * ds * na;
+        defcost += 3.0 * ds * na;
+      } break;
+      default: break;
+    }
+  }
+
+  /* per-device defender actions in listed order (volt:989-1123): explicit order form (may repeat devices) */
+  CYG_HD void defender_per_device_seq(const Act& a, int atype, double& cost, bool& dirty) {
     const cyg_config& c = n->cfg;
     double ds = (double)c.def_scale;
     int dev0 = first_dev(a);
@@ -598,12 +809,12 @@ struct Env {
       if (bit(P_NYA, d)) continue;
       switch (atype) {
         case 1: clean_device(d, ds, cost); break;
-        case 4: /* volt:1013-1018 */
+        case 4:
           cost += -1.0 * ds;
           if (a.app_index >= 0 && a.app_index < (int)((n->dev_static[d] >> CYG_ST_NAPPS_SHIFT) & 0xFFu))
             set_busy(d, stall_draw(0, c.default_high));
           break;
-        case 5: /* volt:1020-1069 with an untrained detector: every prediction is "D" */
+        case 5:
           scal(CYG_S_SCAN)++;
           if (scal(CYG_S_LOGS) > 0) {
             if (scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR;
@@ -614,9 +825,9 @@ struct Env {
         case 6:
           cost += -0.5 * ds;
           defcost += 0.5 * ds;
-          if (flip_incident(d, false, SITE_BLOCK, sblk)) { scal(CYG_S_EBLK)++; dirty = true; }
+          if (flip_incident(d, false, sblk)) { scal(CYG_S_EBLK)++; dirty = true; }
           break;
-        case 7: /* volt:1082-1089 */
+        case 7:
           cost += -0.5 * ds;
           setb(P_NYA, d);
           clrb(P_COMP, d);
@@ -627,16 +838,16 @@ struct Env {
         case 9:
           cost += -0.5 * ds;
           defcost += 0.5 * ds;
-          if (flip_incident(d, true, SITE_UNBLOCK, sunb)) { scal(CYG_S_EADD)++; dirty = true; }
+          if (flip_incident(d, true, sunb)) { scal(CYG_S_EADD)++; dirty = true; }
           break;
-        case 12: /* acts on device_indices[0] each iteration (volt:1102-1109) */
+        case 12:
           if (ckpt[dev0] & CYG_CK_VALID) {
             restore_device(dev0);
             cost += -1.0 * ds;
             defcost += 1.0 * ds;
           }
           break;
-        case 13: /* volt:1111-1123 */
+        case 13:
           clrb(P_COMP, dev0);
           clr_cby(dev0);
           drop_wl(dev0);
@@ -649,8 +860,42 @@ struct Env {
       }
     }
   }
+  CYG_HD void defender_per_device(const Act& a, int atype, double& cost, bool& dirty) {
+    if (a.order) defender_per_device_seq(a, atype, cost, dirty);
+    else defender_per_device_set(a, atype, cost, dirty);
+  }
 
   /* ---- attacker actions (volt:1126-1202) ---- */
+  /* unblocked out-neighbours of s (base row minus blocked pairs, plus unblocked extra edges) */
+  CYG_HD void live_row(int s, bool has_blk, int nx, uint32_t* row) {
+    for (int w = 0; w < W; w++) row[w] = n->adj[s * W + w];
+    if (has_blk) {
+      const uint32_t* b = blocked();
+      int a = n->row_ptr[s], z = n->row_ptr[s + 1];
+      if (a < z) {
+        for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
+          uint32_t x = b[wi];
+          if (wi == (a >> 5)) x &= ~lowmask(a & 31);
+          if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
+          while (x) {
+            int e = wi * 32 + ctz(x);
+            x &= x - 1;
+            int v = n->col[e];
+            for (int w = 0; w < W; w++) if (w == (v >> 5)) row[w] &= ~(1u << (v & 31));
+          }
+        }
+      }
+    }
+    if (nx > 0) {
+      const uint32_t* x = extra();
+      for (int j = 0; j < nx; j++) {
+        uint32_t xe = x[j];
+        if ((int)(xe & CYG_X_IDMASK) != s || (xe & CYG_X_BLOCKED)) continue;
+        int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+        for (int w = 0; w < W; w++) if (w == (v >> 5)) row[w] |= 1u << (v & 31);
+      }
+    }
+  }
   CYG_HD void attacker_act(const Act& a, int atype, double& cost) {
     const cyg_config& c = n->cfg;
     if (c.base_line == CYG_BL_NO_ATTACK) return;
@@ -658,10 +903,13 @@ struct Env {
     uint32_t src[W]; /* snapshot of compromised-or-owned devices, taken before the loop (volt:1127-1128) */
     int ns = 0;
     for (int w = 0; w < W; w++) { src[w] = pl(P_COMP, w) | pl(P_OWNED, w); ns += popc(src[w]); }
-    bool has_blk = any_blocked();
+    const bool has_blk = any_blocked();
+    const int nx = n_extra();
     if (atype == 1) {
       Stream zday(SITE_ZDAY);
       uint32_t logs = scal(CYG_S_LOGS);
+      uint32_t comp[W], known[W];
+      for (int w = 0; w < W; w++) { comp[w] = pl(P_COMP, w); known[w] = pl(P_KNOWN, w); }
       for (int xi = 0; xi < a.n_ex; xi++) {
         int raw = a.ex(xi);
         if (c.zero_day && !(raw >= 0 && raw < 32 && ((c.zero_day_mask >> raw) & 1u))) { /* volt:1135-1136 */
@@ -669,37 +917,51 @@ struct Env {
           raw = select_in_word(c.zero_day_mask, (int)below(zday.next(rng), (uint32_t)cnt));
         }
         if (!(raw >= 0 && raw < c.n_exploits)) continue; /* ids are strings: an int never matches (volt:1141) */
-        const uint32_t* vul = n->m_vuln + raw * W;
+        uint32_t kv[W], dcby[W]; /* known & vulnerable to this exploit; compromised_by additions */
+        for (int w = 0; w < W; w++) { kv[w] = known[w] & n->m_vuln[raw * W + w]; dcby[w] = 0; }
         for (int sw = 0; sw < W; sw++) {
           uint32_t sbits = src[sw];
+          const uint32_t dcw = n->m_dc[sw], mlw = n->m_rowmulti[sw];
           while (sbits) {
-            int s = sw * 32 + ctz(sbits);
+            const int sb = ctz(sbits);
+            const int s = sw * 32 + sb;
             sbits &= sbits - 1;
             uint32_t row[W];
-            out_row(s, has_blk, false, row);
-            bool is_dc = ((n->m_dc[sw] >> (s & 31)) & 1u) != 0;
-            int v = -1;
+            live_row(s, has_blk, nx, row);
+            const bool is_dc = ((dcw >> sb) & 1u) != 0;
+            /* first neighbour that is hit: DC source -> any; reachable_by_attacker; or not yet compromised,
+               known and vulnerable (volt:1163-1183) */
+            int vw = -1;
+            uint32_t cand_w = 0;
             for (int w = W - 1; w >= 0; w--) {
-              uint32_t cand = is_dc ? row[w] : (row[w] & (n->m_reach[w] | (~pl(P_COMP, w) & pl(P_KNOWN, w) & vul[w])));
-              if (cand) v = w * 32 + ctz(cand);
+              uint32_t cand = is_dc ? row[w] : (row[w] & (n->m_reach[w] | (~comp[w] & kv[w])));
+              if (cand) { vw = w; cand_w = cand; }
             }
-            bool multi = ((n->m_rowmulti[sw] >> (s & 31)) & 1u) != 0;
-            /* log_communication per hop walked (volt:1161): every repeat of the neighbours before the hit, +1 */
-            logs += (uint32_t)weight_below(row, n->mlo + s * W, n->mhi + s * W, multi, v < 0 ? 32 * W : v) + (v >= 0 ? 1u : 0u);
-            if (v >= 0) {
-              setb(P_COMP, v);
-              if (is_dc) setb(P_CBY0 + raw, v);
+            /* log_communication once per hop walked (volt:1161): all repeats of the neighbours before the hit, +1 */
+            uint32_t hitbit = cand_w & (0u - cand_w);
+            int cnt = 0;
+            const bool multi = ((mlw >> sb) & 1u) != 0;
+            for (int w = 0; w < W; w++) {
+              uint32_t m = vw < 0 ? row[w] : (w < vw ? row[w] : (w == vw ? (row[w] & (hitbit - 1u)) : 0u));
+              cnt += popc(m);
+              if (multi) cnt += popc(m & n->mlo[s * W + w]) + 2 * popc(m & n->mhi[s * W + w]);
+            }
+            logs += (uint32_t)cnt + (vw >= 0 ? 1u : 0u);
+            if (vw >= 0) {
+              for (int w = 0; w < W; w++) if (w == vw) { comp[w] |= hitbit; if (is_dc) dcby[w] |= hitbit; }
             }
           }
         }
+        for (int w = 0; w < W; w++) if (dcby[w]) pl(P_CBY0 + raw, w) |= dcby[w];
       }
+      for (int w = 0; w < W; w++) pl(P_COMP, w) = comp[w];
       scal(CYG_S_LOGS) = logs;
     } else { /* probe (volt:1187-1202) */
       if (ns > 0) {
         Stream sp(SITE_PROBE);
         int s = select_nth(src, (int)below(sp.next(rng), (uint32_t)ns));
         uint32_t row[W];
-        out_row(s, has_blk, false, row);
+        live_row(s, has_blk, nx, row);
         for (int w = 0; w < W; w++) {
           uint32_t cand = row[w] & ~pl(P_KNOWN, w);
           if (cand) { pl(P_KNOWN, w) |= cand & (0u - cand); cost += 0.1; break; }
@@ -868,46 +1130,43 @@ struct Env {
     n_comp = a; n_comp_dc = b;
   }
 
-  /* ---- the step, split at the two points where the kernel re-maps threads to envs ---- */
-  struct Carry { /* what the action phase hands to the epilogue */
-    double cost;
-    int atype, mode, dirty;
-  };
-
-  /* phase 1: open the epoch, resolve the executed action type, busy tick (volt:847-908) */
-  CYG_HD int prologue(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, uint32_t flags) {
-    const cyg_config& c = n->cfg;
-    begin_epoch();
-    bool grouped = (flags & CYG_STEP_GROUPED) != 0;
-    Act a;
-    decode(hdr, mask, order, a);
-    if (grouped) return -1;
-    int atype = a.atype;
-    if (atype == -1000) { /* action is None (volt:847-874) */
-      if (a.mode == CYG_MODE_DEFENDER) atype = (c.base_line == CYG_BL_NO_DEFENSE) ? 8 : 7;
+  /* ---- the step (volt_typhoon_env.py:818-1333; grouped: :694-779) ---- */
+  /* the action type step() ends up executing: None fill (volt:847-874), clamp into the action space
+   * (:879-884), defender forced to the no-op unless base_line == "Nash" (:913-914).  Needs no env state,
+   * so the kernel can sort a block's envs by it before their records arrive. */
+  CYG_HD static int exec_type(const cyg_config& c, uint32_t h0) {
+    int at = (int)(h0 & 0xFFu);
+    int mode = (int)((h0 >> 8) & 1u);
+    int atype = at == (int)CYG_ATYPE_NONE ? -1000 : (int)(int8_t)at;
+    if (atype == -1000) {
+      if (mode == CYG_MODE_DEFENDER) atype = (c.base_line == CYG_BL_NO_DEFENSE) ? 8 : 7;
       else atype = (c.base_line == CYG_BL_NO_ATTACK) ? 3 : 2;
     }
-    if (a.mode == CYG_MODE_DEFENDER) { if (!(atype >= 0 && atype < c.def_space_n)) atype = 8; }
+    if (mode == CYG_MODE_DEFENDER) { if (!(atype >= 0 && atype < c.def_space_n)) atype = 8; }
     else { if (!(atype >= 0 && atype < c.att_space_n)) atype = 3; }
-    tick_busyset();
-    if (a.mode == CYG_MODE_DEFENDER && c.base_line != CYG_BL_NASH) atype = 8; /* volt:913-914 */
+    if (mode == CYG_MODE_DEFENDER && c.base_line != CYG_BL_NASH) atype = 8;
     return atype;
   }
 
-  /* phase 2: the action(s) (volt:913-1202; grouped: :612-692, :607-610) */
-  CYG_HD void act(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
-                  size_t order_gs, int G, uint32_t flags, int atype, Carry& cy) {
+  CYG_HD int step(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
+                  size_t order_gs, int G, uint32_t flags, float* raw_out, float* shaped_out, int32_t* done_out,
+                  uint32_t* pre_masks) {
     const cyg_config& c = n->cfg;
-    bool grouped = (flags & CYG_STEP_GROUPED) != 0;
+    const bool grouped = (flags & CYG_STEP_GROUPED) != 0;
+    const bool skip_work = (flags & CYG_STEP_SKIP_WORK) != 0;
+    begin_epoch();
     double cost = 0.0;
     bool dirty = false;
     defcost = (double)u2f(scal(CYG_S_DEFCOST));
     cleancost = (double)u2f(scal(CYG_S_CLEANCOST));
     Act a;
     decode(hdr, mask, order, a);
-    int mode = a.mode;
+    const int mode = a.mode;
+    int atype = 0;
     if (!grouped) {
+      atype = exec_type(c, hdr[0]);
       if (a.atype == -1000) { a.n_dev = 0; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
+      tick_busyset(); /* volt:904-908 */
       if (mode == CYG_MODE_DEFENDER) {
         defender_meta(a, atype, false, cost, dirty);
         if (atype == 1 || atype == 4 || atype == 5 || atype == 6 || atype == 7 || atype == 9 || atype == 12 || atype == 13)
@@ -916,7 +1175,6 @@ struct Env {
         attacker_act(a, atype, cost);
       }
     } else {
-      atype = 0;
       for (int g = 0; g < G; g++) { /* _step_apply_only (volt:612-692) */
         Act ga;
         decode(hdr + g * hdr_gs, mask + g * mask_gs, order ? order + g * order_gs : (const uint16_t*)0, ga);
@@ -926,31 +1184,28 @@ struct Env {
           if (c.base_line != CYG_BL_NASH) gt = 8;
           defender_meta(ga, gt, true, cost, dirty);
           if (gt == 1) {
-            DevIter it;
             double ds = (double)c.def_scale;
-            for (int i = 0; i < ga.n_dev; i++) {
-              int d = next_dev(ga, it);
-              if (d < 0 || d >= n->M) break;
-              if (bit(P_NYA, d)) continue;
-              clean_device(d, ds, cost);
+            if (!ga.order) {
+              clean_set(ga, ds, cost);
+            } else {
+              DevIter it;
+              for (int i = 0; i < ga.n_dev; i++) {
+                int d = next_dev(ga, it);
+                if (d < 0 || d >= n->M) break;
+                if (bit(P_NYA, d)) continue;
+                clean_device(d, ds, cost);
+              }
             }
           }
         }
         atype = gt;
       }
-      tick_all();
+      tick_all(); /* _tick_busy_time_once (volt:607-610) */
     }
     scal(CYG_S_DEFCOST) = f2u((float)defcost);
     scal(CYG_S_CLEANCOST) = f2u((float)cleancost);
-    cy.cost = cost; cy.atype = atype; cy.mode = mode; cy.dirty = dirty ? 1 : 0;
-  }
 
-  /* phase 3: work, arrivals, reward, counters, evolve (volt:1207-1333) */
-  CYG_HD void epilogue(const Carry& cy, uint32_t flags, float* raw_out, float* shaped_out, int32_t* done_out,
-                       uint32_t* pre_masks) {
-    const cyg_config& c = n->cfg;
-    bool grouped = (flags & CYG_STEP_GROUPED) != 0;
-    bool skip_work = (flags & CYG_STEP_SKIP_WORK) != 0;
+    /* work, arrivals, reward, counters, evolve (volt:1207-1333) */
     int cur_work = 0;
     if (!skip_work || grouped) {
       cur_work = workload_advance();
@@ -961,16 +1216,16 @@ struct Env {
     count_comp(n_comp, n_comp_dc);
     if (!grouped) scal(CYG_S_COMPCNT) += (uint32_t)n_comp; /* volt:1267-1270; absent from step_grouped */
     double raw, shaped;
-    if (cy.mode == CYG_MODE_DEFENDER) {
-      raw = cy.cost + def_work - n_comp * (double)c.comp_scale;
+    if (mode == CYG_MODE_DEFENDER) {
+      raw = cost + def_work - n_comp * (double)c.comp_scale;
       shaped = raw;
     } else {
-      raw = cy.cost + (double)c.comp_scale * (n_comp + 10 * n_comp_dc);
-      double M = (double)n->M;
-      double phi = (double)n_comp / M;
+      raw = cost + (double)c.comp_scale * (n_comp + 10 * n_comp_dc);
+      double Md = (double)n->M;
+      double phi = (double)n_comp / Md;
       double gam = (double)c.gamma;
       uint32_t pn = scal(CYG_S_PREV_X) & 0xFFFFu;
-      double prev = (pn == 0xFFFFu) ? phi : gam * ((double)pn / M);
+      double prev = (pn == 0xFFFFu) ? phi : gam * ((double)pn / Md);
       double bonus = 0.1 * (gam * phi - prev);
       scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFF0000u) | (uint32_t)n_comp;
       shaped = raw + bonus;
@@ -984,15 +1239,16 @@ struct Env {
     }
     if (!skip_work || grouped) {
       scal(CYG_S_STEP)++;
-      if (cy.mode == CYG_MODE_ATTACKER) scal(CYG_S_ATT_STEP)++; else scal(CYG_S_DEF_STEP)++;
+      if (mode == CYG_MODE_ATTACKER) scal(CYG_S_ATT_STEP)++; else scal(CYG_S_DEF_STEP)++;
     }
     int done = scal(CYG_S_STEP) > 1000u; /* _check_done (CyberDefenseEnv.py:547-552) */
     bool periodic = (scal(CYG_S_STEP) % (uint32_t)c.evolve_period) == 0;
-    if (cy.dirty || periodic) evolve_network();
+    if (dirty || periodic) evolve_network();
     if (!grouped) { /* volt:1330 */
       for (int w = 0; w < W; w++) pl(P_BUSYSET, w) = busy_nz(w);
     }
     *raw_out = (float)raw; *shaped_out = (float)shaped; *done_out = done;
+    return atype;
   }
 
   /* ---- randomize_compromise_and_ownership (volt:330-383) ---- */

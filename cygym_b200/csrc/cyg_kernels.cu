@@ -71,6 +71,7 @@ struct StepParams {
   Net net;              /* pointers into the device copy of the table blob */
   uint32_t* recs;       /* [B][S] internal records */
   uint32_t* ckpt;       /* [B][M] canonical checkpoint words */
+  uint32_t* xtra;       /* [B][xcap] extra edges */
   const uint32_t* hdr;  /* [G][B][4] */
   const uint32_t* mask; /* [G][B][W] */
   const uint16_t* order;
@@ -84,48 +85,42 @@ struct StepParams {
 };
 
 #define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
-
-__host__ __device__ inline int act_stride(int W) { int a = 4 + W; return (a & 1) ? a : a + 1; }
+#define CYG_MAX_BLOCK_ENVS 512 /* threads (= envs) per CTA: 128 registers per thread at one CTA per SM */
 
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned) */
 struct SmemPlan {
-  size_t off_tables, off_recs, off_act, off_cost, off_meta, off_perm, off_cnt, off_net, off_bar, total;
+  size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_net, off_bar, total;
 };
-__host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int W, int NB) {
+__host__ __device__ inline size_t smem_take(size_t& o, size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; }
+__host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB) {
   SmemPlan p;
   size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; };
-  p.off_tables = take((size_t)hot_words * 4);
-  p.off_recs = take((size_t)NB * S * 4);
-  p.off_act = take((size_t)NB * act_stride(W) * 4);
-  p.off_cost = take((size_t)NB * 8);
-  p.off_meta = take((size_t)NB * 4);
-  p.off_perm = take((size_t)NB * 2);
-  p.off_cnt = take((size_t)(CYG_NKEYS + 1) * 4);
-  p.off_net = take(sizeof(Net));
-  p.off_bar = take(8);
+  p.off_tables = smem_take(o, (size_t)hot_words * 4);
+  p.off_recs = smem_take(o, (size_t)NB * S * 4);
+  p.off_out = smem_take(o, (size_t)NB * 3 * 4);
+  p.off_perm = smem_take(o, (size_t)NB * 2);
+  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 1) * 4);
+  p.off_net = smem_take(o, sizeof(Net));
+  p.off_bar = smem_take(o, 8);
   p.total = o;
   return p;
 }
 
 template <int W>
-__global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int NB = blockDim.x, tid = threadIdx.x;
   const int S = p.net.S, M = p.net.M;
   const int env0 = blockIdx.x * NB;
   const int nb = min(NB, p.B - env0);
-  const SmemPlan sp = smem_plan(p.net.hot_words, S, W, NB);
+  const SmemPlan sp = smem_plan(p.net.hot_words, S, NB);
   uint32_t* s_tab = (uint32_t*)(smem + sp.off_tables);
   uint32_t* s_rec = (uint32_t*)(smem + sp.off_recs);
-  uint32_t* s_act = (uint32_t*)(smem + sp.off_act);
-  double* s_cost = (double*)(smem + sp.off_cost);
-  uint32_t* s_meta = (uint32_t*)(smem + sp.off_meta);
+  float* s_out = (float*)(smem + sp.off_out);
   uint16_t* s_perm = (uint16_t*)(smem + sp.off_perm);
   uint32_t* s_cnt = (uint32_t*)(smem + sp.off_cnt);
   Net* s_net = (Net*)(smem + sp.off_net);
   uint64_t* bar = (uint64_t*)(smem + sp.off_bar);
-  const int AS = act_stride(W);
   const bool grouped = (p.flags & CYG_STEP_GROUPED) != 0;
 
   uint32_t* g_rec = p.recs + (size_t)env0 * S;
@@ -142,45 +137,28 @@ __global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ S
     Net n = p.net;
     auto hot = [&](const void* g) { return (const uint32_t*)((const unsigned char*)s_tab + ((const unsigned char*)g - (const unsigned char*)p.net.blob)); };
     n.adj = hot(n.adj); n.m_dc = hot(n.m_dc); n.m_server = hot(n.m_server); n.m_reach = hot(n.m_reach);
-    n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_vuln = hot(n.m_vuln);
+    n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_incmulti = hot(n.m_incmulti); n.m_napps = hot(n.m_napps);
+    n.m_vuln = hot(n.m_vuln);
     n.mlo = hot(n.mlo); n.mhi = hot(n.mhi); n.adjT = hot(n.adjT); n.mloT = hot(n.mloT); n.mhiT = hot(n.mhiT);
     n.in_ptr = (const int32_t*)hot(n.in_ptr); n.in_eid = (const uint16_t*)hot(n.in_eid); n.dev_static = hot(n.dev_static);
     n.row_ptr = (const int32_t*)hot(n.row_ptr); n.col = (const uint16_t*)hot(n.col);
     *s_net = n;
   }
   if (tid < CYG_NKEYS + 1) s_cnt[tid] = 0;
-  /* stage this block's actions (group 0) while the bulk copies fly: coalesced 16-byte loads */
-  if (tid < nb) {
-    const uint32_t* h = p.hdr + (size_t)(env0 + tid) * 4;
-    const uint32_t* m = p.mask + (size_t)(env0 + tid) * W;
-    uint32_t* a = s_act + tid * AS;
-    uint4 hv = *reinterpret_cast<const uint4*>(h);
-    a[0] = hv.x; a[1] = hv.y; a[2] = hv.z; a[3] = hv.w;
-#pragma unroll
-    for (int w = 0; w < W; w++) a[4 + w] = m[w];
-  }
-  __syncthreads(); /* mbarrier initialised; s_net visible */
-  if (!bulk_ok) {
-    for (int i = tid; i < nb * S; i += NB) s_rec[i] = g_rec[i];
-  }
-  mbar_wait(bar, 0);
-  __syncthreads();
+  __syncthreads(); /* mbarrier initialised, counters zeroed */
 
-  const uint16_t* order_t = p.order ? p.order + (size_t)(env0 + tid) * p.order_stride : nullptr;
-
-  /* ---- phase 1: prologue, thread t -> env t ---- */
+  /* ---- sort the block's envs by the action type they will execute (needs only the action headers, so it
+   *      overlaps the bulk copies): a warp then runs ONE branch of the 14 defender / 3+X attacker actions ---- */
   int key = 0;
   if (tid < nb) {
-    Env<W> e(s_net, s_rec + tid * S, p.ckpt + (size_t)(env0 + tid) * M, (uint32_t)(p.env_id0 + env0 + tid));
-    const uint32_t* a = s_act + tid * AS;
-    int atype = e.prologue(a, a + 4, order_t, p.flags);
-    int mode = (int)((a[0] >> 8) & 1u);
-    key = grouped ? 0 : ((mode << 4) | (atype & 15));
-    s_meta[tid] = (uint32_t)(atype & 0xFF);
+    if (!grouped) {
+      uint32_t h0 = p.hdr[(size_t)(env0 + tid) * 4];
+      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W>::exec_type(p.net.cfg, h0) & 15);
+    }
     atomicAdd(&s_cnt[key + 1], 1u);
   }
   __syncthreads();
-  if (tid == 0) { /* exclusive prefix over the 32 keys */
+  if (tid == 0) { /* exclusive prefix over the keys */
     uint32_t run = 0;
     for (int k = 1; k <= CYG_NKEYS; k++) { uint32_t c = s_cnt[k]; s_cnt[k] = run; run += c; }
   }
@@ -189,48 +167,47 @@ __global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ S
     uint32_t pos = atomicAdd(&s_cnt[key + 1], 1u);
     s_perm[pos] = (uint16_t)tid;
   }
+  if (!bulk_ok) {
+    for (int i = tid; i < nb * S; i += NB) s_rec[i] = g_rec[i];
+  }
+  mbar_wait(bar, 0);
   __syncthreads();
 
-  /* ---- phase 2: the action, thread t -> env perm[t] (a warp sees one action type) ---- */
+  /* ---- the whole step of env perm[tid], thread-per-env over bit-planes ---- */
   if (tid < nb) {
     const int el = s_perm[tid];
     const int env = env0 + el;
-    Env<W> e(s_net, s_rec + el * S, p.ckpt + (size_t)env * M, (uint32_t)(p.env_id0 + env));
-    e.resume_epoch();
-    typename Env<W>::Carry cy;
-    const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
-    if (!grouped) {
-      const uint32_t* a = s_act + el * AS;
-      e.act(a, a + 4, ord, 0, 0, 0, 1, p.flags, (int)(int8_t)s_meta[el], cy);
-    } else {
-      e.act(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
-            (size_t)p.B * p.order_stride, p.G, p.flags, 0, cy);
+    Env<W> e(s_net, s_rec + el * S, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+             (uint32_t)(p.env_id0 + env));
+    uint32_t act[4 + W]; /* this env's action (group 0), in registers */
+    {
+      uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env * 4);
+      act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+      for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env * W + w];
     }
-    s_cost[el] = cy.cost;
-    s_meta[el] = (uint32_t)(cy.atype & 0xFF) | ((uint32_t)cy.mode << 8) | ((uint32_t)cy.dirty << 9);
-  }
-  __syncthreads();
-
-  /* ---- phase 3: epilogue, thread t -> env t (coalesced outputs) ---- */
-  if (tid < nb) {
-    const int env = env0 + tid;
-    Env<W> e(s_net, s_rec + tid * S, p.ckpt + (size_t)env * M, (uint32_t)(p.env_id0 + env));
-    e.resume_epoch();
-    typename Env<W>::Carry cy;
-    uint32_t mt = s_meta[tid];
-    cy.cost = s_cost[tid];
-    cy.atype = (int)(int8_t)(mt & 0xFF);
-    cy.mode = (int)((mt >> 8) & 1u);
-    cy.dirty = (int)((mt >> 9) & 1u);
+    const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
     float raw, shaped;
     int32_t done;
-    e.epilogue(cy, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-    p.raw[env] = raw;
-    p.shaped[env] = shaped;
-    p.done[env] = done;
+    uint32_t* pre = p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr;
+    if (!grouped) {
+      e.step(act, act + 4, ord, 0, 0, 0, 1, p.flags, &raw, &shaped, &done, pre);
+    } else {
+      e.step(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
+             (size_t)p.B * p.order_stride, p.G, p.flags, &raw, &shaped, &done, pre);
+    }
+    s_out[el] = raw;
+    s_out[NB + el] = shaped;
+    s_out[2 * NB + el] = __int_as_float(done);
   }
   __syncthreads();
 
+  /* ---- coalesced outputs ---- */
+  if (tid < nb) {
+    p.raw[env0 + tid] = s_out[tid];
+    p.shaped[env0 + tid] = s_out[NB + tid];
+    p.done[env0 + tid] = __float_as_int(s_out[2 * NB + tid]);
+  }
   /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
   if (p.obs && p.obs_mode) {
     const int dim = p.obs_mode == 2 ? 4 * M + p.net.cfg.X : 6 * M;
@@ -258,6 +235,7 @@ __global__ void __launch_bounds__(256) cyg_step_kernel(const __grid_constant__ S
 struct SimpleParams {
   Net net;
   uint32_t* recs;
+  uint32_t* xtra;
   const uint8_t* env_mask;
   uint32_t* hdr;
   uint32_t* mask;
@@ -273,7 +251,7 @@ __global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
   uint32_t* g = p.recs + (size_t)env * p.net.S;
   const int nw = CYG_REC_PLANES + p.net.NP * W;
   for (int i = 0; i < nw; i++) rec[i] = g[i];
-  Env<W> e(&p.net, rec, nullptr, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, rec, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
   e.randomize();
   for (int i = 0; i < nw; i++) g[i] = rec[i];
 }
@@ -285,7 +263,7 @@ __global__ void cyg_sample_kernel(const __grid_constant__ SimpleParams p) {
   uint32_t rec[CYG_NSCAL];
   uint32_t* g = p.recs + (size_t)env * p.net.S;
   for (int i = 0; i < CYG_NSCAL; i++) rec[i] = g[i];
-  Env<W> e(&p.net, rec, nullptr, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, rec, nullptr, nullptr, (uint32_t)(p.env_id0 + env));
   uint32_t h[4], m[W];
   e.sample_action(p.mode, h, m);
   g[CYG_S_EPOCH] = rec[CYG_S_EPOCH];
@@ -298,6 +276,7 @@ struct ConvParams {
   Net net;
   uint32_t* recs;
   uint32_t* ckpt_int;
+  uint32_t* xtra_int;
   uint32_t *dev, *ckpt, *blocked, *extra, *scal;
   int B;
 };
@@ -343,8 +322,8 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     rec[lane] = v;
   }
   for (int i = lane; i < n.EW; i += 32) rec[n.off_blocked + i] = p.blocked[(size_t)warp * n.EW + i];
-  for (int i = lane; i < n.cfg.xcap; i += 32) rec[n.off_extra + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
-  for (int i = n.off_extra + n.cfg.xcap + lane; i < n.S; i += 32) rec[i] = 0u;
+  for (int i = lane; i < n.cfg.xcap; i += 32) p.xtra_int[(size_t)warp * n.cfg.xcap + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
+  for (int i = n.off_blocked + n.EW + lane; i < n.S; i += 32) rec[i] = 0u;
 }
 
 template <int W>
@@ -362,7 +341,7 @@ __global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
   }
   if (lane < CYG_NSCAL) p.scal[(size_t)warp * CYG_NSCAL + lane] = rec[lane];
   for (int i = lane; i < n.EW; i += 32) p.blocked[(size_t)warp * n.EW + i] = rec[n.off_blocked + i];
-  for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = rec[n.off_extra + i];
+  for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = p.xtra_int[(size_t)warp * n.cfg.xcap + i];
 }
 
 struct ObsParams {
@@ -389,7 +368,7 @@ struct cyg_env_s {
   Net net;           /* device pointers */
   uint32_t* d_blob;
   uint32_t* state;   /* bound internal buffer: [B][S] records then [B][M] checkpoint words */
-  int B, env_id0, device, W, NB;
+  int B, env_id0, device, W, NB, n_sms;
   size_t smem_bytes;
   int64_t launches;
 };
@@ -424,20 +403,28 @@ struct DeviceGuard {
   }
 
 static int pick_block_envs(const cyg_env_s* h, int requested) {
-  /* envs (= threads) per CTA: as many as keeps >= 3 CTAs resident per SM, capped at 256 */
+  /* envs (= threads) per CTA.  One CTA per SM: the bigger the block, the purer the per-warp action types after
+   * the in-CTA sort.  Spread B over the SMs in one wave, bounded by shared memory and 512 threads. */
   if (requested > 0) return requested;
-  const size_t budget = 72 * 1024;
-  int nb = 256;
-  while (nb > 32 && smem_plan(h->net.hot_words, h->net.S, h->W, nb).total > budget) nb -= 32;
+  const size_t budget = 226 * 1024;
+  int per_sm = (h->B + h->n_sms - 1) / h->n_sms;
+  int nb = ((per_sm + 31) / 32) * 32;
+  if (nb > CYG_MAX_BLOCK_ENVS) nb = CYG_MAX_BLOCK_ENVS;
+  if (nb < 32) nb = 32;
+  while (nb > 32 && smem_plan(h->net.hot_words, h->net.S, nb).total > budget) nb -= 32;
   return nb;
 }
 
 template <int W>
 static int configure_step(cyg_env_s* h) {
-  SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, W, h->NB);
+  SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
   h->smem_bytes = sp.total;
   if (sp.total > 227 * 1024) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
-  CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sp.total));
+  /* opt in to the device maximum once (handles with different block sizes share the kernel) */
+  int max_optin = 0;
+  CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if ((int)sp.total > max_optin) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
+  CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
   return CYG_OK;
 }
 
@@ -467,9 +454,11 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   e = cudaMemcpy(h->d_blob, h->blob.words.data(), bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(h->d_blob); delete h; return cuda_fail(e, "cudaMemcpy(tables)"); }
   relocate(h->blob, h->d_blob, h->net);
+  cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
+  if (h->n_sms < 1) h->n_sms = 148;
   const char* nb_env = getenv("CYG_BLOCK_ENVS");
   h->NB = pick_block_envs(h, nb_env ? atoi(nb_env) : 0);
-  if (h->NB < 1 || h->NB > 256) { cudaFree(h->d_blob); delete h; return fail(CYG_E_INVAL, "CYG_BLOCK_ENVS must be in 1..256"); }
+  if (h->NB < 1 || h->NB > CYG_MAX_BLOCK_ENVS) { cudaFree(h->d_blob); delete h; return fail(CYG_E_INVAL, "CYG_BLOCK_ENVS must be in 1..512"); }
   int rc = CYG_OK;
   DISPATCH_W(h->W, rc = configure_step<KW>(h));
   if (rc != CYG_OK) { cudaFree(h->d_blob); delete h; return rc; }
@@ -493,7 +482,7 @@ int cyg_set_base_line(cyg_handle h, int32_t base_line) {
 
 int cyg_internal_words(cyg_handle h, int64_t* words_per_env) {
   if (!h || !words_per_env) return fail(CYG_E_INVAL, "null argument");
-  *words_per_env = (int64_t)h->net.S + h->net.M;
+  *words_per_env = (int64_t)h->net.S + h->net.M + h->net.cfg.xcap;
   return CYG_OK;
 }
 
@@ -505,12 +494,13 @@ int cyg_bind(cyg_handle h, uint32_t* internal_state) {
 }
 
 static uint32_t* ckpt_of(cyg_handle h) { return h->state + (size_t)h->B * h->net.S; }
+static uint32_t* xtra_of(cyg_handle h) { return ckpt_of(h) + (size_t)h->B * h->net.M; }
 
 int cyg_import_state(cyg_handle h, const cyg_state* c, void* stream) {
   if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  ConvParams p = {h->net, h->state, ckpt_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
   DISPATCH_W(h->W, (cyg_import_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
   h->launches++;
@@ -522,7 +512,7 @@ int cyg_export_state(cyg_handle h, const cyg_state* c, void* stream) {
   if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  ConvParams p = {h->net, h->state, ckpt_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
   DISPATCH_W(h->W, (cyg_export_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
   h->launches++;
@@ -542,7 +532,7 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   DeviceGuard g(h->device);
   StepParams p;
   p.net = h->net;
-  p.recs = h->state; p.ckpt = ckpt_of(h);
+  p.recs = h->state; p.ckpt = ckpt_of(h); p.xtra = xtra_of(h);
   p.hdr = a->hdr; p.mask = a->mask; p.order = a->order;
   p.raw = out->raw_reward; p.shaped = out->shaped_reward; p.done = out->done;
   p.pre_masks = out->pre_masks; p.obs = out->obs;
@@ -560,7 +550,7 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, env_mask, nullptr, nullptr, h->B, h->env_id0, 0};
+  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   DISPATCH_W(h->W, (cyg_randomize_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
   h->launches++;
@@ -573,7 +563,7 @@ int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   if (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER) return fail(CYG_E_INVAL, "mode must be 0 or 1");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, nullptr, hdr, mask, h->B, h->env_id0, mode};
+  SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   DISPATCH_W(h->W, (cyg_sample_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
   h->launches++;

@@ -25,7 +25,7 @@ struct TableBlob {
   Net net;                     /* pointers are OFFSETS (in words) until relocate() */
   size_t hot_words;            /* prefix that the step kernel stages in shared memory */
   size_t o_adj, o_adjT, o_mlo, o_mhi, o_mloT, o_mhiT, o_row_ptr, o_col, o_in_ptr, o_in_eid, o_static, o_dc, o_server,
-      o_reach, o_valid, o_rowmulti, o_vuln, o_os, o_ver;
+      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver;
 };
 
 inline size_t tb_alloc(TableBlob& b, size_t nwords) {
@@ -55,8 +55,7 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   n.ncby = cfg.n_exploits > 0 ? cfg.n_exploits : 1;
   n.NP = P_CBY0 + n.ncby;
   n.off_blocked = CYG_REC_PLANES + n.NP * W;
-  n.off_extra = n.off_blocked + EW;
-  int S = n.off_extra + cfg.xcap;
+  int S = n.off_blocked + EW;
   if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
   n.S = S;
   b.words.clear();
@@ -67,6 +66,8 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   b.o_reach = tb_alloc(b, W);
   b.o_valid = tb_alloc(b, W);
   b.o_rowmulti = tb_alloc(b, W);
+  b.o_incmulti = tb_alloc(b, W);
+  b.o_napps = tb_alloc(b, (size_t)8 * W);
   b.o_vuln = tb_alloc(b, (size_t)X * W);
   b.o_mlo = tb_alloc(b, (size_t)M * W);
   b.o_mhi = tb_alloc(b, (size_t)M * W);
@@ -104,7 +105,11 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
       w[b.o_adjT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31);
       if ((mu - 1) & 1) { w[b.o_mlo + (size_t)u * W + (v >> 5)] |= 1u << (v & 31); w[b.o_mloT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31); }
       if ((mu - 1) & 2) { w[b.o_mhi + (size_t)u * W + (v >> 5)] |= 1u << (v & 31); w[b.o_mhiT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31); }
-      if (mu > 1) w[b.o_rowmulti + (u >> 5)] |= 1u << (u & 31);
+      if (mu > 1) {
+        w[b.o_rowmulti + (u >> 5)] |= 1u << (u & 31);
+        w[b.o_incmulti + (u >> 5)] |= 1u << (u & 31);
+        w[b.o_incmulti + (v >> 5)] |= 1u << (v & 31);
+      }
       indeg[v + 1]++;
     }
   }
@@ -125,6 +130,8 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
     if (st & CYG_ST_DC) w[b.o_dc + wi] |= bit;
     if (st & CYG_ST_SERVER) w[b.o_server + wi] |= bit;
     if (st & CYG_ST_REACH) w[b.o_reach + wi] |= bit;
+    for (int k = 0; k < 8; k++)
+      if ((st >> (CYG_ST_NAPPS_SHIFT + k)) & 1u) w[b.o_napps + (size_t)k * W + wi] |= bit;
     for (int e = 0; e < X; e++)
       if ((st >> (CYG_ST_VULN_SHIFT + e)) & 1u) w[b.o_vuln + (size_t)e * W + wi] |= bit;
     float osv = hn.os_val ? hn.os_val[i] : (float)i, vv = hn.ver_val ? hn.ver_val[i] : 0.f;
@@ -147,6 +154,8 @@ inline void relocate(const TableBlob& b, const uint32_t* base, Net& n) {
   n.dev_static = base + b.o_static;
   n.m_dc = base + b.o_dc; n.m_server = base + b.o_server; n.m_reach = base + b.o_reach; n.m_valid = base + b.o_valid;
   n.m_rowmulti = base + b.o_rowmulti;
+  n.m_incmulti = base + b.o_incmulti;
+  n.m_napps = base + b.o_napps;
   n.m_vuln = base + b.o_vuln;
   n.os_val = (const float*)(base + b.o_os);
   n.ver_val = (const float*)(base + b.o_ver);

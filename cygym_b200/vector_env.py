@@ -84,7 +84,7 @@ class VectorCyberDefenseEnv:
         K.check(self.L.cyg_create(C.byref(self.h), C.byref(self.cfg), C.byref(hn), self.B, self.env_id0, self.dev_index))
         words = C.c_int64()
         K.check(self.L.cyg_internal_words(self.h, C.byref(words)))
-        self.S = int(words.value) - self.M
+        self.S = int(words.value) - self.M - self.xcap
         i32 = dict(dtype=torch.int32, device=self.device)
         self._state = torch.zeros(self.B * int(words.value), **i32)
         K.check(self.L.cyg_bind(self.h, _ptr(self._state)))

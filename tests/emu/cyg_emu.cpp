@@ -33,14 +33,12 @@ static void import_env(const Net& n, uint32_t* rec, const uint32_t* dev, const u
   for (int i = 0; i < CYG_NSCAL; i++) rec[i] = scal[i];
   for (int d = 0; d < n.M; d++) import_device<W>(&n, rec, d, dev[d]);
   for (int i = 0; i < n.EW; i++) rec[n.off_blocked + i] = blocked[i];
-  for (int i = 0; i < n.cfg.xcap; i++) rec[n.off_extra + i] = extra[i];
 }
 template <int W>
 static void export_env(const Net& n, const uint32_t* rec, uint32_t* dev, uint32_t* blocked, uint32_t* extra, uint32_t* scal) {
   for (int i = 0; i < CYG_NSCAL; i++) scal[i] = rec[i];
   for (int d = 0; d < n.M; d++) dev[d] = export_device<W>(&n, rec, d);
   for (int i = 0; i < n.EW; i++) blocked[i] = rec[n.off_blocked + i];
-  for (int i = 0; i < n.cfg.xcap; i++) extra[i] = rec[n.off_extra + i];
 }
 
 template <int W>
@@ -55,23 +53,10 @@ static void step_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, u
     const uint32_t* h = hdr + (size_t)b * 4;
     const uint32_t* m = mask + (size_t)b * W;
     const uint16_t* o = order ? order + (size_t)b * order_stride : nullptr;
-    int atype;
-    { /* three separate Env objects: the kernel re-maps threads to envs between the phases */
-      Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, (uint32_t)(env_id0 + b));
-      atype = e.prologue(h, m, o, flags);
-    }
-    typename Env<W>::Carry cy;
-    {
-      Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, (uint32_t)(env_id0 + b));
-      e.resume_epoch();
-      e.act(h, m, o, (size_t)B * 4, (size_t)B * W, (size_t)B * order_stride, G, flags, atype, cy);
-    }
-    {
-      Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, (uint32_t)(env_id0 + b));
-      e.resume_epoch();
-      e.epilogue(cy, flags, raw + b, shaped + b, done + b, pre_masks ? pre_masks + (size_t)b * 3 * W : nullptr);
-    }
-    if (exec_atype) exec_atype[b] = cy.atype;
+    Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
+    int atype = e.step(h, m, o, (size_t)B * 4, (size_t)B * W, (size_t)B * order_stride, G, flags, raw + b, shaped + b,
+                       done + b, pre_masks ? pre_masks + (size_t)b * 3 * W : nullptr);
+    if (exec_atype) exec_atype[b] = atype;
     export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
   }
 }
@@ -85,7 +70,7 @@ static void randomize_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* bl
     if (env_mask && !env_mask[b]) continue;
     uint32_t* dv = dev + (size_t)b * n.M;
     import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
-    Env<W> e(&n, rec.data(), nullptr, (uint32_t)(env_id0 + b));
+    Env<W> e(&n, rec.data(), nullptr, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
     e.randomize();
     export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
   }
@@ -97,7 +82,7 @@ static void sample_w(Emu* em, int B, int env_id0, uint32_t* scal, int mode, uint
   std::vector<uint32_t> rec(n.S);
   for (int b = 0; b < B; b++) {
     for (int i = 0; i < CYG_NSCAL; i++) rec[i] = scal[(size_t)b * CYG_NSCAL + i];
-    Env<W> e(&n, rec.data(), nullptr, (uint32_t)(env_id0 + b));
+    Env<W> e(&n, rec.data(), nullptr, nullptr, (uint32_t)(env_id0 + b));
     e.sample_action(mode, hdr + (size_t)b * 4, mask + (size_t)b * W);
     for (int i = 0; i < CYG_NSCAL; i++) scal[(size_t)b * CYG_NSCAL + i] = rec[i];
   }
