@@ -6,7 +6,9 @@
  *
  *   [0, 16)                          the 16 scalars of include/cygym_b200.h (CYG_S_*)
  *   [16 + p*W, 16 + (p+1)*W)         bit-plane p, W = ceil(M/32) words, bit d = device d
- *   [off_blocked, off_blocked + EW)  blocked-edge bitset over base CSR edge ids
+ *   [off_blocked, off_blocked + EW)  blocked-edge bitset over base CSR edge ids (out-list order)
+ *   [off_blocked_in, ... + EW)       the same bits permuted into in-list order, so that the in-edges of a
+ *                                    device are a contiguous bit range too (block / unblock, volt:485-511)
  * (the rarely used per-env extra attacker hub-star edges and the per-device checkpoint words
  * live in side arrays in global memory and are touched only by the actions that need them)
  *
@@ -52,16 +54,17 @@ enum {
 
 /* bit-plane ids */
 enum {
-  P_COMP = 0, P_KNOWN = 1, P_NYA = 2, P_OWNED = 3, P_REMOVED = 4, P_HASWL = 5, P_BUSYSET = 6, P_ACTSET = 7,
-  P_PT0 = 8, P_BUSY0 = 11, P_CBY0 = 15
+  P_COMP = 0, P_KNOWN = 1, P_NYA = 2, P_OWNED = 3, P_HASWL = 4, P_BUSYSET = 5, P_ACTSET = 6,
+  P_PT0 = 7, P_BUSY0 = 10, P_CBY0 = 14
 };
 #define CYG_REC_PLANES 16 /* word offset of plane 0 inside a record */
+#define CYG_CKI_REMOVED 0x40000000u /* internal checkpoint word, spare bit: Device.removed_before (never read by step) */
 #define CYG_MAX_W 4       /* M <= 128 for the bit-matrix kernels */
 
 /* ---- shared network tables + derived sizes (device pointers on the GPU) ---- */
 struct Net {
   cyg_config cfg;
-  int M, W, E, EW, NP, S, ncby, off_blocked;
+  int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in;
   const uint32_t* adj;        /* [M][W] out-neighbour bit rows (unique pairs; _outnbrs, volt:456-473) */
   const uint32_t* adjT;       /* [M][W] in-neighbour bit rows (_innbrs) */
   const uint32_t* mlo;        /* [M][W] bit v of row u: (mult(u,v)-1) & 1 */
@@ -72,6 +75,11 @@ struct Net {
   const uint16_t* col;        /* [E] */
   const int32_t* in_ptr;      /* [M+1] */
   const uint16_t* in_eid;     /* [E] base edge id of the j-th in-edge (ascending source) */
+  const uint16_t* out2in;     /* [E] inverse of in_eid */
+  const uint32_t* e_mlo;      /* [EW] bit e: (mult(e)-1) & 1, out-list order; e_mhi: & 2 */
+  const uint32_t* e_mhi;
+  const uint32_t* ei_mlo;     /* the same in in-list order */
+  const uint32_t* ei_mhi;
   const uint32_t* dev_static; /* [M] CYG_ST_* */
   const uint32_t* m_dc;       /* [W] masks over devices */
   const uint32_t* m_server;
@@ -204,6 +212,7 @@ struct Env {
   CYG_HD uint32_t& scal(int i) { return rec[i]; }
   CYG_HD uint32_t& pl(int p, int w) { return rec[CYG_REC_PLANES + p * W + w]; }
   CYG_HD uint32_t* blocked() { return rec + n->off_blocked; }
+  CYG_HD uint32_t* blocked_in() { return rec + n->off_blocked_in; }
   CYG_HD uint32_t* extra() { return xtra; }
   CYG_HD int n_extra() { return (int)(rec[CYG_S_PREV_X] >> 16); }
 
@@ -380,11 +389,15 @@ struct Env {
     for (int j = 0; j < nx; j++) if ((x[j] & 0xFFFFFFu) == key) return true;
     return false;
   }
+  CYG_HD void set_base_blocked(int e, bool b) { /* both orders of the bitset */
+    int j = n->out2in[e];
+    if (b) { blocked()[e >> 5] |= 1u << (e & 31); blocked_in()[j >> 5] |= 1u << (j & 31); }
+    else { blocked()[e >> 5] &= ~(1u << (e & 31)); blocked_in()[j >> 5] &= ~(1u << (j & 31)); }
+  }
   /* flip the blocked flag of edge (u, v) */
   CYG_HD void set_edge_blocked(int u, int v, bool b) {
     if ((n->adj[u * W + (v >> 5)] >> (v & 31)) & 1u) {
-      int e = base_eid(u, v);
-      if (b) blocked()[e >> 5] |= 1u << (e & 31); else blocked()[e >> 5] &= ~(1u << (e & 31));
+      set_base_blocked(base_eid(u, v), b);
       return;
     }
     int nx = n_extra();
@@ -395,8 +408,8 @@ struct Env {
   }
   /* _rebuild_graph_cache (volt:456-483) forgets every block (:476) */
   CYG_HD void rebuild_cache() {
-    uint32_t* b = blocked();
-    for (int i = 0; i < n->EW; i++) b[i] = 0;
+    uint32_t *b = blocked(), *bi = blocked_in();
+    for (int i = 0; i < n->EW; i++) { b[i] = 0; bi[i] = 0; }
     int nx = n_extra();
     uint32_t* x = extra();
     for (int j = 0; j < nx; j++) x[j] &= ~CYG_X_BLOCKED;
@@ -614,7 +627,7 @@ struct Env {
         if (bit(P_HASWL, d)) k |= CYG_CK_HASWL | (field(P_PT0, 3, d) << CYG_DEV_PT_SHIFT);
         k |= busy(d) << CYG_DEV_BUSY_SHIFT;
         k |= cby(d) << CYG_DEV_CBY_SHIFT;
-        ckpt[d] = k;
+        ckpt[d] = k | (ckpt[d] & CYG_CKI_REMOVED);
         scal(CYG_S_CKPT)++;
         cost += -0.1 * ds;
         defcost += 0.1 * ds;
@@ -658,61 +671,56 @@ struct Env {
     }
     return true;
   }
-  /* Same pick in EDGE-ID space, for the common case (no extra edges, no multi-edge at d): the out-edges of d
-   * are the contiguous bits [row_ptr[d], row_ptr[d+1]) of the blocked bitset (ascending neighbour id == pool
-   * order) and its in-edges are in_eid[in_ptr[d] .. in_ptr[d+1]) (ascending source id). */
-  CYG_HD bool flip_incident(int d, bool want, Stream& st) {
-    if (n_extra() > 0 || ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u)) return flip_incident_general(d, want, st);
-    uint32_t* b = blocked();
-    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
-    int a = n->row_ptr[d], z = n->row_ptr[d + 1];
-    int to = 0;
-    if (a < z) {
-      for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
-        uint32_t x = b[wi] ^ flipw;
-        if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-        if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-        to += popc(x);
-      }
+  /* Same pick in EDGE-ID space when the env has no extra edges: the out-edges of d are the contiguous bits
+   * [row_ptr[d], row_ptr[d+1]) of the blocked bitset (ascending neighbour id == pool order) and its in-edges the
+   * bits [in_ptr[d], in_ptr[d+1]) of the in-order copy (ascending source id). */
+  CYG_HD int range_weight(const uint32_t* b, uint32_t flipw, int a, int z, bool multi, const uint32_t* lo, const uint32_t* hi) {
+    int c = 0;
+    if (a >= z) return 0;
+    for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
+      uint32_t x = b[wi] ^ flipw;
+      if (wi == (a >> 5)) x &= ~lowmask(a & 31);
+      if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
+      c += popc(x);
+      if (multi) c += popc(x & lo[wi]) + 2 * popc(x & hi[wi]);
     }
-    int c0 = n->in_ptr[d], c1 = n->in_ptr[d + 1];
-    uint32_t inb[CYG_MAX_W]; /* pool membership of the in-edges, by position in the in-list (in-degree <= M-1) */
-    int ti = 0;
-    for (int q = 0; q < CYG_MAX_W; q++) {
-      uint32_t acc = 0;
-      int j0 = c0 + 32 * q;
-      if (j0 < c1) {
-        int lim = c1 - j0 < 32 ? c1 - j0 : 32;
-        for (int j = 0; j < lim; j++) {
-          int e = n->in_eid[j0 + j];
-          acc |= (((b[e >> 5] ^ flipw) >> (e & 31)) & 1u) << j;
+    return c;
+  }
+  CYG_HD int range_select(const uint32_t* b, uint32_t flipw, int a, int z, bool multi, const uint32_t* lo, const uint32_t* hi, int r) {
+    for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
+      uint32_t x = b[wi] ^ flipw;
+      if (wi == (a >> 5)) x &= ~lowmask(a & 31);
+      if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
+      int cnt = popc(x);
+      if (multi) cnt += popc(x & lo[wi]) + 2 * popc(x & hi[wi]);
+      if (r < cnt) {
+        if (!multi || ((x & (lo[wi] | hi[wi])) == 0)) return wi * 32 + select_in_word(x, r);
+        while (x) {
+          int sb = ctz(x);
+          x &= x - 1;
+          int wt = 1 + (int)((lo[wi] >> sb) & 1u) + 2 * (int)((hi[wi] >> sb) & 1u);
+          if (r < wt) return wi * 32 + sb;
+          r -= wt;
         }
       }
-      inb[q] = acc;
-      ti += popc(acc);
+      r -= cnt;
     }
+    return -1;
+  }
+  CYG_HD bool flip_incident(int d, bool want, Stream& st) {
+    if (n_extra() > 0) return flip_incident_general(d, want, st);
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
+    const bool multi = ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u) != 0;
+    const int a = n->row_ptr[d], z = n->row_ptr[d + 1], c0 = n->in_ptr[d], c1 = n->in_ptr[d + 1];
+    int to = range_weight(blocked(), flipw, a, z, multi, n->e_mlo, n->e_mhi);
+    int ti = range_weight(blocked_in(), flipw, c0, c1, multi, n->ei_mlo, n->ei_mhi);
     int total = to + ti;
     if (total == 0) return false;
     int r = (int)below(st.next(rng), (uint32_t)total);
-    int e = -1;
-    if (r < to) {
-      for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
-        uint32_t x = b[wi] ^ flipw;
-        if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-        if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-        int cnt = popc(x);
-        if (r < cnt) { e = wi * 32 + select_in_word(x, r); break; }
-        r -= cnt;
-      }
-    } else {
-      r -= to;
-      for (int q = 0; q < CYG_MAX_W; q++) {
-        int cnt = popc(inb[q]);
-        if (r < cnt) { e = n->in_eid[c0 + 32 * q + select_in_word(inb[q], r)]; break; }
-        r -= cnt;
-      }
-    }
-    if (want) b[e >> 5] &= ~(1u << (e & 31)); else b[e >> 5] |= 1u << (e & 31);
+    int e;
+    if (r < to) e = range_select(blocked(), flipw, a, z, multi, n->e_mlo, n->e_mhi, r);
+    else e = n->in_eid[range_select(blocked_in(), flipw, c0, c1, multi, n->ei_mlo, n->ei_mhi, r - to)];
+    set_base_blocked(e, !want);
     return true;
   }
 
@@ -1089,7 +1097,7 @@ struct Env {
         for (int w = 0; w < W; w++) m[w] = pl(P_ACTSET, w);
         int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)n_act));
         setb(P_NYA, node);
-        setb(P_REMOVED, node);
+        ckpt[node] |= CYG_CKI_REMOVED; /* removed_before */
         drop_wl(node);
         set_field(P_BUSY0, 4, node, 0);
         clrb(P_ACTSET, node);
@@ -1314,7 +1322,7 @@ CYG_HD void import_device(const Net* n, uint32_t* rec, int d, uint32_t w) {
   uint32_t* pl = rec + CYG_REC_PLANES;
   auto put = [&](int p, bool v) { if (v) pl[p * W + wi] |= m; else pl[p * W + wi] &= ~m; };
   put(P_COMP, w & CYG_DEV_COMP); put(P_KNOWN, w & CYG_DEV_KNOWN); put(P_NYA, w & CYG_DEV_NYA);
-  put(P_OWNED, w & CYG_DEV_OWNED); put(P_REMOVED, w & CYG_DEV_REMOVED); put(P_HASWL, w & CYG_DEV_HASWL);
+  put(P_OWNED, w & CYG_DEV_OWNED); put(P_HASWL, w & CYG_DEV_HASWL);
   put(P_BUSYSET, w & CYG_DEV_BUSYSET); put(P_ACTSET, w & CYG_DEV_ACTSET);
   uint32_t pt = (w >> CYG_DEV_PT_SHIFT) & CYG_DEV_PT_MASK;
   for (int k = 0; k < 3; k++) put(P_PT0 + k, (pt >> k) & 1u);
@@ -1325,7 +1333,7 @@ CYG_HD void import_device(const Net* n, uint32_t* rec, int d, uint32_t w) {
   for (int k = 0; k < n->ncby; k++) put(P_CBY0 + k, (cb >> k) & 1u);
 }
 template <int W>
-CYG_HD uint32_t export_device(const Net* n, const uint32_t* rec, int d) {
+CYG_HD uint32_t export_device(const Net* n, const uint32_t* rec, int d, uint32_t ckpt_internal) {
   int wi = d >> 5, s = d & 31;
   const uint32_t* pl = rec + CYG_REC_PLANES;
   auto get = [&](int p) -> uint32_t { return (pl[p * W + wi] >> s) & 1u; };
@@ -1334,7 +1342,7 @@ CYG_HD uint32_t export_device(const Net* n, const uint32_t* rec, int d) {
   if (get(P_KNOWN)) w |= CYG_DEV_KNOWN;
   if (get(P_NYA)) w |= CYG_DEV_NYA;
   if (get(P_OWNED)) w |= CYG_DEV_OWNED;
-  if (get(P_REMOVED)) w |= CYG_DEV_REMOVED;
+  if (ckpt_internal & CYG_CKI_REMOVED) w |= CYG_DEV_REMOVED;
   if (get(P_HASWL)) w |= CYG_DEV_HASWL;
   if (get(P_BUSYSET)) w |= CYG_DEV_BUSYSET;
   if (get(P_ACTSET)) w |= CYG_DEV_ACTSET;

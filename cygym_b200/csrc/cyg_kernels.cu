@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
     n.adj = hot(n.adj); n.m_dc = hot(n.m_dc); n.m_server = hot(n.m_server); n.m_reach = hot(n.m_reach);
     n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_incmulti = hot(n.m_incmulti); n.m_napps = hot(n.m_napps);
     n.m_vuln = hot(n.m_vuln);
-    n.mlo = hot(n.mlo); n.mhi = hot(n.mhi); n.adjT = hot(n.adjT); n.mloT = hot(n.mloT); n.mhiT = hot(n.mhiT);
     n.in_ptr = (const int32_t*)hot(n.in_ptr); n.in_eid = (const uint16_t*)hot(n.in_eid); n.dev_static = hot(n.dev_static);
+    n.out2in = (const uint16_t*)hot(n.out2in); n.e_mlo = hot(n.e_mlo); n.e_mhi = hot(n.e_mhi); n.ei_mlo = hot(n.ei_mlo); n.ei_mhi = hot(n.ei_mhi);
     n.row_ptr = (const int32_t*)hot(n.row_ptr); n.col = (const uint16_t*)hot(n.col);
     *s_net = n;
   }
@@ -247,7 +247,7 @@ __global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.B) return;
   if (p.env_mask && !p.env_mask[env]) return;
-  uint32_t rec[CYG_REC_PLANES + 21 * W]; /* scalars + planes are all randomize touches */
+  uint32_t rec[CYG_REC_PLANES + 20 * W]; /* scalars + planes are all randomize touches */
   uint32_t* g = p.recs + (size_t)env * p.net.S;
   const int nw = CYG_REC_PLANES + p.net.NP * W;
   for (int i = 0; i < nw; i++) rec[i] = g[i];
@@ -294,9 +294,9 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     uint32_t x = d < M ? p.dev[(size_t)warp * M + d] : 0u;
     uint32_t b = (x >> CYG_DEV_BUSY_SHIFT) & CYG_DEV_BUSY_MASK;
     if (b > CYG_BUSY_MAX) { b = CYG_BUSY_MAX; err = CYG_FL_ERR_BUSY; }
-    uint32_t flags8 = x & 0xFFu; /* COMP KNOWN NYA OWNED REMOVED HASWL BUSYSET ACTSET are bits 0..7 == planes 0..7 */
-    for (int pnum = 0; pnum < 8; pnum++) {
-      uint32_t m = __ballot_sync(0xFFFFFFFFu, (flags8 >> pnum) & 1u);
+    const uint32_t cbits[7] = {CYG_DEV_COMP, CYG_DEV_KNOWN, CYG_DEV_NYA, CYG_DEV_OWNED, CYG_DEV_HASWL, CYG_DEV_BUSYSET, CYG_DEV_ACTSET};
+    for (int pnum = 0; pnum < 7; pnum++) { /* planes P_COMP .. P_ACTSET */
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, (x & cbits[pnum]) != 0);
       if (lane == 0) rec[CYG_REC_PLANES + pnum * W + w] = m;
     }
     uint32_t pt = (x >> CYG_DEV_PT_SHIFT) & CYG_DEV_PT_MASK;
@@ -313,7 +313,7 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
       uint32_t m = __ballot_sync(0xFFFFFFFFu, (cb >> k) & 1u);
       if (lane == 0) rec[CYG_REC_PLANES + (P_CBY0 + k) * W + w] = m;
     }
-    if (d < M) p.ckpt_int[(size_t)warp * M + d] = p.ckpt ? p.ckpt[(size_t)warp * M + d] : 0u;
+    if (d < M) p.ckpt_int[(size_t)warp * M + d] = ((p.ckpt ? p.ckpt[(size_t)warp * M + d] : 0u) & ~CYG_CKI_REMOVED) | ((x & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u);
   }
   err = __reduce_or_sync(0xFFFFFFFFu, err);
   if (lane < CYG_NSCAL) {
@@ -321,9 +321,18 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     if (lane == CYG_S_FLAGS) v |= err;
     rec[lane] = v;
   }
-  for (int i = lane; i < n.EW; i += 32) rec[n.off_blocked + i] = p.blocked[(size_t)warp * n.EW + i];
+  for (int i = lane; i < n.EW; i += 32) {
+    const uint32_t* bo = p.blocked + (size_t)warp * n.EW;
+    rec[n.off_blocked + i] = bo[i];
+    uint32_t bi = 0; /* the same bits in in-list order */
+    for (int j = 0; j < 32 && i * 32 + j < n.E; j++) {
+      int e = n.in_eid[i * 32 + j];
+      bi |= ((bo[e >> 5] >> (e & 31)) & 1u) << j;
+    }
+    rec[n.off_blocked_in + i] = bi;
+  }
   for (int i = lane; i < n.cfg.xcap; i += 32) p.xtra_int[(size_t)warp * n.cfg.xcap + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
-  for (int i = n.off_blocked + n.EW + lane; i < n.S; i += 32) rec[i] = 0u;
+  for (int i = n.off_blocked_in + n.EW + lane; i < n.S; i += 32) rec[i] = 0u;
 }
 
 template <int W>
@@ -336,8 +345,9 @@ __global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
   for (int w = 0; w < W; w++) {
     int d = w * 32 + lane;
     if (d >= M) continue;
-    p.dev[(size_t)warp * M + d] = export_device<W>(&n, rec, d);
-    if (p.ckpt) p.ckpt[(size_t)warp * M + d] = p.ckpt_int[(size_t)warp * M + d];
+    uint32_t ck = p.ckpt_int[(size_t)warp * M + d];
+    p.dev[(size_t)warp * M + d] = export_device<W>(&n, rec, d, ck);
+    if (p.ckpt) p.ckpt[(size_t)warp * M + d] = ck & ~CYG_CKI_REMOVED;
   }
   if (lane < CYG_NSCAL) p.scal[(size_t)warp * CYG_NSCAL + lane] = rec[lane];
   for (int i = lane; i < n.EW; i += 32) p.blocked[(size_t)warp * n.EW + i] = rec[n.off_blocked + i];

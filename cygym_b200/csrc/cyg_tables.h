@@ -25,7 +25,7 @@ struct TableBlob {
   Net net;                     /* pointers are OFFSETS (in words) until relocate() */
   size_t hot_words;            /* prefix that the step kernel stages in shared memory */
   size_t o_adj, o_adjT, o_mlo, o_mhi, o_mloT, o_mhiT, o_row_ptr, o_col, o_in_ptr, o_in_eid, o_static, o_dc, o_server,
-      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver;
+      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver, o_out2in, o_emlo, o_emhi, o_eimlo, o_eimhi;
 };
 
 inline size_t tb_alloc(TableBlob& b, size_t nwords) {
@@ -55,7 +55,8 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   n.ncby = cfg.n_exploits > 0 ? cfg.n_exploits : 1;
   n.NP = P_CBY0 + n.ncby;
   n.off_blocked = CYG_REC_PLANES + n.NP * W;
-  int S = n.off_blocked + EW;
+  n.off_blocked_in = n.off_blocked + EW;
+  int S = n.off_blocked_in + EW;
   if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
   n.S = S;
   b.words.clear();
@@ -69,18 +70,23 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   b.o_incmulti = tb_alloc(b, W);
   b.o_napps = tb_alloc(b, (size_t)8 * W);
   b.o_vuln = tb_alloc(b, (size_t)X * W);
-  b.o_mlo = tb_alloc(b, (size_t)M * W);
-  b.o_mhi = tb_alloc(b, (size_t)M * W);
   b.o_row_ptr = tb_alloc(b, M + 1);
   b.o_col = tb_alloc(b, (E + 1) / 2 + 1);
-  b.o_adjT = tb_alloc(b, (size_t)M * W);
-  b.o_mloT = tb_alloc(b, (size_t)M * W);
-  b.o_mhiT = tb_alloc(b, (size_t)M * W);
   b.o_in_ptr = tb_alloc(b, M + 1);
   b.o_in_eid = tb_alloc(b, (E + 1) / 2 + 1);
   b.o_static = tb_alloc(b, M);
+  b.o_out2in = tb_alloc(b, (E + 1) / 2 + 1);
+  b.o_emlo = tb_alloc(b, EW);
+  b.o_emhi = tb_alloc(b, EW);
+  b.o_eimlo = tb_alloc(b, EW);
+  b.o_eimhi = tb_alloc(b, EW);
   b.hot_words = b.words.size();
-  /* cold section (observation rows only) */
+  /* cold section: read through L1/L2 (multi-edge weights, in-rows for envs with extra edges, observation rows) */
+  b.o_mlo = tb_alloc(b, (size_t)M * W);
+  b.o_mhi = tb_alloc(b, (size_t)M * W);
+  b.o_adjT = tb_alloc(b, (size_t)M * W);
+  b.o_mloT = tb_alloc(b, (size_t)M * W);
+  b.o_mhiT = tb_alloc(b, (size_t)M * W);
   b.o_os = tb_alloc(b, M);
   b.o_ver = tb_alloc(b, M);
   uint32_t* w = b.words.data();
@@ -119,7 +125,12 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   for (int u = 0; u < M; u++) /* ascending u => in-lists ascending by source */
     for (int e = hn.row_ptr[u]; e < hn.row_ptr[u + 1]; e++) {
       int v = hn.col[e];
-      ineid16[indeg[v] + fill[v]++] = (uint16_t)e;
+      int j = indeg[v] + fill[v]++;
+      ineid16[j] = (uint16_t)e;
+      ((uint16_t*)(w + b.o_out2in))[e] = (uint16_t)j;
+      int mu = hn.mult ? hn.mult[e] : 1;
+      if ((mu - 1) & 1) { w[b.o_emlo + (e >> 5)] |= 1u << (e & 31); w[b.o_eimlo + (j >> 5)] |= 1u << (j & 31); }
+      if ((mu - 1) & 2) { w[b.o_emhi + (e >> 5)] |= 1u << (e & 31); w[b.o_eimhi + (j >> 5)] |= 1u << (j & 31); }
     }
   for (int i = 0; i < M; i++) {
     uint32_t st = hn.dev_static[i];
@@ -151,6 +162,8 @@ inline void relocate(const TableBlob& b, const uint32_t* base, Net& n) {
   n.col = (const uint16_t*)(base + b.o_col);
   n.in_ptr = (const int32_t*)(base + b.o_in_ptr);
   n.in_eid = (const uint16_t*)(base + b.o_in_eid);
+  n.out2in = (const uint16_t*)(base + b.o_out2in);
+  n.e_mlo = base + b.o_emlo; n.e_mhi = base + b.o_emhi; n.ei_mlo = base + b.o_eimlo; n.ei_mhi = base + b.o_eimhi;
   n.dev_static = base + b.o_static;
   n.m_dc = base + b.o_dc; n.m_server = base + b.o_server; n.m_reach = base + b.o_reach; n.m_valid = base + b.o_valid;
   n.m_rowmulti = base + b.o_rowmulti;

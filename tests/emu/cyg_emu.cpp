@@ -28,16 +28,27 @@ static std::string g_err;
 
 template <int W>
 static void import_env(const Net& n, uint32_t* rec, const uint32_t* dev, const uint32_t* blocked, const uint32_t* extra,
-                       const uint32_t* scal) {
+                       const uint32_t* scal, uint32_t* ckpt) {
   memset(rec, 0, sizeof(uint32_t) * (size_t)n.S);
   for (int i = 0; i < CYG_NSCAL; i++) rec[i] = scal[i];
-  for (int d = 0; d < n.M; d++) import_device<W>(&n, rec, d, dev[d]);
+  for (int d = 0; d < n.M; d++) {
+    import_device<W>(&n, rec, d, dev[d]);
+    if (ckpt) ckpt[d] = (ckpt[d] & ~CYG_CKI_REMOVED) | ((dev[d] & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u);
+  }
   for (int i = 0; i < n.EW; i++) rec[n.off_blocked + i] = blocked[i];
+  for (int j = 0; j < n.E; j++) {
+    int e = n.in_eid[j];
+    if ((blocked[e >> 5] >> (e & 31)) & 1u) rec[n.off_blocked_in + (j >> 5)] |= 1u << (j & 31);
+  }
 }
 template <int W>
-static void export_env(const Net& n, const uint32_t* rec, uint32_t* dev, uint32_t* blocked, uint32_t* extra, uint32_t* scal) {
+static void export_env(const Net& n, const uint32_t* rec, uint32_t* dev, uint32_t* blocked, uint32_t* extra, uint32_t* scal,
+                       uint32_t* ckpt) {
   for (int i = 0; i < CYG_NSCAL; i++) scal[i] = rec[i];
-  for (int d = 0; d < n.M; d++) dev[d] = export_device<W>(&n, rec, d);
+  for (int d = 0; d < n.M; d++) {
+    dev[d] = export_device<W>(&n, rec, d, ckpt ? ckpt[d] : ((dev[d] & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u));
+    if (ckpt) ckpt[d] &= ~CYG_CKI_REMOVED;
+  }
   for (int i = 0; i < n.EW; i++) blocked[i] = rec[n.off_blocked + i];
 }
 
@@ -49,7 +60,8 @@ static void step_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, u
   std::vector<uint32_t> rec(n.S);
   for (int b = 0; b < B; b++) {
     uint32_t* dv = dev + (size_t)b * n.M;
-    import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
+    import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL,
+                  ckpt + (size_t)b * n.M);
     const uint32_t* h = hdr + (size_t)b * 4;
     const uint32_t* m = mask + (size_t)b * W;
     const uint16_t* o = order ? order + (size_t)b * order_stride : nullptr;
@@ -57,7 +69,8 @@ static void step_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, u
     int atype = e.step(h, m, o, (size_t)B * 4, (size_t)B * W, (size_t)B * order_stride, G, flags, raw + b, shaped + b,
                        done + b, pre_masks ? pre_masks + (size_t)b * 3 * W : nullptr);
     if (exec_atype) exec_atype[b] = atype;
-    export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
+    export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL,
+                  ckpt + (size_t)b * n.M);
   }
 }
 
@@ -69,10 +82,10 @@ static void randomize_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* bl
   for (int b = 0; b < B; b++) {
     if (env_mask && !env_mask[b]) continue;
     uint32_t* dv = dev + (size_t)b * n.M;
-    import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
+    import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL, nullptr);
     Env<W> e(&n, rec.data(), nullptr, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
     e.randomize();
-    export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL);
+    export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL, nullptr);
   }
 }
 
