@@ -178,6 +178,10 @@ def main():
             ab = sets[r % a.sets].sample_actions(mode)
             if mode == 0:  # detector untrained: defender 10 -> no-op 8
                 ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == 10, (ab.hdr[:, 0] & ~0xFF) | 8, ab.hdr[:, 0])
+            for spec in filter(None, os.environ.get('CYG_BENCH_EXCLUDE', '').split(',')):  # diagnostics only
+                m_, t_ = spec.split(':')
+                if int(m_) == mode:
+                    ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == int(t_), (ab.hdr[:, 0] & ~0xFF) | (8 if mode == 0 else 3), ab.hdr[:, 0])
             ring[mode].append(ActionBatch(ab.hdr.clone(), ab.mask.clone()))
     torch.cuda.synchronize()
 

@@ -10,7 +10,7 @@ import subprocess
 from . import draw_tables as DT
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcygym_b200.so")
+LIB_PATH = os.environ.get("CYGYM_B200_LIB") or os.path.join(_HERE, "libcygym_b200.so")  # override: profiling builds only
 _SRC = os.path.join(_HERE, "csrc", "cyg_kernels.cu")
 _DEPS = [_SRC, os.path.join(_HERE, "csrc", "cyg_core.cuh"), os.path.join(_HERE, "csrc", "cyg_tables.h"),
          os.path.join(os.path.dirname(_HERE), "include", "cygym_b200.h")]
@@ -73,7 +73,7 @@ class CygStepOut(C.Structure):
 
 EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_internal_words",
            "cyg_bind", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_randomize", "cyg_sample_actions",
-           "cyg_observe", "cyg_launch_count"]
+           "cyg_observe", "cyg_launch_count", "cyg_set_debug_cycles"]
 
 
 class CygError(RuntimeError):
@@ -121,6 +121,7 @@ def lib():
         L.cyg_observe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.cyg_launch_count.argtypes = [C.c_void_p]
         L.cyg_launch_count.restype = C.c_int64
+        L.cyg_set_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -1,0 +1,223 @@
+/*
+ * cyg_coop.cuh -- warp-per-env forms of the draw-heavy defender actions (device only).
+ *
+ * Thread-per-env is the right mapping for the word-wide parts of a step, but four defender actions walk the
+ * listed devices one by one, each with its own random draw: clean (volt_typhoon_env.py:996-1011), revert
+ * (:928-943), upgrade (:1013-1018) and block / unblock (:1071-1100 -> :485-511).  One thread doing that for ~90
+ * devices is a ~10^5-cycle dependent chain that the rest of the CTA waits for.  Here a whole warp takes ONE env
+ * and its 32 lanes take 32 consecutive listed devices.
+ *
+ * Draws are addressable (oracle/draws.py: x = Philox(seed; env, epoch, site, k)), so lane i simply computes the
+ * draw of ITS device, k = (draws consumed so far) + (rank of the device among those that draw).
+ *
+ *  - clean / revert / upgrade: every listed device draws, nothing a device does depends on another device, so
+ *    the result is one ballot per busy_time bit-plane.
+ *  - block / unblock is sequential in the reference: the pool of device i (its incident edges with the wanted
+ *    blocked flag) shrinks when an EARLIER device flips an edge that also touches i.  The lanes pick
+ *    speculatively against the state at the start of the round; a pick is invalid only if a lower lane picked an
+ *    edge whose far endpoint is that lane's device.  The round commits the lanes below the first such lane and
+ *    restarts from it, so the outcome is bit-identical to the sequential walk.
+ *
+ * All lanes call these functions with identical arguments; only lane 0 touches per-env scalars and cost sums.
+ */
+#ifndef CYG_COOP_CUH
+#define CYG_COOP_CUH
+
+#include "cyg_core.cuh"
+
+namespace cyg {
+
+#define CYG_FULL 0xFFFFFFFFu
+
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
+__device__ __forceinline__ uint32_t lanes_below(int lane) { return (1u << lane) - 1u; }
+
+/* k-th draw of `site` in the current epoch */
+__device__ __forceinline__ uint32_t draw_at(const Rng& r, int site, uint32_t k) {
+  uint32_t o[4];
+  philox4x32_10(r.env, r.epoch, (uint32_t)site, k >> 2, r.k0, r.k1, o);
+  uint32_t j = k & 3u;
+  return j == 0 ? o[0] : j == 1 ? o[1] : j == 2 ? o[2] : o[3];
+}
+
+template <int W>
+struct Coop {
+  typedef Env<W, true> E;
+
+  /* busy_time = low + below(draw, range) for the devices of A[] (lane-uniform), draws k_base, k_base+1, ... in
+   * ascending device order (the set form of _stall, volt:135-138) */
+  static __device__ void deposit(E& e, const uint32_t* A, int low, int high, uint32_t k_base) {
+    const int lane = lane_id();
+    const uint32_t range = (uint32_t)(high - low + 1);
+    uint32_t kw = k_base;
+    bool over = false;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+      const uint32_t aw = A[w];
+      if (aw == 0) continue; /* uniform */
+      const bool on = ((aw >> lane) & 1u) != 0;
+      uint32_t v = 0;
+      if (on) {
+        v = (uint32_t)low + below(draw_at(e.rng, SITE_STALL, kw + (uint32_t)popc(aw & lanes_below(lane))), range);
+        if (v > CYG_BUSY_MAX) { v = CYG_BUSY_MAX; over = true; }
+      }
+      const uint32_t r0 = __ballot_sync(CYG_FULL, v & 1u), r1 = __ballot_sync(CYG_FULL, v & 2u);
+      const uint32_t r2 = __ballot_sync(CYG_FULL, v & 4u), r3 = __ballot_sync(CYG_FULL, v & 8u);
+      if (lane == 0) {
+        const uint32_t keep = ~aw;
+        e.pl(P_BUSY0, w) = (e.pl(P_BUSY0, w) & keep) | r0;
+        e.pl(P_BUSY0 + 1, w) = (e.pl(P_BUSY0 + 1, w) & keep) | r1;
+        e.pl(P_BUSY0 + 2, w) = (e.pl(P_BUSY0 + 2, w) & keep) | r2;
+        e.pl(P_BUSY0 + 3, w) = (e.pl(P_BUSY0 + 3, w) & keep) | r3;
+      }
+      kw += (uint32_t)popc(aw);
+    }
+    if (__any_sync(CYG_FULL, over) && lane == 0) e.scal(CYG_S_FLAGS) |= CYG_FL_ERR_BUSY;
+    __syncwarp();
+  }
+
+  static __device__ __forceinline__ void set_blocked_atomic(E& e, int eid, bool b) {
+    const int j = e.out2in(eid);
+    uint32_t* bo = e.blocked() + (eid >> 5);
+    uint32_t* bi = e.blocked_in() + (j >> 5);
+    if (b) { atomicOr(bo, 1u << (eid & 31)); atomicOr(bi, 1u << (j & 31)); }
+    else { atomicAnd(bo, ~(1u << (eid & 31))); atomicAnd(bi, ~(1u << (j & 31))); }
+  }
+
+  /* block (6) / unblock (9) one incident edge per listed active device, in listed order.
+   * A group of G lanes owns the env (the kernel uses G = 32; the first invalid pick of a round is typically 4-6
+   * lanes in, but sub-warp groups diverge from each other and were measured slower). */
+  template <int G>
+  static __device__ void flip(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
+    const int lane = lane_id(), lg = lane % G, gbase = lane - lg;
+    const uint32_t gm = (G == 32) ? CYG_FULL : (((1u << (G & 31)) - 1u) << gbase);
+    const bool want = atype == 9;
+    const int site = want ? SITE_UNBLOCK : SITE_BLOCK;
+    const double ds = (double)e.n->cfg.def_scale;
+    uint32_t act[W];
+    const int na = e.listed_active(a, act);
+    if (na == 0) return;
+    if (lg == 0) { cost += -0.5 * ds * na; e.defcost += 0.5 * ds * na; }
+    uint32_t cnt = 0;
+    if (e.n_extra() > 0) { /* envs with extra (hub-star) edges: the general sequential walk on one lane */
+      if (lg == 0) {
+        Stream st(site);
+        for (;;) {
+          int d = e.pop_lowest(act);
+          if (d < 0) break;
+          if (e.flip_incident(d, want, st)) cnt++;
+        }
+      }
+    } else {
+      int pos = 0;
+      uint32_t kbase = 0;
+      while (pos < na) { /* uniform within the group */
+        const int idx = pos + lg;
+        const bool valid = idx < na;
+        const int d = valid ? e.select_nth(act, idx) : 0;
+        const bool gen = valid && (((e.T(e.n->o_dmulti + 2 * d) | e.T(e.n->o_dmulti + 2 * d + 1)) >> 31) != 0);
+        const uint32_t genm = __ballot_sync(gm, gen) >> gbase;
+        if (genm & 1u) { /* > 2 multi-edges in one of the lists of the FIRST device of the round: general routine */
+          int f = 0;
+          if (lg == 0) {
+            Stream st(site);
+            st.skip(e.rng, kbase);
+            f = e.flip_incident_general(d, want, st) ? 1 : 0;
+          }
+          f = __shfl_sync(gm, f, gbase);
+          cnt += (uint32_t)f; kbase += (uint32_t)f; pos += 1;
+          __syncwarp(gm);
+          continue;
+        }
+        typename E::Pool P;
+        int total = 0;
+        if (valid && !gen) total = e.flip_pool(d, want, P);
+        const bool nonempty = total > 0;
+        const uint32_t nem = __ballot_sync(gm, nonempty) >> gbase;
+        int eid = 0, other = -1;
+        if (nonempty) {
+          uint32_t x = draw_at(e.rng, site, kbase + (uint32_t)popc(nem & lanes_below(lg)));
+          eid = e.flip_pick(P, (int)below(x, (uint32_t)total), other);
+        }
+        /* devices of this round as a mask; a pick whose far endpoint is the device of a HIGHER lane invalidates it */
+        uint32_t target = 0;
+        {
+          int rank = 0;
+          bool in_round = false;
+#pragma unroll
+          for (int w = 0; w < W; w++) {
+            const uint32_t mine = valid ? ((1u << (d & 31)) & eqmask(w, d >> 5)) : 0u;
+            const uint32_t rm = __reduce_or_sync(gm, mine);
+            if (other >= 0) {
+              const uint32_t ob = (1u << (other & 31)) & eqmask(w, other >> 5);
+              in_round = in_round || ((rm & ob) != 0);
+              rank += popc(rm & ((w < (other >> 5)) ? 0xFFFFFFFFu : 0u)) + popc(rm & (ob - 1u) & eqmask(w, other >> 5));
+            }
+          }
+          if (nonempty && in_round && rank > lg) target = 1u << rank;
+        }
+        uint32_t conf = __reduce_or_sync(gm, target) | genm;
+        int c = conf ? (__ffs((int)conf) - 1) : G;
+        const int nvalid = (na - pos) < G ? (na - pos) : G;
+        if (c > nvalid) c = nvalid;
+        if (nonempty && lg < c) set_blocked_atomic(e, eid, !want);
+        const uint32_t done = (uint32_t)popc(nem & lanes_below(c));
+        cnt += done; kbase += done; pos += c;
+        __syncwarp(gm);
+      }
+    }
+    if (lg == 0 && cnt) {
+      e.scal(want ? CYG_S_EADD : CYG_S_EBLK) += cnt;
+      dirty = true;
+    }
+    __syncwarp(gm);
+  }
+
+  static __device__ __forceinline__ bool is_heavy(int mode, int atype) {
+    return mode == CYG_MODE_DEFENDER && (atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9);
+  }
+
+  /* the deposit-type heavy defender actions (clean / revert / upgrade) of a plain set-form step, one warp per env;
+   * lane 0 owns cost / dirty / scalars */
+  static __device__ void defender(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
+    const int lane = lane_id();
+    const cyg_config& c = e.n->cfg;
+    const double ds = (double)c.def_scale;
+    if (atype == 1) {
+      uint32_t A[W];
+      e.clean_mask(a, A);
+      __syncwarp();
+      if (lane == 0) e.clean_scalar(A, ds, cost);
+      __syncwarp();
+      deposit(e, A, 0, c.default_high, 0);
+    } else if (atype == 3) {
+      const bool has = (e.scal(CYG_S_FLAGS) & CYG_FL_HAS_CKPT) != 0;
+      __syncwarp();
+      if (lane == 0) e.scal(CYG_S_REVERT)++;
+      if (has) {
+        uint32_t A[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) A[w] = e.m_valid(w);
+        deposit(e, A, 0, c.default_high, 0);
+        if (lane == 0) {
+#pragma unroll
+          for (int w = 0; w < W; w++) { e.pl(P_HASWL, w) = 0; e.pl(P_PT0, w) = 0; e.pl(P_PT0 + 1, w) = 0; e.pl(P_PT0 + 2, w) = 0; }
+          cost += -1.0 * a.n_dev * ds;
+          dirty = true;
+        }
+      }
+    } else if (atype == 4) {
+      uint32_t act[W], up[W];
+      const int na = e.listed_active(a, act);
+      if (na > 0) {
+        e.upgrade_mask(act, a.app_index, up);
+        if (lane == 0) cost += -1.0 * ds * na;
+        deposit(e, up, 0, c.default_high, 0);
+      }
+    }
+    __syncwarp();
+  }
+};
+
+}  // namespace cyg
+#endif

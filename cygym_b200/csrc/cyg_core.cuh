@@ -44,6 +44,13 @@
 
 namespace cyg {
 
+/* optional phase timestamps inside step() (profiling builds only: -DCYG_PHASE_TIMING) */
+#if defined(CYG_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define CYG_MARK(i) do { if (phase_t) phase_t[i] = clock64(); } while (0)
+#else
+#define CYG_MARK(i) do { } while (0)
+#endif
+
 /* draw sites: oracle/draws.py (each is one RNG call site of the reference) */
 enum {
   SITE_STALL = 1, SITE_BLOCK = 2, SITE_UNBLOCK = 3, SITE_ZDAY = 4, SITE_PROBE = 5, SITE_WL_SAMPLE = 6,
@@ -61,38 +68,38 @@ enum {
 #define CYG_CKI_REMOVED 0x40000000u /* internal checkpoint word, spare bit: Device.removed_before (never read by step) */
 #define CYG_MAX_W 4       /* M <= 128 for the bit-matrix kernels */
 
-/* ---- shared network tables + derived sizes (device pointers on the GPU) ---- */
+/* ---- shared network tables + derived sizes -------------------------------------------------
+ * All tables live in ONE blob of uint32 words (cyg_tables.h); the Net holds word OFFSETS into it.  The step
+ * kernel receives the Net by value as a __grid_constant__ parameter, so every size and offset below is a
+ * constant-bank operand, and reads the hot prefix of the blob [0, hot_words) from its shared-memory copy. */
 struct Net {
   cyg_config cfg;
   int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in;
-  const uint32_t* adj;        /* [M][W] out-neighbour bit rows (unique pairs; _outnbrs, volt:456-473) */
-  const uint32_t* adjT;       /* [M][W] in-neighbour bit rows (_innbrs) */
-  const uint32_t* mlo;        /* [M][W] bit v of row u: (mult(u,v)-1) & 1 */
-  const uint32_t* mhi;        /* [M][W] bit v of row u: (mult(u,v)-1) & 2 */
-  const uint32_t* mloT;       /* transposes of mlo / mhi */
-  const uint32_t* mhiT;
-  const int32_t* row_ptr;     /* [M+1] */
-  const uint16_t* col;        /* [E] */
-  const int32_t* in_ptr;      /* [M+1] */
-  const uint16_t* in_eid;     /* [E] base edge id of the j-th in-edge (ascending source) */
-  const uint16_t* out2in;     /* [E] inverse of in_eid */
-  const uint32_t* e_mlo;      /* [EW] bit e: (mult(e)-1) & 1, out-list order; e_mhi: & 2 */
-  const uint32_t* e_mhi;
-  const uint32_t* ei_mlo;     /* the same in in-list order */
-  const uint32_t* ei_mhi;
-  const uint32_t* dev_static; /* [M] CYG_ST_* */
-  const uint32_t* m_dc;       /* [W] masks over devices */
-  const uint32_t* m_server;
-  const uint32_t* m_reach;
-  const uint32_t* m_valid;    /* bits < M */
-  const uint32_t* m_rowmulti; /* device has an out-pair with multiplicity > 1 */
-  const uint32_t* m_incmulti; /* device has an incident (out or in) pair with multiplicity > 1 */
-  const uint32_t* m_napps;    /* [8][W] bit-planes of len(device.apps) */
-  const uint32_t* m_vuln;     /* [X][W] */
-  const float* os_val;        /* [M] */
-  const float* ver_val;       /* [M] */
-  const uint32_t* blob;       /* base of the table blob; [blob, blob + hot_words) is what a CTA stages in smem */
-  uint32_t hot_words;
+  double inv_M;               /* 1.0 / M */
+  uint32_t hot_words;         /* prefix of the blob that a CTA stages in shared memory */
+  /* hot tables */
+  uint32_t o_adj;             /* [M][W] out-neighbour bit rows (unique pairs; _outnbrs, volt:456-473) */
+  uint32_t o_dc, o_server, o_reach, o_valid; /* [W] masks over devices */
+  uint32_t o_rowmulti;        /* [W] device has an out-pair with multiplicity > 1 */
+  uint32_t o_incmulti;        /* [W] device has an incident (out or in) pair with multiplicity > 1 */
+  uint32_t o_napps;           /* [8][W] bit-planes of len(device.apps) */
+  uint32_t o_vuln;            /* [X][W] device has an app vulnerability in exploits[e].target */
+  uint32_t o_row_ptr;         /* [M+1] int32 */
+  uint32_t o_col;             /* [E] uint16 */
+  uint32_t o_in_ptr;          /* [M+1] int32 */
+  uint32_t o_in_eid;          /* [E] uint16: base edge id of the j-th in-edge (ascending source) */
+  uint32_t o_out2in;          /* [E] uint16: inverse of in_eid */
+  uint32_t o_in_src;          /* [E] uint16: source device of the j-th in-edge */
+  uint32_t o_static;          /* [M] CYG_ST_* */
+  uint32_t o_emlo, o_emhi;    /* [EW] bit e: (mult(e)-1) & 1 / & 2, out-list order */
+  uint32_t o_eimlo, o_eimhi;  /* the same in in-list order */
+  uint32_t o_dmulti;          /* [M][2] multi-edges of a device's out / in list: off1 | (m1-1)<<8 | off2<<10 | (m2-1)<<18, offsets
+                                 relative to the list start (0xFF = none); bit 31 = more than two (generic path) */
+  /* cold tables (global memory only) */
+  uint32_t o_mlo, o_mhi;      /* [M][W] bit v of row u: (mult(u,v)-1) & 1 / & 2 */
+  uint32_t o_adjT, o_mloT, o_mhiT; /* [M][W] in-neighbour rows and transposed multiplicity bits */
+  uint32_t o_os, o_ver;       /* [M] float: os_to_float(d.OS), float(d.version) */
+  const uint32_t* blob;       /* the blob in global (device) / host memory */
 };
 
 CYG_HD int popc(uint32_t x) {
@@ -116,6 +123,17 @@ CYG_HD uint32_t below(uint32_t x, uint32_t n) { /* floor(x*n/2^32): oracle/draws
   return (uint32_t)(((uint64_t)x * n) >> 32);
 #endif
 }
+CYG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { /* bits [sh, sh+32) of hi:lo, 0 <= sh < 32 */
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, (uint32_t)sh);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
+}
+/* all-ones when a == b.  Per-word updates are written branch-free (x |= bit & eqmask(w, idx)) on purpose: a
+ * conditional store inside an unrolled loop is merged by the compiler into ONE dynamically indexed access, which
+ * forces the whole array out of registers into local memory. */
+CYG_HD uint32_t eqmask(int a, int b) { return a == b ? 0xFFFFFFFFu : 0u; }
 CYG_HD uint32_t lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
 CYG_HD float u2f(uint32_t u) {
 #ifdef __CUDA_ARCH__
@@ -191,30 +209,76 @@ struct Stream {
   }
 };
 
-/* ---- per-env view over an internal record --------------------------------- */
-template <int W>
+/* ---- per-env view over an internal record ---------------------------------
+ * SM = true : the record and the hot tables are addressed as offsets into the kernel's dynamic shared memory
+ *             (every access is an LDS with a constant-bank offset);
+ * SM = false: plain pointers (host build, and the small kernels that work on records in global memory). */
+#ifdef __CUDACC__
+extern __shared__ __align__(128) uint32_t cyg_smem[];
+#endif
+template <int W, bool SM = false>
 struct Env {
   const Net* n;
-  uint32_t* rec;   /* the record (shared memory on the GPU) */
+  uint32_t* rec;   /* the record (SM: unused) */
+  const uint32_t* th; /* hot tables (SM: unused) */
+  const uint32_t* tc; /* cold tables: the blob in global / host memory */
+  uint32_t ro, to; /* SM: word offsets of the record / the hot tables inside cyg_smem */
   uint32_t* ckpt;  /* canonical per-device checkpoint words of this env [M] (global memory) */
   uint32_t* xtra;  /* extra (attacker hub-star) edges of this env [xcap] (global memory) */
   Rng rng;
   Stream stall;    /* SITE_STALL is shared by every group of a grouped step */
   double defcost, cleancost;
+  long long* phase_t = nullptr; /* profiling builds only */
 
-  CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t* xt, uint32_t env_id)
-      : n(net), rec(record), ckpt(ck), xtra(xt), stall(SITE_STALL), defcost(0.0), cleancost(0.0) {
+  CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t* xt, uint32_t env_id, uint32_t rec_off = 0,
+             uint32_t tab_off = 0)
+      : n(net), rec(record), th(net->blob), tc(net->blob), ro(rec_off), to(tab_off), ckpt(ck), xtra(xt), stall(SITE_STALL),
+        defcost(0.0), cleancost(0.0) {
     rng.k0 = (uint32_t)net->cfg.seed;
     rng.k1 = (uint32_t)(net->cfg.seed >> 32);
     rng.env = env_id;
     rng.epoch = 0;
   }
-  CYG_HD uint32_t& scal(int i) { return rec[i]; }
-  CYG_HD uint32_t& pl(int p, int w) { return rec[CYG_REC_PLANES + p * W + w]; }
-  CYG_HD uint32_t* blocked() { return rec + n->off_blocked; }
-  CYG_HD uint32_t* blocked_in() { return rec + n->off_blocked_in; }
+  /* record word i / hot-table word i */
+  CYG_HD uint32_t& R(int i) {
+#ifdef __CUDA_ARCH__
+    if (SM) return cyg_smem[ro + i];
+#endif
+    return rec[i];
+  }
+  CYG_HD uint32_t T(uint32_t i) const {
+#ifdef __CUDA_ARCH__
+    if (SM) return cyg_smem[to + i];
+#endif
+    return th[i];
+  }
+  CYG_HD const uint32_t* Tp(uint32_t i) const {
+#ifdef __CUDA_ARCH__
+    if (SM) return cyg_smem + to + i;
+#endif
+    return th + i;
+  }
+  CYG_HD int row_ptr(int i) const { return (int)T(n->o_row_ptr + i); }
+  CYG_HD int in_ptr(int i) const { return (int)T(n->o_in_ptr + i); }
+  CYG_HD int u16(uint32_t off, int i) const { return (int)((T(off + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu); }
+  CYG_HD int col(int e) const { return u16(n->o_col, e); }
+  CYG_HD int in_eid(int j) const { return u16(n->o_in_eid, j); }
+  CYG_HD int out2in(int e) const { return u16(n->o_out2in, e); }
+  CYG_HD int in_src(int j) const { return u16(n->o_in_src, j); }
+  CYG_HD uint32_t adj(int u, int w) const { return T(n->o_adj + u * W + w); }
+  CYG_HD uint32_t m_dc(int w) const { return T(n->o_dc + w); }
+  CYG_HD uint32_t m_server(int w) const { return T(n->o_server + w); }
+  CYG_HD uint32_t m_reach(int w) const { return T(n->o_reach + w); }
+  CYG_HD uint32_t m_valid(int w) const { return T(n->o_valid + w); }
+  CYG_HD uint32_t m_vuln(int e, int w) const { return T(n->o_vuln + e * W + w); }
+  CYG_HD bool devbit(uint32_t off, int d) const { return (T(off + (d >> 5)) >> (d & 31)) & 1u; }
+  CYG_HD uint32_t dev_static(int d) const { return T(n->o_static + d); }
+  CYG_HD uint32_t& scal(int i) { return R(i); }
+  CYG_HD uint32_t& pl(int p, int w) { return R(CYG_REC_PLANES + p * W + w); }
+  CYG_HD uint32_t* blocked() { return &R(n->off_blocked); }
+  CYG_HD uint32_t* blocked_in() { return &R(n->off_blocked_in); }
   CYG_HD uint32_t* extra() { return xtra; }
-  CYG_HD int n_extra() { return (int)(rec[CYG_S_PREV_X] >> 16); }
+  CYG_HD int n_extra() { return (int)(R(CYG_S_PREV_X) >> 16); }
 
   /* open a draw epoch (one per step / randomize / sample_action call) */
   CYG_HD void begin_epoch() {
@@ -286,14 +350,31 @@ struct Env {
       }
     }
   }
+  /* pop the lowest member of mask m[] (-1 when empty).  ONE loop over all W words keeps the lanes of a warp on the
+   * same loop body (a loop per word would be unrolled into W copies that the lanes enter at different times). */
+  CYG_HD int pop_lowest(uint32_t* m) {
+    int w0 = -1;
+    uint32_t x = 0;
+    for (int w = W - 1; w >= 0; w--) { bool nz = m[w] != 0; w0 = nz ? w : w0; x = nz ? m[w] : x; }
+    if (w0 < 0) return -1;
+    uint32_t lb = x & (0u - x);
+    for (int w = 0; w < W; w++) m[w] ^= lb & eqmask(w, w0);
+    return w0 * 32 + ctz(lb);
+  }
   /* r-th (0-based, ascending id) member of mask m[]; r < total popcount */
-  CYG_HD int select_nth(const uint32_t* m, int r) {
+  CYG_HD int select_nth(const uint32_t* m, int r) { /* branch-free over the words: ONE select_in_word */
+    int cum = 0, wsel = -1, base = 0;
+    uint32_t xw = 0;
     for (int w = 0; w < W; w++) {
       int c = popc(m[w]);
-      if (r < c) return w * 32 + select_in_word(m[w], r);
-      r -= c;
+      bool take = r >= cum && r < cum + c;
+      xw = take ? m[w] : xw;
+      wsel = take ? w : wsel;
+      base = take ? cum : base;
+      cum += c;
     }
-    return -1;
+    if (wsel < 0) return -1;
+    return wsel * 32 + select_in_word(xw, r - base);
   }
 
   /* ---- topology: base bit rows + blocked bitset + extra edges ---------------- */
@@ -312,7 +393,7 @@ struct Env {
     for (int w = 0; w < W; w++) bl[w] = 0;
     if (has_blk) {
       const uint32_t* b = blocked();
-      int a = n->row_ptr[u], z = n->row_ptr[u + 1];
+      int a = row_ptr(u), z = row_ptr(u + 1);
       for (int wi = a >> 5; wi <= (z - 1) >> 5 && a < z; wi++) {
         uint32_t x = b[wi];
         if (wi == (a >> 5)) x &= ~lowmask(a & 31);
@@ -320,13 +401,13 @@ struct Env {
         while (x) {
           int e = wi * 32 + ctz(x);
           x &= x - 1;
-          int v = n->col[e];
-          for (int w = 0; w < W; w++) if (w == (v >> 5)) bl[w] |= 1u << (v & 31);
+          int v = col(e);
+          for (int w = 0; w < W; w++) bl[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
         }
       }
     }
     for (int w = 0; w < W; w++) {
-      uint32_t r = n->adj[u * W + w];
+      uint32_t r = adj(u, w);
       out[w] = want_blocked ? (r & bl[w]) : (r & ~bl[w]);
     }
     int nx = n_extra();
@@ -336,7 +417,7 @@ struct Env {
       if ((int)(xe & CYG_X_IDMASK) != u) continue;
       if (((xe & CYG_X_BLOCKED) != 0) != want_blocked) continue;
       int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
-      for (int w = 0; w < W; w++) if (w == (v >> 5)) out[w] |= 1u << (v & 31);
+      for (int w = 0; w < W; w++) out[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
     }
   }
   /* in[] = in-neighbours (sources) of u whose edge has blocked-state == want_blocked */
@@ -345,21 +426,21 @@ struct Env {
     for (int w = 0; w < W; w++) bl[w] = 0;
     if (has_blk) {
       const uint32_t* b = blocked();
-      int a = n->in_ptr[u], z = n->in_ptr[u + 1];
+      int a = in_ptr(u), z = in_ptr(u + 1);
       int j = a;
       for (int w = 0; w < W; w++) { /* the j-th in-edge belongs to the j-th set bit of adjT[u] */
-        uint32_t r = n->adjT[u * W + w];
+        uint32_t r = tc[n->o_adjT + u * W + w];
         while (r) {
           int s = ctz(r);
           r &= r - 1;
-          int e = n->in_eid[j++];
+          int e = in_eid(j++);
           if ((b[e >> 5] >> (e & 31)) & 1u) bl[w] |= 1u << s;
         }
       }
       (void)z;
     }
     for (int w = 0; w < W; w++) {
-      uint32_t r = n->adjT[u * W + w];
+      uint32_t r = tc[n->o_adjT + u * W + w];
       in[w] = want_blocked ? (r & bl[w]) : (r & ~bl[w]);
     }
     int nx = n_extra();
@@ -369,20 +450,20 @@ struct Env {
       if ((int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK) != u) continue;
       if (((xe & CYG_X_BLOCKED) != 0) != want_blocked) continue;
       int s = (int)(xe & CYG_X_IDMASK);
-      for (int w = 0; w < W; w++) if (w == (s >> 5)) in[w] |= 1u << (s & 31);
+      for (int w = 0; w < W; w++) in[w] |= (1u << (s & 31)) & eqmask(w, s >> 5);
     }
   }
   CYG_HD int base_eid(int u, int v) { /* edge id of the base pair (u, v); the bit must be set in adj[u] */
-    int e = n->row_ptr[u];
+    int e = row_ptr(u);
     for (int w = 0; w < W; w++) {
-      uint32_t r = n->adj[u * W + w];
+      uint32_t r = adj(u, w);
       if (w < (v >> 5)) e += popc(r);
       else if (w == (v >> 5)) e += popc(r & lowmask(v & 31));
     }
     return e;
   }
   CYG_HD bool has_edge(int u, int v) { /* g.get_eid(u, v) != -1 (CyberDefenseEnv.py:752-770) */
-    if ((n->adj[u * W + (v >> 5)] >> (v & 31)) & 1u) return true;
+    if ((adj(u, (v >> 5)) >> (v & 31)) & 1u) return true;
     int nx = n_extra();
     const uint32_t* x = extra();
     uint32_t key = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
@@ -390,13 +471,13 @@ struct Env {
     return false;
   }
   CYG_HD void set_base_blocked(int e, bool b) { /* both orders of the bitset */
-    int j = n->out2in[e];
+    int j = out2in(e);
     if (b) { blocked()[e >> 5] |= 1u << (e & 31); blocked_in()[j >> 5] |= 1u << (j & 31); }
     else { blocked()[e >> 5] &= ~(1u << (e & 31)); blocked_in()[j >> 5] &= ~(1u << (j & 31)); }
   }
   /* flip the blocked flag of edge (u, v) */
   CYG_HD void set_edge_blocked(int u, int v, bool b) {
-    if ((n->adj[u * W + (v >> 5)] >> (v & 31)) & 1u) {
+    if ((adj(u, (v >> 5)) >> (v & 31)) & 1u) {
       set_base_blocked(base_eid(u, v), b);
       return;
     }
@@ -506,16 +587,19 @@ struct Env {
   /* busy_time = randint(0, high) for every device of mask a[] in ascending id order (one _stall draw each) */
   CYG_HD void stall_deposit(const uint32_t* a, int low, int high) {
     uint32_t range = (uint32_t)(high - low + 1);
-    for (int w = 0; w < W; w++) {
+    for (int w = 0; w < W; w++) { /* word by word: the word index stays a compile-time constant */
       uint32_t bits = a[w];
       if (!bits) continue;
       uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
       while (bits) {
-        int s = ctz(bits);
-        bits &= bits - 1;
+        uint32_t lb = bits & (0u - bits);
+        bits ^= lb;
         uint32_t v = (uint32_t)low + below(stall.next(rng), range);
         if (v > CYG_BUSY_MAX) { v = CYG_BUSY_MAX; scal(CYG_S_FLAGS) |= CYG_FL_ERR_BUSY; }
-        r0 |= (v & 1u) << s; r1 |= ((v >> 1) & 1u) << s; r2 |= ((v >> 2) & 1u) << s; r3 |= ((v >> 3) & 1u) << s;
+        r0 |= lb & (0u - (v & 1u));
+        r1 |= lb & (0u - ((v >> 1) & 1u));
+        r2 |= lb & (0u - ((v >> 2) & 1u));
+        r3 |= lb & (0u - ((v >> 3) & 1u));
       }
       uint32_t keep = ~a[w];
       pl(P_BUSY0, w) = (pl(P_BUSY0, w) & keep) | r0;
@@ -539,7 +623,7 @@ struct Env {
   /* device_indices as a set: the first n_dev bits of the mask (what the reference loop visits) */
   CYG_HD void listed(const Act& a, uint32_t* l) {
     int nl = 0;
-    for (int w = 0; w < W; w++) { l[w] = a.mask[w] & n->m_valid[w]; nl += popc(l[w]); }
+    for (int w = 0; w < W; w++) { l[w] = a.mask[w] & m_valid(w); nl += popc(l[w]); }
     if (a.n_dev >= nl) return;
     int keep = a.n_dev < 0 ? 0 : a.n_dev, seen = 0; /* inconsistent header: fewer entries than mask bits */
     for (int w = 0; w < W; w++) {
@@ -549,14 +633,16 @@ struct Env {
     }
   }
 
-  /* clean every listed device: volt_typhoon_env.py:996-1011 (and :676-690 in the grouped path), set form */
-  CYG_HD void clean_set(const Act& act, double ds, double& cost) {
-    uint32_t a[W];
+  /* clean every listed device: volt_typhoon_env.py:996-1011 (and :676-690 in the grouped path), set form.
+   * Three pieces so that the kernel can run the draw-bearing part with a whole warp: */
+  CYG_HD void clean_mask(const Act& act, uint32_t* a) { /* the devices that get cleaned */
+    listed(act, a);
+    for (int w = 0; w < W; w++) a[w] &= ~pl(P_NYA, w) & ~pl(P_OWNED, w);
+  }
+  CYG_HD void clean_scalar(const uint32_t* a, double ds, double& cost) { /* rewards, discovery flags, state wipe */
     int nc = 0, nu = 0;
     uint32_t disc = 0;
-    listed(act, a);
     for (int w = 0; w < W; w++) {
-      a[w] &= ~pl(P_NYA, w) & ~pl(P_OWNED, w);
       nc += popc(a[w] & pl(P_COMP, w));
       nu += popc(a[w] & ~pl(P_COMP, w));
       for (int k = 0; k < n->ncby; k++) if (pl(P_CBY0 + k, w) & a[w]) disc |= 1u << k;
@@ -566,7 +652,12 @@ struct Env {
     defcost += (nc * 0.3 + nu * 0.01) * ds;
     scal(CYG_S_FLAGS) |= disc << CYG_FL_DISC_SHIFT; /* exp.discovered = True */
     wipe(a, true);
-    stall_deposit(a, 0, n->cfg.default_high);
+  }
+  CYG_HD void clean_set(const Act& act, double ds, double& cost) {
+    uint32_t a[W];
+    clean_mask(act, a);
+    clean_scalar(a, ds, cost);
+    stall_deposit(a, 0, n->cfg.default_high); /* busy_time = randint(0, high) each */
   }
   CYG_HD void clean_device(int d, double ds, double& cost) { /* same, one device (explicit order form) */
     if (bit(P_OWNED, d)) return;
@@ -597,7 +688,7 @@ struct Env {
       scal(CYG_S_REVERT)++;
       if (scal(CYG_S_FLAGS) & CYG_FL_HAS_CKPT) { /* every device: busy = randint(0, high), workload dropped */
         uint32_t all[W];
-        for (int w = 0; w < W; w++) all[w] = n->m_valid[w];
+        for (int w = 0; w < W; w++) all[w] = m_valid(w);
         stall_deposit(all, 0, c.default_high);
         for (int w = 0; w < W; w++) { pl(P_HASWL, w) = 0; pl(P_PT0, w) = 0; pl(P_PT0 + 1, w) = 0; pl(P_PT0 + 2, w) = 0; }
         cost += -1.0 * a.n_dev * ds;
@@ -623,7 +714,7 @@ struct Env {
         if (bit(P_COMP, d)) k |= CYG_CK_COMP;
         if (bit(P_KNOWN, d)) k |= CYG_CK_KNOWN;
         if (bit(P_NYA, d)) k |= CYG_CK_NYA;
-        if (n->dev_static[d] & CYG_ST_REACH) k |= CYG_CK_REACH;
+        if (dev_static(d) & CYG_ST_REACH) k |= CYG_CK_REACH;
         if (bit(P_HASWL, d)) k |= CYG_CK_HASWL | (field(P_PT0, 3, d) << CYG_DEV_PT_SHIFT);
         k |= busy(d) << CYG_DEV_BUSY_SHIFT;
         k |= cby(d) << CYG_DEV_CBY_SHIFT;
@@ -655,8 +746,8 @@ struct Env {
     uint32_t o[W], in[W];
     out_row(d, has_blk, want, o);
     in_row(d, has_blk, want, in);
-    bool multi = ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u) != 0;
-    const uint32_t *lo = n->mlo + d * W, *hi = n->mhi + d * W, *loT = n->mloT + d * W, *hiT = n->mhiT + d * W;
+    bool multi = devbit(n->o_incmulti, d);
+    const uint32_t *lo = tc + n->o_mlo + d * W, *hi = tc + n->o_mhi + d * W, *loT = tc + n->o_mloT + d * W, *hiT = tc + n->o_mhiT + d * W;
     int to = weight_below(o, lo, hi, multi, 32 * W);
     int ti = weight_below(in, loT, hiT, multi, 32 * W);
     int total = to + ti;
@@ -674,54 +765,119 @@ struct Env {
   /* Same pick in EDGE-ID space when the env has no extra edges: the out-edges of d are the contiguous bits
    * [row_ptr[d], row_ptr[d+1]) of the blocked bitset (ascending neighbour id == pool order) and its in-edges the
    * bits [in_ptr[d], in_ptr[d+1]) of the in-order copy (ascending source id). */
-  CYG_HD int range_weight(const uint32_t* b, uint32_t flipw, int a, int z, bool multi, const uint32_t* lo, const uint32_t* hi) {
+  /* W-word window of bitset b[0, nw): bits [a, a + len) (len <= 32 W), XORed with flipw, zero beyond len */
+  CYG_HD void window(const uint32_t* b, int nw, int a, int len, uint32_t flipw, uint32_t* x) {
+    int wa = a >> 5, sh = a & 31;
+    uint32_t lo = wa < nw ? b[wa] : 0u;
+    for (int q = 0; q < W; q++) {
+      uint32_t hi = (wa + q + 1 < nw) ? b[wa + q + 1] : 0u;
+      uint32_t v = funnel_r(lo, hi, sh) ^ flipw;
+      int rem = len - 32 * q;
+      x[q] = rem <= 0 ? 0u : (rem >= 32 ? v : (v & lowmask(rem)));
+      lo = hi;
+    }
+  }
+  CYG_HD int wrank(const uint32_t* x, int pos) { /* set bits of the window below position pos */
     int c = 0;
-    if (a >= z) return 0;
-    for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
-      uint32_t x = b[wi] ^ flipw;
-      if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-      if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-      c += popc(x);
-      if (multi) c += popc(x & lo[wi]) + 2 * popc(x & hi[wi]);
+    for (int q = 0; q < W; q++) {
+      int rem = pos - 32 * q;
+      c += rem <= 0 ? 0 : popc(rem >= 32 ? x[q] : (x[q] & lowmask(rem)));
     }
     return c;
   }
-  CYG_HD int range_select(const uint32_t* b, uint32_t flipw, int a, int z, bool multi, const uint32_t* lo, const uint32_t* hi, int r) {
-    for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
-      uint32_t x = b[wi] ^ flipw;
-      if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-      if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-      int cnt = popc(x);
-      if (multi) cnt += popc(x & lo[wi]) + 2 * popc(x & hi[wi]);
-      if (r < cnt) {
-        if (!multi || ((x & (lo[wi] | hi[wi])) == 0)) return wi * 32 + select_in_word(x, r);
-        while (x) {
-          int sb = ctz(x);
-          x &= x - 1;
-          int wt = 1 + (int)((lo[wi] >> sb) & 1u) + 2 * (int)((hi[wi] >> sb) & 1u);
-          if (r < wt) return wi * 32 + sb;
-          r -= wt;
+  CYG_HD bool wbit(const uint32_t* x, int pos) {
+    uint32_t v = 0;
+    for (int q = 0; q < W; q++) v |= x[q] & eqmask(q, pos >> 5);
+    return (v >> (pos & 31)) & 1u;
+  }
+  /* multiplicity-weighted pool over a window: dm = packed multi-edge entries of the list (Net::o_dmulti) */
+  CYG_HD int wweight(const uint32_t* x, uint32_t dm) {
+    int c = 0;
+    for (int q = 0; q < W; q++) c += popc(x[q]);
+    for (int k = 0; k < 2; k++) {
+      int off = (int)((dm >> (10 * k)) & 0xFFu);
+      if (off != 0xFF && wbit(x, off)) c += (int)((dm >> (8 + 10 * k)) & 3u);
+    }
+    return c;
+  }
+  /* window position of the pool element that holds weight unit r (no early exits: the lanes of a warp stay together) */
+  CYG_HD int wselect(const uint32_t* x, uint32_t dm, int r) {
+    int extra_before = 0, direct = -1;
+    if ((dm & 0x3FFFFu) != (0xFFu | (0xFFu << 10))) { /* the list has multi-edges */
+      bool stop = false;
+      for (int k = 0; k < 2; k++) {
+        int off = (int)((dm >> (10 * k)) & 0xFFu);
+        int ex = (int)((dm >> (8 + 10 * k)) & 3u);
+        bool valid = off != 0xFF && !stop && direct < 0 && wbit(x, off & 0x7F);
+        int lo = wrank(x, off) + extra_before;
+        if (valid) {
+          if (r < lo) stop = true;
+          else if (r <= lo + ex) direct = off;
+          else extra_before += ex;
         }
       }
-      r -= cnt;
     }
-    return -1;
+    int pos = select_nth(x, r - extra_before);
+    return direct >= 0 ? direct : pos;
+  }
+  /* the pool of one device: windows over its out-edges and in-edges whose blocked flag == want */
+  struct Pool {
+    int a, c0, to, ti;
+    uint32_t dmo, dmi;
+    uint32_t xo[W], xi[W];
+  };
+  CYG_HD bool flip_needs_general(int d) { /* extra edges in this env, or > 2 multi-edges in one of d's lists */
+    return n_extra() > 0 || ((T(n->o_dmulti + 2 * d) | T(n->o_dmulti + 2 * d + 1)) >> 31);
+  }
+  CYG_HD int flip_pool(int d, bool want, Pool& P) { /* returns the multiplicity-weighted pool size */
+    P.dmo = T(n->o_dmulti + 2 * d); P.dmi = T(n->o_dmulti + 2 * d + 1);
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
+    P.a = row_ptr(d); P.c0 = in_ptr(d);
+    window(blocked(), n->EW, P.a, row_ptr(d + 1) - P.a, flipw, P.xo);
+    window(blocked_in(), n->EW, P.c0, in_ptr(d + 1) - P.c0, flipw, P.xi);
+    P.to = wweight(P.xo, P.dmo); P.ti = wweight(P.xi, P.dmi);
+    return P.to + P.ti;
+  }
+  /* pool element holding weight unit r: returns the base edge id, `other` = the far endpoint of that edge */
+  CYG_HD int flip_pick(const Pool& P, int r, int& other) {
+    const bool from_out = r < P.to;
+    uint32_t xs[W];
+    for (int q = 0; q < W; q++) xs[q] = from_out ? P.xo[q] : P.xi[q];
+    int pos = wselect(xs, from_out ? P.dmo : P.dmi, from_out ? r : r - P.to);
+    int j_in = P.c0 + (from_out ? 0 : pos);
+    int e = from_out ? P.a + pos : in_eid(j_in);
+    other = from_out ? col(e) : in_src(j_in);
+    return e;
   }
   CYG_HD bool flip_incident(int d, bool want, Stream& st) {
-    if (n_extra() > 0) return flip_incident_general(d, want, st);
-    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
-    const bool multi = ((n->m_incmulti[d >> 5] >> (d & 31)) & 1u) != 0;
-    const int a = n->row_ptr[d], z = n->row_ptr[d + 1], c0 = n->in_ptr[d], c1 = n->in_ptr[d + 1];
-    int to = range_weight(blocked(), flipw, a, z, multi, n->e_mlo, n->e_mhi);
-    int ti = range_weight(blocked_in(), flipw, c0, c1, multi, n->ei_mlo, n->ei_mhi);
-    int total = to + ti;
+    if (flip_needs_general(d)) return flip_incident_general(d, want, st);
+    Pool P;
+    int total = flip_pool(d, want, P);
     if (total == 0) return false;
-    int r = (int)below(st.next(rng), (uint32_t)total);
-    int e;
-    if (r < to) e = range_select(blocked(), flipw, a, z, multi, n->e_mlo, n->e_mhi, r);
-    else e = n->in_eid[range_select(blocked_in(), flipw, c0, c1, multi, n->ei_mlo, n->ei_mhi, r - to)];
+    int other;
+    int e = flip_pick(P, (int)below(st.next(rng), (uint32_t)total), other);
     set_base_blocked(e, !want);
     return true;
+  }
+
+  /* devices of act[] with app_index < len(device.apps) (volt:1014-1016): bit-sliced compare over the napps planes */
+  CYG_HD void upgrade_mask(const uint32_t* act, int app_index, uint32_t* up) {
+    for (int w = 0; w < W; w++) {
+      uint32_t gt = 0, eq = 0xFFFFFFFFu;
+      for (int bb = 7; bb >= 0; bb--) {
+        uint32_t nb = T(n->o_napps + bb * W + w), ab = ((app_index >> bb) & 1) ? 0xFFFFFFFFu : 0u;
+        gt |= eq & nb & ~ab;
+        eq &= ~(nb ^ ab);
+      }
+      up[w] = (app_index >= 0 && app_index < 256) ? (act[w] & gt) : 0u;
+    }
+  }
+  /* listed (first n_dev mask bits) & active */
+  CYG_HD int listed_active(const Act& a, uint32_t* act) {
+    int na = 0;
+    listed(a, act);
+    for (int w = 0; w < W; w++) { act[w] &= ~pl(P_NYA, w); na += popc(act[w]); }
+    return na;
   }
 
   /* per-device defender actions when device_indices is a SET (ascending, duplicate-free): the loop of
@@ -731,26 +887,14 @@ struct Env {
     double ds = (double)c.def_scale;
     if (atype == 1) { clean_set(a, ds, cost); return; }
     uint32_t act[W];
-    int na = 0;
-    listed(a, act);
-    for (int w = 0; w < W; w++) { act[w] &= ~pl(P_NYA, w); na += popc(act[w]); }
+    int na = listed_active(a, act);
     if (na == 0) return;
     switch (atype) {
       case 4: { /* volt:1013-1018 */
         cost += -1.0 * ds * na;
-        if (a.app_index >= 0 && a.app_index < 256) { /* devices with app_index < len(apps): bit-sliced compare */
-          uint32_t up[W];
-          for (int w = 0; w < W; w++) {
-            uint32_t gt = 0, eq = 0xFFFFFFFFu;
-            for (int bb = 7; bb >= 0; bb--) {
-              uint32_t nb = n->m_napps[bb * W + w], ab = ((a.app_index >> bb) & 1) ? 0xFFFFFFFFu : 0u;
-              gt |= eq & nb & ~ab;
-              eq &= ~(nb ^ ab);
-            }
-            up[w] = act[w] & gt;
-          }
-          stall_deposit(up, 0, c.default_high);
-        }
+        uint32_t up[W];
+        upgrade_mask(act, a.app_index, up);
+        stall_deposit(up, 0, c.default_high);
       } break;
       case 5: /* volt:1020-1069 with an untrained detector: every prediction is "D" */
         scal(CYG_S_SCAN) += (uint32_t)na;
@@ -765,13 +909,10 @@ struct Env {
         cost += -0.5 * ds * na;
         defcost += 0.5 * ds * na;
         uint32_t cnt = 0;
-        for (int w = 0; w < W; w++) {
-          uint32_t bits = act[w];
-          while (bits) {
-            int d = w * 32 + ctz(bits);
-            bits &= bits - 1;
-            if (flip_incident(d, atype == 9, st)) cnt++;
-          }
+        for (;;) {
+          int d = pop_lowest(act);
+          if (d < 0) break;
+          if (flip_incident(d, atype == 9, st)) cnt++;
         }
         if (cnt) { scal(atype == 6 ? CYG_S_EBLK : CYG_S_EADD) += cnt; dirty = true; }
       } break;
@@ -819,7 +960,7 @@ struct Env {
         case 1: clean_device(d, ds, cost); break;
         case 4:
           cost += -1.0 * ds;
-          if (a.app_index >= 0 && a.app_index < (int)((n->dev_static[d] >> CYG_ST_NAPPS_SHIFT) & 0xFFu))
+          if (a.app_index >= 0 && a.app_index < (int)((dev_static(d) >> CYG_ST_NAPPS_SHIFT) & 0xFFu))
             set_busy(d, stall_draw(0, c.default_high));
           break;
         case 5:
@@ -876,10 +1017,10 @@ struct Env {
   /* ---- attacker actions (volt:1126-1202) ---- */
   /* unblocked out-neighbours of s (base row minus blocked pairs, plus unblocked extra edges) */
   CYG_HD void live_row(int s, bool has_blk, int nx, uint32_t* row) {
-    for (int w = 0; w < W; w++) row[w] = n->adj[s * W + w];
+    for (int w = 0; w < W; w++) row[w] = adj(s, w);
     if (has_blk) {
       const uint32_t* b = blocked();
-      int a = n->row_ptr[s], z = n->row_ptr[s + 1];
+      int a = row_ptr(s), z = row_ptr(s + 1);
       if (a < z) {
         for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
           uint32_t x = b[wi];
@@ -888,8 +1029,8 @@ struct Env {
           while (x) {
             int e = wi * 32 + ctz(x);
             x &= x - 1;
-            int v = n->col[e];
-            for (int w = 0; w < W; w++) if (w == (v >> 5)) row[w] &= ~(1u << (v & 31));
+            int v = col(e);
+            for (int w = 0; w < W; w++) row[w] &= ~((1u << (v & 31)) & eqmask(w, v >> 5));
           }
         }
       }
@@ -900,7 +1041,7 @@ struct Env {
         uint32_t xe = x[j];
         if ((int)(xe & CYG_X_IDMASK) != s || (xe & CYG_X_BLOCKED)) continue;
         int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
-        for (int w = 0; w < W; w++) if (w == (v >> 5)) row[w] |= 1u << (v & 31);
+        for (int w = 0; w < W; w++) row[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
       }
     }
   }
@@ -926,37 +1067,88 @@ struct Env {
         }
         if (!(raw >= 0 && raw < c.n_exploits)) continue; /* ids are strings: an int never matches (volt:1141) */
         uint32_t kv[W], dcby[W]; /* known & vulnerable to this exploit; compromised_by additions */
-        for (int w = 0; w < W; w++) { kv[w] = known[w] & n->m_vuln[raw * W + w]; dcby[w] = 0; }
-        for (int sw = 0; sw < W; sw++) {
-          uint32_t sbits = src[sw];
-          const uint32_t dcw = n->m_dc[sw], mlw = n->m_rowmulti[sw];
-          while (sbits) {
-            const int sb = ctz(sbits);
-            const int s = sw * 32 + sb;
-            sbits &= sbits - 1;
-            uint32_t row[W];
-            live_row(s, has_blk, nx, row);
-            const bool is_dc = ((dcw >> sb) & 1u) != 0;
-            /* first neighbour that is hit: DC source -> any; reachable_by_attacker; or not yet compromised,
-               known and vulnerable (volt:1163-1183) */
+        for (int w = 0; w < W; w++) { kv[w] = known[w] & m_vuln(raw, w); dcby[w] = 0; }
+        uint32_t todo[W];
+        for (int w = 0; w < W; w++) todo[w] = src[w];
+        {
+          for (;;) {
+            const int s = pop_lowest(todo);
+            if (s < 0) break;
+            const bool is_dc = devbit(n->o_dc, s);
+            const uint32_t dmo = T(n->o_dmulti + 2 * s);
             int vw = -1;
-            uint32_t cand_w = 0;
-            for (int w = W - 1; w >= 0; w--) {
-              uint32_t cand = is_dc ? row[w] : (row[w] & (n->m_reach[w] | (~comp[w] & kv[w])));
-              if (cand) { vw = w; cand_w = cand; }
+            uint32_t hitbit = 0;
+            int cnt; /* hops logged before the hit */
+            if (nx > 0 || (dmo >> 31)) {
+              /* general form: materialise the unblocked row (extra edges, > 2 multi-edges in the row) */
+              uint32_t row[W];
+              live_row(s, has_blk, nx, row);
+              uint32_t cand_w = 0;
+              for (int w = W - 1; w >= 0; w--) {
+                uint32_t cand = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
+                bool nz = cand != 0;
+                vw = nz ? w : vw;
+                cand_w = nz ? cand : cand_w;
+              }
+              hitbit = cand_w & (0u - cand_w);
+              cnt = 0;
+              const bool multi = devbit(n->o_rowmulti, s);
+              for (int w = 0; w < W; w++) {
+                uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
+                uint32_t m = row[w] & bm;
+                cnt += popc(m);
+                if (multi) cnt += popc(m & tc[n->o_mlo + s * W + w]) + 2 * popc(m & tc[n->o_mhi + s * W + w]);
+              }
+            } else {
+              /* edge-id form: the pair (s, v) is bit row_ptr[s] + rank of v in adj[s] of the blocked bitset */
+              uint32_t row[W], cand[W];
+              const int a = row_ptr(s);
+              int deg = 0;
+              for (int w = 0; w < W; w++) {
+                row[w] = adj(s, w);
+                deg += popc(row[w]);
+                cand[w] = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
+              }
+              int nb = deg; /* pairs walked before the hit (all of them when nothing is hit) */
+              const uint32_t* b = blocked();
+              for (;;) { /* first candidate whose edge is not blocked (volt:1157-1159) */
+                int w0 = -1;
+                uint32_t cw = 0;
+                for (int w = W - 1; w >= 0; w--) { bool nz = cand[w] != 0; w0 = nz ? w : w0; cw = nz ? cand[w] : cw; }
+                if (w0 < 0) break;
+                uint32_t lb = cw & (0u - cw);
+                int rk = 0;
+                for (int w = 0; w < W; w++) rk += popc(row[w] & ((w < w0 ? 0xFFFFFFFFu : 0u) | ((lb - 1u) & eqmask(w, w0))));
+                int e = a + rk;
+                if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) {
+                  for (int w = 0; w < W; w++) cand[w] ^= lb & eqmask(w, w0);
+                  continue;
+                }
+                vw = w0; hitbit = lb; nb = rk;
+                break;
+              }
+              cnt = nb;
+              if (has_blk && nb > 0) { /* minus the blocked pairs among the first nb of the row */
+                uint32_t xb[W];
+                window(b, n->EW, a, nb, 0u, xb);
+                for (int q = 0; q < W; q++) cnt -= popc(xb[q]);
+              }
+              for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged (volt:1161) */
+                int off = (int)((dmo >> (10 * k)) & 0xFFu);
+                if (off == 0xFF || off >= nb) continue;
+                int e = a + off;
+                if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
+                cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
+              }
             }
             /* log_communication once per hop walked (volt:1161): all repeats of the neighbours before the hit, +1 */
-            uint32_t hitbit = cand_w & (0u - cand_w);
-            int cnt = 0;
-            const bool multi = ((mlw >> sb) & 1u) != 0;
-            for (int w = 0; w < W; w++) {
-              uint32_t m = vw < 0 ? row[w] : (w < vw ? row[w] : (w == vw ? (row[w] & (hitbit - 1u)) : 0u));
-              cnt += popc(m);
-              if (multi) cnt += popc(m & n->mlo[s * W + w]) + 2 * popc(m & n->mhi[s * W + w]);
-            }
             logs += (uint32_t)cnt + (vw >= 0 ? 1u : 0u);
             if (vw >= 0) {
-              for (int w = 0; w < W; w++) if (w == vw) { comp[w] |= hitbit; if (is_dc) dcby[w] |= hitbit; }
+              for (int w = 0; w < W; w++) {
+                uint32_t hb = hitbit & eqmask(w, vw);
+                comp[w] |= hb;
+                dcby[w] |= is_dc ? hb : 0u;
+              }
             }
           }
         }
@@ -1007,8 +1199,8 @@ struct Env {
     uint32_t cand[W];
     int nc = 0;
     for (int w = 0; w < W; w++) {
-      uint32_t t = n->m_valid[w] & ~pl(P_NYA, w) & ~pl(P_HASWL, w) & ~busy_nz(w);
-      t &= server ? n->m_server[w] : ~n->m_server[w];
+      uint32_t t = m_valid(w) & ~pl(P_NYA, w) & ~pl(P_HASWL, w) & ~busy_nz(w);
+      t &= server ? m_server(w) : ~m_server(w);
       cand[w] = t;
       nc += popc(t);
     }
@@ -1016,7 +1208,7 @@ struct Env {
     for (int j = 0; j < k; j++) { /* random.sample: pop the r-th remaining candidate (CDSimulator.py:298) */
       int r = (int)below(ssamp.next(rng), (uint32_t)(nc - j));
       int did = select_nth(cand, r);
-      for (int w = 0; w < W; w++) if (w == (did >> 5)) cand[w] &= ~(1u << (did & 31));
+      for (int w = 0; w < W; w++) cand[w] &= ~((1u << (did & 31)) & eqmask(w, did >> 5));
       uint32_t xt = stri.next(rng); /* CDSimulator.py:308 */
       int pt = 1;
       for (int v = 0; v < 8; v++) pt += xt >= c.tri_tab[v];
@@ -1029,15 +1221,25 @@ struct Env {
     const cyg_config& c = n->cfg;
     int n_active = 0, idle = 0, free_s = 0;
     for (int w = 0; w < W; w++) {
-      uint32_t act = n->m_valid[w] & ~pl(P_NYA, w);
+      uint32_t act = m_valid(w) & ~pl(P_NYA, w);
       uint32_t idl = act & ~busy_nz(w) & ~pl(P_HASWL, w);
       n_active += popc(act);
       idle += popc(idl);
-      free_s += popc(idl & n->m_server[w]);
+      free_s += popc(idl & m_server(w));
     }
     int free_c = idle - free_s;
     /* _arrival_period (volt:141-145) */
-    int period = (int)(c.wl_period_base + 0.5 * sqrt((double)(n_active > 1 ? n_active : 1)));
+    int period; /* int(base + 0.5 * sqrt(max(1, n_active))) == base + max{k : 4k^2 <= n} for base >= 0 */
+    {
+      int na1 = n_active > 1 ? n_active : 1;
+      if (c.wl_period_base >= 0) {
+        int k = 0;
+        while (4 * (k + 1) * (k + 1) <= na1) k++;
+        period = c.wl_period_base + k;
+      } else {
+        period = (int)(c.wl_period_base + 0.5 * sqrt((double)na1));
+      }
+    }
     if (period < 10) period = 10;
     if (period > c.wl_period_max) period = c.wl_period_max;
     if (scal(CYG_S_STEP) % (uint32_t)period != 0) return;
@@ -1069,14 +1271,14 @@ struct Env {
   CYG_HD void evolve_network() {
     const cyg_config& c = n->cfg;
     if (!(scal(CYG_S_FLAGS) & CYG_FL_SETS_INIT)) { /* :654-659 */
-      for (int w = 0; w < W; w++) pl(P_ACTSET, w) = n->m_valid[w] & ~pl(P_NYA, w);
+      for (int w = 0; w < W; w++) pl(P_ACTSET, w) = m_valid(w) & ~pl(P_NYA, w);
       scal(CYG_S_FLAGS) |= CYG_FL_SETS_INIT;
     }
     int n_act = count(P_ACTSET);
     Stream sp(SITE_EV_POISSON), sadd(SITE_EV_ADD), spick(SITE_EV_PICK), satt(SITE_EV_ATT);
     uint32_t xp = sp.next(rng); /* :668 */
-    int num_events = 0;
-    for (int j = 0; j < 16; j++) num_events += xp >= c.poisson_tab[j];
+    int num_events = 0; /* #{j : xp >= tab[j]}; the table is ascending */
+    while (num_events < 16 && xp >= c.poisson_tab[num_events]) num_events++;
     int floor_n = c.num_of_device > c.min_network_size ? c.num_of_device : c.min_network_size;
     for (int ev = 0; ev < num_events; ev++) {
       uint32_t xa = sadd.next(rng); /* :679 */
@@ -1084,7 +1286,7 @@ struct Env {
         int n_inact = n->M - n_act;
         if (n_inact > 0) {
           uint32_t m[W];
-          for (int w = 0; w < W; w++) m[w] = n->m_valid[w] & ~pl(P_ACTSET, w);
+          for (int w = 0; w < W; w++) m[w] = m_valid(w) & ~pl(P_ACTSET, w);
           int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)n_inact)); /* :675 */
           clrb(P_NYA, node);
           setb(P_ACTSET, node);
@@ -1133,7 +1335,7 @@ struct Env {
     for (int w = 0; w < W; w++) {
       uint32_t m = pl(P_COMP, w) & ~pl(P_NYA, w) & ~pl(P_OWNED, w);
       a += popc(m);
-      b += popc(m & n->m_dc[w]);
+      b += popc(m & m_dc(w));
     }
     n_comp = a; n_comp_dc = b;
   }
@@ -1156,25 +1358,37 @@ struct Env {
     return atype;
   }
 
-  CYG_HD int step(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
-                  size_t order_gs, int G, uint32_t flags, float* raw_out, float* shaped_out, int32_t* done_out,
-                  uint32_t* pre_masks) {
-    const cyg_config& c = n->cfg;
-    const bool grouped = (flags & CYG_STEP_GROUPED) != 0;
-    const bool skip_work = (flags & CYG_STEP_SKIP_WORK) != 0;
+  /* The step in three pieces (the kernel may run the middle one with a whole warp per env):
+   * step_pre : open the epoch, resolve the executed action type, busy tick (volt:847-908)
+   * step_act : the action(s) (volt:913-1202; grouped: :612-692, :607-610)
+   * step_post: work, arrivals, reward, counters, evolve_network (volt:1207-1333) */
+  CYG_HD int step_pre(const uint32_t* hdr, uint32_t flags) {
     begin_epoch();
-    double cost = 0.0;
-    bool dirty = false;
+    CYG_MARK(0);
+    if (flags & CYG_STEP_GROUPED) return 0;
+    int atype = exec_type(n->cfg, hdr[0]);
+    tick_busyset(); /* volt:904-908 */
+    CYG_MARK(1);
+    return atype;
+  }
+  CYG_HD void load_costs() {
     defcost = (double)u2f(scal(CYG_S_DEFCOST));
     cleancost = (double)u2f(scal(CYG_S_CLEANCOST));
+  }
+  CYG_HD void store_costs() {
+    scal(CYG_S_DEFCOST) = f2u((float)defcost);
+    scal(CYG_S_CLEANCOST) = f2u((float)cleancost);
+  }
+  CYG_HD int step_act(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
+                      size_t order_gs, int G, uint32_t flags, int atype, double& cost, bool& dirty) {
+    const cyg_config& c = n->cfg;
+    const bool grouped = (flags & CYG_STEP_GROUPED) != 0;
+    load_costs();
     Act a;
     decode(hdr, mask, order, a);
     const int mode = a.mode;
-    int atype = 0;
     if (!grouped) {
-      atype = exec_type(c, hdr[0]);
       if (a.atype == -1000) { a.n_dev = 0; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
-      tick_busyset(); /* volt:904-908 */
       if (mode == CYG_MODE_DEFENDER) {
         defender_meta(a, atype, false, cost, dirty);
         if (atype == 1 || atype == 4 || atype == 5 || atype == 6 || atype == 7 || atype == 9 || atype == 12 || atype == 13)
@@ -1183,6 +1397,7 @@ struct Env {
         attacker_act(a, atype, cost);
       }
     } else {
+      atype = 0;
       for (int g = 0; g < G; g++) { /* _step_apply_only (volt:612-692) */
         Act ga;
         decode(hdr + g * hdr_gs, mask + g * mask_gs, order ? order + g * order_gs : (const uint16_t*)0, ga);
@@ -1210,18 +1425,26 @@ struct Env {
       }
       tick_all(); /* _tick_busy_time_once (volt:607-610) */
     }
-    scal(CYG_S_DEFCOST) = f2u((float)defcost);
-    scal(CYG_S_CLEANCOST) = f2u((float)cleancost);
-
+    CYG_MARK(2);
+    store_costs();
+    return atype;
+  }
+  CYG_HD void step_post(int mode, double cost, bool dirty, uint32_t flags, float* raw_out, float* shaped_out,
+                        int32_t* done_out, uint32_t* pre_masks) {
+    const cyg_config& c = n->cfg;
+    const bool grouped = (flags & CYG_STEP_GROUPED) != 0;
+    const bool skip_work = (flags & CYG_STEP_SKIP_WORK) != 0;
     /* work, arrivals, reward, counters, evolve (volt:1207-1333) */
     int cur_work = 0;
     if (!skip_work || grouped) {
       cur_work = workload_advance();
+      CYG_MARK(3);
       arrivals_if_due();
     }
     double def_work = (double)c.work_scale * cur_work;
     int n_comp, n_comp_dc;
     count_comp(n_comp, n_comp_dc);
+    CYG_MARK(4);
     if (!grouped) scal(CYG_S_COMPCNT) += (uint32_t)n_comp; /* volt:1267-1270; absent from step_grouped */
     double raw, shaped;
     if (mode == CYG_MODE_DEFENDER) {
@@ -1229,15 +1452,15 @@ struct Env {
       shaped = raw;
     } else {
       raw = cost + (double)c.comp_scale * (n_comp + 10 * n_comp_dc);
-      double Md = (double)n->M;
-      double phi = (double)n_comp / Md;
+      double phi = (double)n_comp * n->inv_M; /* n_comp / len(net): within 1 ulp of the division */
       double gam = (double)c.gamma;
       uint32_t pn = scal(CYG_S_PREV_X) & 0xFFFFu;
-      double prev = (pn == 0xFFFFu) ? phi : gam * ((double)pn / Md);
+      double prev = (pn == 0xFFFFu) ? phi : gam * ((double)pn * n->inv_M);
       double bonus = 0.1 * (gam * phi - prev);
       scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFF0000u) | (uint32_t)n_comp;
       shaped = raw + bonus;
     }
+    CYG_MARK(5);
     if (pre_masks) { /* the `state` step() returns is the pre-evolve view (volt:1306) */
       for (int w = 0; w < W; w++) {
         pre_masks[0 * W + w] = pl(P_COMP, w);
@@ -1252,11 +1475,27 @@ struct Env {
     int done = scal(CYG_S_STEP) > 1000u; /* _check_done (CyberDefenseEnv.py:547-552) */
     bool periodic = (scal(CYG_S_STEP) % (uint32_t)c.evolve_period) == 0;
     if (dirty || periodic) evolve_network();
+    CYG_MARK(6);
     if (!grouped) { /* volt:1330 */
       for (int w = 0; w < W; w++) pl(P_BUSYSET, w) = busy_nz(w);
     }
+    CYG_MARK(7);
     *raw_out = (float)raw; *shaped_out = (float)shaped; *done_out = done;
+  }
+
+  CYG_HD int step(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
+                  size_t order_gs, int G, uint32_t flags, float* raw_out, float* shaped_out, int32_t* done_out,
+                  uint32_t* pre_masks) {
+    int atype = step_pre(hdr, flags);
+    double cost = 0.0;
+    bool dirty = false;
+    atype = step_act(hdr, mask, order, hdr_gs, mask_gs, order_gs, G, flags, atype, cost, dirty);
+    step_post((int)((hdr[0] >> 8) & 1u), cost, dirty, flags, raw_out, shaped_out, done_out, pre_masks);
     return atype;
+  }
+  CYG_HD void resume_epoch() { /* re-attach to the epoch step_pre opened (the kernel changes threads between pieces) */
+    rng.epoch = scal(CYG_S_EPOCH) - 1u;
+    stall = Stream(SITE_STALL);
   }
 
   /* ---- randomize_compromise_and_ownership (volt:330-383) ---- */
@@ -1265,7 +1504,7 @@ struct Env {
     uint32_t pool[W];
     int np = 0, k_owned = 0, k_comp = 0;
     for (int w = 0; w < W; w++) {
-      uint32_t p = n->m_valid[w] & ~pl(P_NYA, w) & ~n->m_dc[w];
+      uint32_t p = m_valid(w) & ~pl(P_NYA, w) & ~m_dc(w);
       pool[w] = p;
       np += popc(p);
       k_owned += popc(p & pl(P_OWNED, w));
@@ -1280,7 +1519,7 @@ struct Env {
     for (int j = 0; j < k_owned + extra_c && j < np; j++) { /* shuffle == successive uniform picks */
       int r = rem > 1 ? (int)below(ss.next(rng), (uint32_t)rem) : 0;
       int d = select_nth(pool, r);
-      for (int w = 0; w < W; w++) if (w == (d >> 5)) pool[w] &= ~(1u << (d & 31));
+      for (int w = 0; w < W; w++) pool[w] &= ~((1u << (d & 31)) & eqmask(w, d >> 5));
       rem--;
       if (j < k_owned) setb(P_OWNED, d);
       setb(P_COMP, d);
@@ -1297,11 +1536,11 @@ struct Env {
     int atype = (int)below(st.next(rng), (uint32_t)space);
     int ndev = 1 + (int)below(sn.next(rng), (uint32_t)c.num_of_device);
     uint32_t pool[W], pick[W];
-    for (int w = 0; w < W; w++) { pool[w] = n->m_valid[w]; pick[w] = 0; }
+    for (int w = 0; w < W; w++) { pool[w] = m_valid(w); pick[w] = 0; }
     int rem = n->M;
     for (int j = 0; j < ndev; j++) {
       int d = select_nth(pool, (int)below(sd.next(rng), (uint32_t)rem));
-      for (int w = 0; w < W; w++) if (w == (d >> 5)) { pool[w] &= ~(1u << (d & 31)); pick[w] |= 1u << (d & 31); }
+      for (int w = 0; w < W; w++) { uint32_t bw = (1u << (d & 31)) & eqmask(w, d >> 5); pool[w] &= ~bw; pick[w] |= bw; }
       rem--;
     }
     int ex = (int)below(sx.next(rng), (uint32_t)c.X);
@@ -1362,8 +1601,8 @@ CYG_HD float observe_elem(const Net* n, const uint32_t* rec, int obs_mode, int j
     int d = j >> 2, k = j & 3, wi = d >> 5, s = d & 31;
     bool known = (pl[P_KNOWN * W + wi] >> s) & 1u, nya = (pl[P_NYA * W + wi] >> s) & 1u, owned = (pl[P_OWNED * W + wi] >> s) & 1u;
     if (!known || nya || !owned) return -1.f;
-    if (k == 0) return n->os_val[d];
-    if (k == 1) return n->ver_val[d];
+    if (k == 0) return ((const float*)(n->blob + n->o_os))[d];
+    if (k == 1) return ((const float*)(n->blob + n->o_ver))[d];
     if (k == 2) return ((pl[P_COMP * W + wi] >> s) & 1u) ? 1.f : 0.f;
     return 1.f; /* known */
   }
@@ -1372,8 +1611,8 @@ CYG_HD float observe_elem(const Net* n, const uint32_t* rec, int obs_mode, int j
   bool comp = (pl[P_COMP * W + wi] >> s) & 1u;
   if (obs_mode == 1 && (nya || !owned)) return -1.f;
   switch (k) {
-    case 0: return n->os_val[d];
-    case 1: return n->ver_val[d];
+    case 0: return ((const float*)(n->blob + n->o_os))[d];
+    case 1: return ((const float*)(n->blob + n->o_ver))[d];
     case 2: return obs_mode == 1 ? -1.f : (comp ? 1.f : 0.f);
     case 3: return 0.f; /* anomaly_score stays 0 under fast_scan (volt:46) */
     case 4: return known ? 1.f : 0.f;

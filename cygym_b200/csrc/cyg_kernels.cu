@@ -25,6 +25,7 @@
 #include <new>
 #include <string>
 
+#include "cyg_coop.cuh"
 #include "cyg_core.cuh"
 #include "cyg_tables.h"
 
@@ -80,6 +81,7 @@ struct StepParams {
   int32_t* done;
   uint32_t* pre_masks;
   float* obs;
+  unsigned long long* dbg_cycles; /* optional [B]: SM cycles each env's step took (diagnostics) */
   int B, env_id0, G, order_stride, obs_mode;
   uint32_t flags;
 };
@@ -87,9 +89,9 @@ struct StepParams {
 #define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
 #define CYG_MAX_BLOCK_ENVS 512 /* threads (= envs) per CTA: 128 registers per thread at one CTA per SM */
 
-/* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned) */
+/* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
-  size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_net, off_bar, total;
+  size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_bar, total;
 };
 __host__ __device__ inline size_t smem_take(size_t& o, size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; }
 __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB) {
@@ -97,10 +99,9 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
   size_t o = 0;
   p.off_tables = smem_take(o, (size_t)hot_words * 4);
   p.off_recs = smem_take(o, (size_t)NB * S * 4);
-  p.off_out = smem_take(o, (size_t)NB * 3 * 4);
+  p.off_out = smem_take(o, (size_t)NB * 2 * 4); /* phase B -> C carry: action cost, topology-dirty flag */
   p.off_perm = smem_take(o, (size_t)NB * 2);
-  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 1) * 4);
-  p.off_net = smem_take(o, sizeof(Net));
+  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 3) * 4); /* key histogram / run ends + two task counters */
   p.off_bar = smem_take(o, 8);
   p.total = o;
   return p;
@@ -108,7 +109,7 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
 
 template <int W>
 __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(cyg_smem);
   const int NB = blockDim.x, tid = threadIdx.x;
   const int S = p.net.S, M = p.net.M;
   const int env0 = blockIdx.x * NB;
@@ -119,7 +120,6 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
   float* s_out = (float*)(smem + sp.off_out);
   uint16_t* s_perm = (uint16_t*)(smem + sp.off_perm);
   uint32_t* s_cnt = (uint32_t*)(smem + sp.off_cnt);
-  Net* s_net = (Net*)(smem + sp.off_net);
   uint64_t* bar = (uint64_t*)(smem + sp.off_bar);
   const bool grouped = (p.flags & CYG_STEP_GROUPED) != 0;
 
@@ -133,18 +133,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
     mbar_expect_tx(bar, tab_bytes + (bulk_ok ? rec_bytes : 0u));
     bulk_g2s(s_tab, p.net.blob, tab_bytes, bar);
     if (bulk_ok) bulk_g2s(s_rec, g_rec, rec_bytes, bar);
-    /* CTA-local copy of the Net whose hot tables point into shared memory */
-    Net n = p.net;
-    auto hot = [&](const void* g) { return (const uint32_t*)((const unsigned char*)s_tab + ((const unsigned char*)g - (const unsigned char*)p.net.blob)); };
-    n.adj = hot(n.adj); n.m_dc = hot(n.m_dc); n.m_server = hot(n.m_server); n.m_reach = hot(n.m_reach);
-    n.m_valid = hot(n.m_valid); n.m_rowmulti = hot(n.m_rowmulti); n.m_incmulti = hot(n.m_incmulti); n.m_napps = hot(n.m_napps);
-    n.m_vuln = hot(n.m_vuln);
-    n.in_ptr = (const int32_t*)hot(n.in_ptr); n.in_eid = (const uint16_t*)hot(n.in_eid); n.dev_static = hot(n.dev_static);
-    n.out2in = (const uint16_t*)hot(n.out2in); n.e_mlo = hot(n.e_mlo); n.e_mhi = hot(n.e_mhi); n.ei_mlo = hot(n.ei_mlo); n.ei_mhi = hot(n.ei_mhi);
-    n.row_ptr = (const int32_t*)hot(n.row_ptr); n.col = (const uint16_t*)hot(n.col);
-    *s_net = n;
   }
-  if (tid < CYG_NKEYS + 1) s_cnt[tid] = 0;
+  if (tid < CYG_NKEYS + 3) s_cnt[tid] = 0;
   __syncthreads(); /* mbarrier initialised, counters zeroed */
 
   /* ---- sort the block's envs by the action type they will execute (needs only the action headers, so it
@@ -153,7 +143,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
   if (tid < nb) {
     if (!grouped) {
       uint32_t h0 = p.hdr[(size_t)(env0 + tid) * 4];
-      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W>::exec_type(p.net.cfg, h0) & 15);
+      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W, true>::exec_type(p.net.cfg, h0) & 15);
     }
     atomicAdd(&s_cnt[key + 1], 1u);
   }
@@ -173,12 +163,17 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
   mbar_wait(bar, 0);
   __syncthreads();
 
-  /* ---- the whole step of env perm[tid], thread-per-env over bit-planes ---- */
+  /* ---- phase A, thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or
+   *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
+  const int lane = tid & 31;
+  const bool coop_ok = !grouped && p.order == nullptr;
+  bool deferred = false;
+  int el = 0, env = 0;
   if (tid < nb) {
-    const int el = s_perm[tid];
-    const int env = env0 + el;
-    Env<W> e(s_net, s_rec + el * S, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
-             (uint32_t)(p.env_id0 + env));
+    el = s_perm[tid];
+    env = env0 + el;
+    Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+                   (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
     uint32_t act[4 + W]; /* this env's action (group 0), in registers */
     {
       uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env * 4);
@@ -187,34 +182,153 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
       for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env * W + w];
     }
     const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
-    float raw, shaped;
-    int32_t done;
-    uint32_t* pre = p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr;
-    if (!grouped) {
-      e.step(act, act + 4, ord, 0, 0, 0, 1, p.flags, &raw, &shaped, &done, pre);
-    } else {
-      e.step(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
-             (size_t)p.B * p.order_stride, p.G, p.flags, &raw, &shaped, &done, pre);
+    long long t_begin = p.dbg_cycles ? clock64() : 0;
+#ifdef CYG_PHASE_TIMING
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e.phase_t = ph;
+#endif
+    const int mode = (int)((act[0] >> 8) & 1u);
+    int atype = e.step_pre(act, p.flags);
+    deferred = coop_ok && Coop<W>::is_heavy(mode, atype);
+    if (!deferred) {
+      double cost = 0.0;
+      bool dirty = false;
+      if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
+      else e.step_act(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
+                      (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
+      float raw, shaped;
+      int32_t done;
+      e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
+      p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
     }
-    s_out[el] = raw;
-    s_out[NB + el] = shaped;
-    s_out[2 * NB + el] = __int_as_float(done);
+#ifdef CYG_PHASE_TIMING
+    if (p.dbg_cycles) for (int i = 0; i < 8; i++) p.dbg_cycles[(size_t)env * 8 + i] = (unsigned long long)(ph[i] - t_begin);
+#else
+    if (p.dbg_cycles) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
+#endif
+  }
+
+  /* ---- phase B, warp per env: clean / revert / upgrade / block / unblock with 32 lanes on the listed devices.
+   *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
+  if (coop_ok) {
+    __syncthreads();
+    if (tid == 0) { s_cnt[CYG_NKEYS + 1] = 0; s_cnt[CYG_NKEYS + 2] = 0; } /* task counters */
+    __syncthreads();
+    /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
+     * groups were measured slower (the groups of a warp diverge and no longer issue together). */
+    {
+      constexpr int G = 32;
+      const int lg = lane % G, gbase = lane - lg;
+      const uint32_t gm = (G == 32) ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << gbase);
+      const int lo9 = (int)s_cnt[9], n9 = (int)s_cnt[10] - lo9, lo6 = (int)s_cnt[6], n6 = (int)s_cnt[7] - lo6;
+      for (;;) {
+        int task = 0;
+        if (lg == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 1], 1u);
+        task = __shfl_sync(gm, task, gbase);
+        if (task >= n9 + n6) break;
+        const int el_b = s_perm[task < n9 ? lo9 + task : lo6 + (task - n9)];
+        const int env_b = env0 + el_b;
+        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
+                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+        e.resume_epoch();
+        uint32_t act[4 + W];
+        {
+          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+        }
+        typename Env<W, true>::Act a;
+        Env<W, true>::decode(act, act + 4, nullptr, a);
+        double cost = 0.0;
+        bool dirty = false;
+        long long tb0 = p.dbg_cycles ? clock64() : 0;
+        if (lg == 0) e.load_costs();
+        Coop<W>::template flip<G>(e, a, task < n9 ? 9 : 6, cost, dirty);
+        if (lg == 0) {
+#ifndef CYG_PHASE_TIMING
+          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
+#endif
+          e.store_costs();
+          s_out[el_b] = (float)cost;
+          s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
+        }
+        __syncwarp(gm);
+      }
+    }
+    __syncwarp();
+    /* B2: clean / revert / upgrade (keys 1, 3, 4), one env per warp: 32 lanes = the 32 devices of a plane word */
+    {
+      const int heavy_keys[3] = {1, 3, 4};
+      int ntasks = 0;
+#pragma unroll
+      for (int i = 0; i < 3; i++) ntasks += (int)(s_cnt[heavy_keys[i] + 1] - s_cnt[heavy_keys[i]]);
+      for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 2], 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= ntasks) break;
+        int ppos = -1, rem = task;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { /* s_cnt[k] .. s_cnt[k+1] = run of key k in perm[] (k >= 1) */
+          const int lo = (int)s_cnt[heavy_keys[i]], n_k = (int)s_cnt[heavy_keys[i] + 1] - lo;
+          const bool here = ppos < 0 && rem < n_k;
+          ppos = here ? lo + rem : ppos;
+          rem -= (ppos < 0) ? n_k : 0;
+        }
+        const int el_b = s_perm[ppos];
+        const int env_b = env0 + el_b;
+        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
+                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+        e.resume_epoch();
+        uint32_t act[4 + W];
+        {
+          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+        }
+        typename Env<W, true>::Act a;
+        Env<W, true>::decode(act, act + 4, nullptr, a);
+        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0]);
+        double cost = 0.0;
+        bool dirty = false;
+        long long tb0 = p.dbg_cycles ? clock64() : 0;
+        if (lane == 0) e.load_costs();
+        Coop<W>::defender(e, a, atype, cost, dirty);
+        if (lane == 0) {
+#ifndef CYG_PHASE_TIMING
+          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0); /* heavy envs: phase-B cycles */
+#endif
+          e.store_costs();
+          s_out[el_b] = (float)cost;
+          s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
+    if (deferred) {
+      Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+                     (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
+      e.resume_epoch();
+      float raw, shaped;
+      int32_t done;
+      e.step_post(CYG_MODE_DEFENDER, (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
+                  p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
+      p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+    }
   }
   __syncthreads();
 
-  /* ---- coalesced outputs ---- */
-  if (tid < nb) {
-    p.raw[env0 + tid] = s_out[tid];
-    p.shaped[env0 + tid] = s_out[NB + tid];
-    p.done[env0 + tid] = __float_as_int(s_out[2 * NB + tid]);
-  }
   /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
   if (p.obs && p.obs_mode) {
     const int dim = p.obs_mode == 2 ? 4 * M + p.net.cfg.X : 6 * M;
     float* o = p.obs + (size_t)env0 * dim;
     for (int i = tid; i < nb * dim; i += NB) {
       int el = i / dim;
-      o[i] = observe_elem<W>(s_net, s_rec + el * S, p.obs_mode, i - el * dim);
+      o[i] = observe_elem<W>(&p.net, s_rec + el * S, p.obs_mode, i - el * dim);
     }
   }
 
@@ -326,7 +440,8 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     rec[n.off_blocked + i] = bo[i];
     uint32_t bi = 0; /* the same bits in in-list order */
     for (int j = 0; j < 32 && i * 32 + j < n.E; j++) {
-      int e = n.in_eid[i * 32 + j];
+      int jj = i * 32 + j;
+      int e = (int)((n.blob[n.o_in_eid + (jj >> 1)] >> ((jj & 1) * 16)) & 0xFFFFu);
       bi |= ((bo[e >> 5] >> (e & 31)) & 1u) << j;
     }
     rec[n.off_blocked_in + i] = bi;
@@ -379,6 +494,7 @@ struct cyg_env_s {
   uint32_t* d_blob;
   uint32_t* state;   /* bound internal buffer: [B][S] records then [B][M] checkpoint words */
   int B, env_id0, device, W, NB, n_sms;
+  unsigned long long* dbg_cycles;
   size_t smem_bytes;
   int64_t launches;
 };
@@ -454,7 +570,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   if (!h) return fail(CYG_E_NOMEM, "out of host memory");
   std::string err = build_tables(*cfg, *host_net, h->blob);
   if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
-  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0;
+  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr;
   h->W = h->blob.net.W;
   DeviceGuard g(device);
   if (!g.ok) { delete h; return fail(CYG_E_CUDA, "cudaSetDevice failed"); }
@@ -545,7 +661,7 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   p.recs = h->state; p.ckpt = ckpt_of(h); p.xtra = xtra_of(h);
   p.hdr = a->hdr; p.mask = a->mask; p.order = a->order;
   p.raw = out->raw_reward; p.shaped = out->shaped_reward; p.done = out->done;
-  p.pre_masks = out->pre_masks; p.obs = out->obs;
+  p.pre_masks = out->pre_masks; p.obs = out->obs; p.dbg_cycles = h->dbg_cycles;
   p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
@@ -598,5 +714,11 @@ int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream) {
 }
 
 int64_t cyg_launch_count(cyg_handle h) { return h ? h->launches : 0; }
+
+int cyg_set_debug_cycles(cyg_handle h, uint64_t* per_env_cycles) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  h->dbg_cycles = (unsigned long long*)per_env_cycles;
+  return CYG_OK;
+}
 
 } /* extern "C" */

@@ -25,7 +25,7 @@ struct TableBlob {
   Net net;                     /* pointers are OFFSETS (in words) until relocate() */
   size_t hot_words;            /* prefix that the step kernel stages in shared memory */
   size_t o_adj, o_adjT, o_mlo, o_mhi, o_mloT, o_mhiT, o_row_ptr, o_col, o_in_ptr, o_in_eid, o_static, o_dc, o_server,
-      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver, o_out2in, o_emlo, o_emhi, o_eimlo, o_eimhi;
+      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver, o_out2in, o_in_src, o_emlo, o_emhi, o_eimlo, o_eimhi, o_dmulti;
 };
 
 inline size_t tb_alloc(TableBlob& b, size_t nwords) {
@@ -76,10 +76,12 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   b.o_in_eid = tb_alloc(b, (E + 1) / 2 + 1);
   b.o_static = tb_alloc(b, M);
   b.o_out2in = tb_alloc(b, (E + 1) / 2 + 1);
+  b.o_in_src = tb_alloc(b, (E + 1) / 2 + 1);
   b.o_emlo = tb_alloc(b, EW);
   b.o_emhi = tb_alloc(b, EW);
   b.o_eimlo = tb_alloc(b, EW);
   b.o_eimhi = tb_alloc(b, EW);
+  b.o_dmulti = tb_alloc(b, (size_t)2 * M);
   b.hot_words = b.words.size();
   /* cold section: read through L1/L2 (multi-edge weights, in-rows for envs with extra edges, observation rows) */
   b.o_mlo = tb_alloc(b, (size_t)M * W);
@@ -128,10 +130,29 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
       int j = indeg[v] + fill[v]++;
       ineid16[j] = (uint16_t)e;
       ((uint16_t*)(w + b.o_out2in))[e] = (uint16_t)j;
+      ((uint16_t*)(w + b.o_in_src))[j] = (uint16_t)u;
       int mu = hn.mult ? hn.mult[e] : 1;
       if ((mu - 1) & 1) { w[b.o_emlo + (e >> 5)] |= 1u << (e & 31); w[b.o_eimlo + (j >> 5)] |= 1u << (j & 31); }
       if ((mu - 1) & 2) { w[b.o_emhi + (e >> 5)] |= 1u << (e & 31); w[b.o_eimhi + (j >> 5)] |= 1u << (j & 31); }
     }
+  /* packed multi-edge entries of every device's out list and in list */
+  for (int i = 0; i < M; i++) {
+    for (int side = 0; side < 2; side++) {
+      int lo = side ? ip[i] : rp[i], hi = side ? ip[i + 1] : rp[i + 1];
+      uint32_t dm = 0xFFu | (0xFFu << 10);
+      int cnt = 0;
+      for (int p = lo; p < hi; p++) {
+        int e = side ? ineid16[p] : p;
+        int mu = hn.mult ? hn.mult[e] : 1;
+        if (mu <= 1) continue;
+        if (cnt >= 2 || p - lo >= 0xFF) { dm |= 0x80000000u; continue; }
+        dm &= ~(0x3FFu << (10 * cnt));
+        dm |= ((uint32_t)(p - lo) | ((uint32_t)(mu - 1) << 8)) << (10 * cnt);
+        cnt++;
+      }
+      w[b.o_dmulti + 2 * i + side] = dm;
+    }
+  }
   for (int i = 0; i < M; i++) {
     uint32_t st = hn.dev_static[i];
     w[b.o_static + i] = st;
@@ -155,23 +176,19 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
 /* point the Net at a copy of the blob living at `base` (host or device address) */
 inline void relocate(const TableBlob& b, const uint32_t* base, Net& n) {
   n = b.net;
-  n.blob = base; n.hot_words = (uint32_t)b.hot_words;
-  n.adj = base + b.o_adj; n.adjT = base + b.o_adjT;
-  n.mlo = base + b.o_mlo; n.mhi = base + b.o_mhi; n.mloT = base + b.o_mloT; n.mhiT = base + b.o_mhiT;
-  n.row_ptr = (const int32_t*)(base + b.o_row_ptr);
-  n.col = (const uint16_t*)(base + b.o_col);
-  n.in_ptr = (const int32_t*)(base + b.o_in_ptr);
-  n.in_eid = (const uint16_t*)(base + b.o_in_eid);
-  n.out2in = (const uint16_t*)(base + b.o_out2in);
-  n.e_mlo = base + b.o_emlo; n.e_mhi = base + b.o_emhi; n.ei_mlo = base + b.o_eimlo; n.ei_mhi = base + b.o_eimhi;
-  n.dev_static = base + b.o_static;
-  n.m_dc = base + b.o_dc; n.m_server = base + b.o_server; n.m_reach = base + b.o_reach; n.m_valid = base + b.o_valid;
-  n.m_rowmulti = base + b.o_rowmulti;
-  n.m_incmulti = base + b.o_incmulti;
-  n.m_napps = base + b.o_napps;
-  n.m_vuln = base + b.o_vuln;
-  n.os_val = (const float*)(base + b.o_os);
-  n.ver_val = (const float*)(base + b.o_ver);
+  n.blob = base;
+  n.hot_words = (uint32_t)b.hot_words;
+  n.inv_M = 1.0 / (double)n.M;
+  n.o_adj = (uint32_t)b.o_adj; n.o_adjT = (uint32_t)b.o_adjT;
+  n.o_mlo = (uint32_t)b.o_mlo; n.o_mhi = (uint32_t)b.o_mhi; n.o_mloT = (uint32_t)b.o_mloT; n.o_mhiT = (uint32_t)b.o_mhiT;
+  n.o_row_ptr = (uint32_t)b.o_row_ptr; n.o_col = (uint32_t)b.o_col; n.o_in_ptr = (uint32_t)b.o_in_ptr;
+  n.o_in_eid = (uint32_t)b.o_in_eid; n.o_out2in = (uint32_t)b.o_out2in; n.o_in_src = (uint32_t)b.o_in_src; n.o_static = (uint32_t)b.o_static;
+  n.o_dc = (uint32_t)b.o_dc; n.o_server = (uint32_t)b.o_server; n.o_reach = (uint32_t)b.o_reach; n.o_valid = (uint32_t)b.o_valid;
+  n.o_rowmulti = (uint32_t)b.o_rowmulti; n.o_incmulti = (uint32_t)b.o_incmulti; n.o_napps = (uint32_t)b.o_napps;
+  n.o_vuln = (uint32_t)b.o_vuln;
+  n.o_dmulti = (uint32_t)b.o_dmulti;
+  n.o_emlo = (uint32_t)b.o_emlo; n.o_emhi = (uint32_t)b.o_emhi; n.o_eimlo = (uint32_t)b.o_eimlo; n.o_eimhi = (uint32_t)b.o_eimhi;
+  n.o_os = (uint32_t)b.o_os; n.o_ver = (uint32_t)b.o_ver;
 }
 
 }  // namespace cyg

@@ -232,6 +232,10 @@ int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream);
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t cyg_launch_count(cyg_handle h);
 
+/* Diagnostics: when a device buffer [B] is set, every cyg_step writes the SM cycles each env's transition
+ * took (profiles/type_cycles.py groups them by action type).  NULL switches it off (the default). */
+int cyg_set_debug_cycles(cyg_handle h, uint64_t* per_env_cycles);
+
 #ifdef __cplusplus
 }
 #endif
