@@ -112,6 +112,9 @@ struct Coop {
       int pos = 0;
       uint32_t kbase = 0;
       while (pos < na) { /* uniform within the group */
+#ifdef CYG_COUNT_ROUNDS
+        e.dbg_rounds++;
+#endif
         const int idx = pos + lg;
         const bool valid = idx < na;
         const int d = valid ? e.select_nth(act, idx) : 0;

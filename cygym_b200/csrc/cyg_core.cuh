@@ -229,6 +229,7 @@ struct Env {
   Stream stall;    /* SITE_STALL is shared by every group of a grouped step */
   double defcost, cleancost;
   long long* phase_t = nullptr; /* profiling builds only */
+  int dbg_rounds = 0;           /* profiling builds only */
 
   CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t* xt, uint32_t env_id, uint32_t rec_off = 0,
              uint32_t tab_off = 0)

@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
 #ifndef CYG_PHASE_TIMING
           if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
 #endif
+#ifdef CYG_COUNT_ROUNDS
+          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)e.dbg_rounds;
+#endif
           e.store_costs();
           s_out[el_b] = (float)cost;
           s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
