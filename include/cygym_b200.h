@@ -205,8 +205,10 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
 int cyg_destroy(cyg_handle h);
 int cyg_set_base_line(cyg_handle h, int32_t base_line);
 
-/* Sizes the caller must allocate (in uint32 words per env) for the kernels' internal
- * bit-plane state: state words per env. */
+/* uint32 words PER ENV the caller must allocate for the kernels' internal state.  The buffer holds, in this
+ * order: B records of S words (16 scalars + bit-planes + the blocked-edge bitset in out- and in-list order;
+ * what a CTA bulk-copies into shared memory), then B*M per-device checkpoint words (actions 11/12,
+ * volt_typhoon_env.py:419-453), then B*xcap extra-edge words.  words_per_env = S + M + xcap. */
 int cyg_internal_words(cyg_handle h, int64_t* words_per_env);
 
 /* Bind the internal state buffer (device pointer, B * words_per_env uint32, 16-byte aligned). */
