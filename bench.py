@@ -54,43 +54,64 @@ def workload_name(a):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons DURING the timed region.  The timed region is tens of milliseconds, so the
+    sampler polls NVML in-process every ~2 ms (nvidia-smi, the B200_PROFILING.md clocks line, is the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
+        self.sm, self.max_sm, self.reasons, self.how = [], 0.0, set(), "nvml"
         self._stop_evt = threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[gpu_index])
+                                                        if os.environ.get("CUDA_VISIBLE_DEVICES") else gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+            self.how = "nvidia-smi"
+
+    def _poll_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            s = [x.strip() for x in out.split(",")]
+            self.sm.append(float(s[1]))
+            self.max_sm = max(self.max_sm, float(s[2]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._poll_nvml() if self._nvml else self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.002 if self._nvml else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                mx = max(mx, float(s[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm or None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "how": self.how}
 
 
 def cpu_arm(a, seconds, threads=None):
@@ -259,6 +280,14 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650"
         alg = net.algorithmic_bytes_per_step(obs=bool(a.obs))
+        traffic = None  # dram read+write bytes per launch of the step kernel from the committed `ncu --set full` capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_step_kernel_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("envs_per_launch") == B and tj.get("device_slots") == a.devices and not a.obs:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         launch_s = ms * 1e-3 / K
         achieved = alg * B / launch_s / 1e9
         value = world * B * K / (ms * 1e-3)
@@ -267,11 +296,11 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
-                       "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4,
+                       "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
                        "l2_policy": f"rotating {a.sets} env sets ({a.sets * B * (sets[0].S + net.M) * 4 / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
                        "parallelism": f"env-sharded x{world}, no per-step collective", "error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
+                         "traffic": traffic, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
                          "launch_us": launch_s * 1e6, "peak_source": peak_src,
                          "actual_bytes_per_env_step": 2 * sets[0].S * 4 + 4 * (4 + net.W) + 12},
             "clocks": clocks, "gpu_launches": int(launches),
