@@ -82,12 +82,15 @@ struct StepParams {
   uint32_t* pre_masks;
   float* obs;
   unsigned long long* dbg_cycles; /* optional [B]: SM cycles each env's step took (diagnostics) */
-  int B, env_id0, G, order_stride, obs_mode;
+  int B, env_id0, G, order_stride, obs_mode, block_envs;
   uint32_t flags;
 };
 
 #define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
-#define CYG_MAX_BLOCK_ENVS 512 /* threads (= envs) per CTA: 128 registers per thread at one CTA per SM */
+#define CYG_MAX_BLOCK_ENVS 512   /* envs per CTA */
+#define CYG_MAX_BLOCK_THREADS 896 /* threads per CTA: 72 registers per thread at one CTA per SM.  A CTA runs twice as
+                                    many threads as envs: phases A / C use one thread per env, the warp-per-env phase
+                                    B all 28 warps (it is latency-bound; more warps in flight is what it needs) */
 
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
@@ -108,9 +111,9 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
 }
 
 template <int W>
-__global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>(cyg_smem);
-  const int NB = blockDim.x, tid = threadIdx.x;
+  const int NB = p.block_envs, NT = blockDim.x, tid = threadIdx.x; /* NB envs, NT >= NB threads */
   const int S = p.net.S, M = p.net.M;
   const int env0 = blockIdx.x * NB;
   const int nb = min(NB, p.B - env0);
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
     s_perm[pos] = (uint16_t)tid;
   }
   if (!bulk_ok) {
-    for (int i = tid; i < nb * S; i += NB) s_rec[i] = g_rec[i];
+    for (int i = tid; i < nb * S; i += NT) s_rec[i] = g_rec[i];
   }
   mbar_wait(bar, 0);
   __syncthreads();
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
   if (p.obs && p.obs_mode) {
     const int dim = p.obs_mode == 2 ? 4 * M + p.net.cfg.X : 6 * M;
     float* o = p.obs + (size_t)env0 * dim;
-    for (int i = tid; i < nb * dim; i += NB) {
+    for (int i = tid; i < nb * dim; i += NT) {
       int el = i / dim;
       o[i] = observe_elem<W>(&p.net, s_rec + el * S, p.obs_mode, i - el * dim);
     }
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_ENVS, 1) cyg_step_kernel(const _
       bulk_commit_wait_read();
     }
   } else {
-    for (int i = tid; i < nb * S; i += NB) g_rec[i] = s_rec[i];
+    for (int i = tid; i < nb * S; i += NT) g_rec[i] = s_rec[i];
   }
 }
 
@@ -668,8 +671,12 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
+  p.block_envs = h->NB;
   int blocks = (h->B + h->NB - 1) / h->NB;
-  DISPATCH_W(h->W, (cyg_step_kernel<KW><<<blocks, h->NB, h->smem_bytes, (cudaStream_t)stream>>>(p)));
+  int threads = ((2 * h->NB + 31) / 32) * 32;
+  if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
+  if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
+  DISPATCH_W(h->W, (cyg_step_kernel<KW><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p)));
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

@@ -1,0 +1,158 @@
+"""Snapshots: networks + env state in and out of the struct-of-arrays form.
+
+The reference persists experiments as pickled env objects (`initial_net_DO_its<N>.pkl`, init_experiments.py:53-62,
+volt_typhoon_env.py:1877-1895, reloaded by reset(from_init=True), :1904-1925).  Two entry points:
+
+ * `from_reference_env(env)`  -- flatten a LIVE reference env object (e.g. one just unpickled in a process that
+   can import the reference) into a `Network` whose template is the env's current state.  Duck-typed: it only
+   reads the attributes listed in SURVEY.md section 8(a)/(b) and never imports the reference.
+ * `save_npz / load_npz`      -- our own portable snapshot (numpy .npz) of a Network + template, so that the same
+   experiment can be re-run where the reference is not installed (the GPU box).
+"""
+import json
+
+import numpy as np
+
+from .network import (DEV_ACTSET, DEV_BUSY_SHIFT, DEV_BUSYSET, DEV_CBY_SHIFT, DEV_COMP, DEV_HASWL, DEV_KNOWN, DEV_NYA,
+                      DEV_OWNED, DEV_PT_SHIFT, DEV_REMOVED, NSCAL, ST_DC, ST_NAPPS_SHIFT, ST_REACH, ST_SERVER,
+                      ST_VULN_SHIFT, Network)
+
+CK_COMP, CK_KNOWN, CK_NYA, CK_REACH, CK_HASWL, CK_VALID = 1 << 0, 1 << 1, 1 << 2, 1 << 3, 1 << 5, 1 << 31
+
+
+def save_npz(path, net: Network):
+    t = net.template
+    np.savez_compressed(path, row_ptr=net.row_ptr, col=net.col, mult=net.mult, dev_static=net.dev_static,
+                        os_val=net.os_val, ver_val=net.ver_val, cfg=np.asarray(json.dumps(net.cfg)),
+                        **{"t_" + k: np.asarray(v, np.uint32) for k, v in t.items()})
+    return path
+
+
+def load_npz(path):
+    g = np.load(path)
+    template = {k[2:]: np.array(g[k]) for k in g.files if k.startswith("t_")}
+    d = {k: np.array(g[k]) for k in ("row_ptr", "col", "mult", "dev_static", "os_val", "ver_val")}
+    return Network.from_arrays(d, json.loads(str(g["cfg"])), template)
+
+
+def from_reference_env(env):
+    """Flatten a live reference Volt_Typhoon_CyberDefenseEnv (its graph cache must be current: call
+    env._rebuild_graph_cache() first, as DoubleOracle.restore does, do_agent.py:891-895)."""
+    net = env.simulator.subnet.net
+    M = len(net)
+    if sorted(net.keys()) != list(range(M)):
+        raise ValueError("device ids must be 0..M-1")
+    row_ptr, col, mult = [0], [], []
+    for u in range(M):  # _outnbrs: ascending neighbour ids, multi-edges as repeats (volt:456-473)
+        prev = None
+        for v in env._outnbrs.get(u, []):
+            v = int(v)
+            if prev is not None and v < prev:
+                raise ValueError("neighbour list not ascending")
+            if v == prev:
+                mult[-1] += 1
+            else:
+                col.append(v)
+                mult.append(1)
+            prev = v
+        row_ptr.append(len(col))
+    exploits = list(env.simulator.exploits)
+    eid_of = {exp.id: i for i, exp in enumerate(exploits)}
+    X = int(env.MaxExploits)
+    dev_static = np.zeros(M, np.uint32)
+    os_val = np.zeros(M, np.float32)
+    ver_val = np.zeros(M, np.float32)
+    dev = np.zeros(M, np.uint32)
+    ckpt = np.zeros(M, np.uint32)
+    busyset = {d.id for d in (getattr(env, "_busy_devices", None) or ())}
+    has_sets = hasattr(env, "_active_ids") and hasattr(env, "_inactive_ids")
+    for i in range(M):
+        d = net[i]
+        w = 0
+        if d.device_type == "DomainController":
+            w |= ST_DC
+        if d.wtype == "server":
+            w |= ST_SERVER
+        if d.reachable_by_attacker:
+            w |= ST_REACH
+        w |= min(255, len(d.apps)) << ST_NAPPS_SHIFT
+        for e, exp in enumerate(exploits):
+            if any(vul.id in exp.target for app in d.apps.values() for vul in app.vulnerabilities.values()):
+                w |= 1 << (ST_VULN_SHIFT + e)
+        dev_static[i] = w
+        os_val[i] = env.os_to_float(d.OS)
+        try:
+            ver_val[i] = float(d.version)
+        except Exception:
+            ver_val[i] = -1.0
+        s = 0
+        s |= DEV_COMP if d.isCompromised else 0
+        s |= DEV_KNOWN if d.Known_to_attacker else 0
+        s |= DEV_NYA if d.Not_yet_added else 0
+        s |= DEV_OWNED if d.attacker_owned else 0
+        s |= DEV_REMOVED if d.removed_before else 0
+        if d.workload is not None:
+            s |= DEV_HASWL | (int(d.workload.processing_time) << DEV_PT_SHIFT)
+        s |= int(d.busy_time) << DEV_BUSY_SHIFT
+        for x in d.compromised_by:
+            s |= (1 << eid_of[x]) << DEV_CBY_SHIFT
+        if i in busyset:
+            s |= DEV_BUSYSET
+        if has_sets and i in env._active_ids:
+            s |= DEV_ACTSET
+        dev[i] = s
+        c = getattr(env, "_device_ckpts", {}).get(i)
+        if c is not None:
+            k = CK_VALID
+            k |= CK_COMP if c["isCompromised"] else 0
+            k |= CK_KNOWN if c["Known_to_attacker"] else 0
+            k |= CK_NYA if c["Not_yet_added"] else 0
+            k |= CK_REACH if c["reachable_by_attacker"] else 0
+            if c["workload"]:
+                k |= CK_HASWL | (int(c["workload"]["processing_time"]) << DEV_PT_SHIFT)
+            k |= int(c["busy_time"]) << DEV_BUSY_SHIFT
+            for x in c["compromised_by"]:
+                k |= (1 << eid_of[x]) << DEV_CBY_SHIFT
+            ckpt[i] = k
+    E = len(col)
+    eidx = {}
+    for u in range(M):
+        for e in range(row_ptr[u], row_ptr[u + 1]):
+            eidx[(u, col[e])] = e
+    blocked = np.zeros(max(1, (E + 31) // 32), np.uint32)
+    for (u, v) in getattr(env, "_blocked", ()):  # blocked pairs outside the cache cannot occur after a rebuild
+        e = eidx.get((int(u), int(v)))
+        if e is not None:
+            blocked[e >> 5] |= np.uint32(1 << (e & 31))
+    scal = np.zeros(NSCAL, np.uint32)
+    scal[0] = env.step_num
+    fl = (1 if env.checkpoint is not None else 0) | (2 if has_sets else 0)
+    for i, exp in enumerate(exploits):
+        if exp.discovered:
+            fl |= 1 << (8 + i)
+    scal[2] = fl
+    prev = getattr(env, "_prev_att_potential", None)
+    scal[3] = 0xFFFF if prev is None else int(round(prev * M / env.γ))
+    scal[4], scal[5] = env.defender_step, env.attacker_step
+    scal[6] = len(env.simulator.logger.logs)
+    scal[7], scal[8] = env.compromised_devices_cnt, env.work_done
+    f32 = np.array([env.defensive_cost, env.clearning_cost], np.float32).view(np.uint32)
+    scal[9], scal[10] = f32[0], f32[1]
+    scal[11], scal[12], scal[13] = env.scan_cnt, env.revert_count, env.checkpoint_count
+    scal[14], scal[15] = env.edges_blocked, env.edges_added
+    zd = 0
+    if env.zero_day:
+        for i in (set(env.common_exploit_indices) | set(env.private_exploit_indices)):
+            zd |= 1 << int(i)
+    cfg = dict(
+        M=M, X=X, n_exploits=len(exploits), numOfDevice=int(env.numOfDevice), Min_network_size=int(env.Min_network_size),
+        work_scale=float(env.work_scale), comp_scale=float(env.comp_scale), def_scale=float(env.def_scale),
+        gamma=float(env.γ), default_high=int(env.default_high), lambda_events=float(env.lambda_events),
+        p_add=float(env.p_add), p_attacker=float(env.p_attacker), evolve_period=int(env._evolve_period),
+        workload_period_base=int(env.workload_period_base), workload_period_max=int(env.workload_period_max),
+        workload_cap=(-1 if env.workload_cap is None else int(env.workload_cap)),
+        scaling_vulnerability=int(bool(env.scaling_vulnerability)), turbo=int(bool(env.turbo)),
+        zero_day=int(bool(env.zero_day)), zero_day_mask=zd, att_space_n=int(env.attacker_action_space.n),
+        def_space_n=int(env.defender_action_space.n), n_app_ids=int(env.get_num_app_indices()))
+    template = dict(dev=dev, ckpt=ckpt, blocked=blocked, extra=np.zeros(0, np.uint32), scal=scal)
+    return Network(row_ptr, col, mult, dev_static, os_val, ver_val, cfg, template)
