@@ -176,8 +176,69 @@ struct Coop {
     __syncwarp(gm);
   }
 
+  /* attacker action 1, exploit + lateral movement (volt:1126-1185), one warp per env: the 32 lanes take 32
+   * consecutive sources of the snapshot.  A source's scan depends on earlier sources only through isCompromised
+   * of its own hit (a "not yet compromised" hit is invalid if a lower lane hit the same device), so a round
+   * commits the lanes below the first such lane and restarts from it: bit-identical to the sequential loop. */
+  static __device__ void attack(E& e, const typename E::Act& a) {
+    const int lane = lane_id();
+    uint32_t src[W];
+    int ns = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) { src[w] = e.pl(P_COMP, w) | e.pl(P_OWNED, w); ns += popc(src[w]); }
+    const bool has_blk = e.any_blocked();
+    const int nx = e.n_extra();
+    __syncwarp();
+    if (nx > 0) { /* envs with extra (hub-star) edges: the sequential loop on one lane */
+      if (lane == 0) { double cost = 0.0; e.attacker_act(a, 1, cost); }
+      __syncwarp();
+      return;
+    }
+    uint32_t logs_add = 0, zk = 0;
+    for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
+      int raw = a.ex(xi);
+      uint32_t zx = 0;
+      if (e.needs_zday_draw(raw)) zx = draw_at(e.rng, SITE_ZDAY, zk++);
+      raw = e.resolve_exploit(raw, zx);
+      if (raw < 0) continue;
+      uint32_t kv[W];
+#pragma unroll
+      for (int w = 0; w < W; w++) kv[w] = e.pl(P_KNOWN, w) & e.m_vuln(raw, w);
+      int pos = 0;
+      while (pos < ns) { /* uniform */
+        const int idx = pos + lane;
+        const bool valid = idx < ns;
+        const int s = valid ? e.select_nth(src, idx) : 0;
+        uint32_t comp[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) comp[w] = e.pl(P_COMP, w);
+        int cnt = 0, v = -1;
+        bool rule3 = false;
+        if (valid) v = e.attack_source(s, comp, kv, has_blk, 0, cnt, rule3);
+        const uint32_t same = __match_any_sync(CYG_FULL, v >= 0 ? v : (0x1000 + lane));
+        const bool conflict = valid && rule3 && (same & lanes_below(lane)) != 0;
+        const uint32_t conf = __ballot_sync(CYG_FULL, conflict);
+        int c = conf ? (__ffs((int)conf) - 1) : 32;
+        if (c > ns - pos) c = ns - pos;
+        if (valid && lane < c) {
+          logs_add += (uint32_t)cnt + (v >= 0 ? 1u : 0u);
+          if (v >= 0) {
+            atomicOr(&e.pl(P_COMP, v >> 5), 1u << (v & 31));
+            if (e.devbit(e.n->o_dc, s)) atomicOr(&e.pl(P_CBY0 + raw, v >> 5), 1u << (v & 31));
+          }
+        }
+        pos += c;
+        __syncwarp();
+      }
+    }
+    logs_add = __reduce_add_sync(CYG_FULL, logs_add);
+    if (lane == 0) e.scal(CYG_S_LOGS) += logs_add;
+    __syncwarp();
+  }
+
   static __device__ __forceinline__ bool is_heavy(int mode, int atype) {
-    return mode == CYG_MODE_DEFENDER && (atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9);
+    if (mode == CYG_MODE_ATTACKER) return atype == 1;
+    return atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9;
   }
 
   /* the deposit-type heavy defender actions (clean / revert / upgrade) of a plain set-form step, one warp per env;

@@ -1046,6 +1046,95 @@ struct Env {
       }
     }
   }
+  /* One source of the lateral-movement loop (volt:1148-1185): scan the unblocked out-neighbours of s in ascending
+   * order; a DomainController source hits the first one, otherwise the first that is reachable_by_attacker or
+   * (not compromised, known, vulnerable to the exploit).  comp[] = current isCompromised words, kv[] = known &
+   * vulnerable.  Returns the hit device (-1: none); cnt = hops logged before the hit (log_communication, volt:1161:
+   * every repeat of a multi-edge counts); rule3 = the hit relied on "not yet compromised". */
+  CYG_HD int attack_source(int s, const uint32_t* comp, const uint32_t* kv, bool has_blk, int nx, int& cnt, bool& rule3) {
+    const bool is_dc = devbit(n->o_dc, s);
+    const uint32_t dmo = T(n->o_dmulti + 2 * s);
+    int vw = -1;
+    uint32_t hitbit = 0;
+    if (nx > 0 || (dmo >> 31)) {
+      /* general form: materialise the unblocked row (extra edges, > 2 multi-edges in the row) */
+      uint32_t row[W];
+      live_row(s, has_blk, nx, row);
+      uint32_t cand_w = 0;
+      for (int w = W - 1; w >= 0; w--) {
+        uint32_t cand = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
+        bool nz = cand != 0;
+        vw = nz ? w : vw;
+        cand_w = nz ? cand : cand_w;
+      }
+      hitbit = cand_w & (0u - cand_w);
+      cnt = 0;
+      const bool multi = devbit(n->o_rowmulti, s);
+      for (int w = 0; w < W; w++) {
+        uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
+        uint32_t m = row[w] & bm;
+        cnt += popc(m);
+        if (multi) cnt += popc(m & tc[n->o_mlo + s * W + w]) + 2 * popc(m & tc[n->o_mhi + s * W + w]);
+      }
+    } else {
+      /* edge-id form: the pair (s, v) is bit row_ptr[s] + rank of v in adj[s] of the blocked bitset */
+      uint32_t row[W], cand[W];
+      const int a = row_ptr(s);
+      int deg = 0;
+      for (int w = 0; w < W; w++) {
+        row[w] = adj(s, w);
+        deg += popc(row[w]);
+        cand[w] = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
+      }
+      int nb = deg; /* pairs walked before the hit (all of them when nothing is hit) */
+      const uint32_t* b = blocked();
+      for (;;) { /* first candidate whose edge is not blocked (volt:1157-1159) */
+        int w0 = -1;
+        uint32_t cw = 0;
+        for (int w = W - 1; w >= 0; w--) { bool nz = cand[w] != 0; w0 = nz ? w : w0; cw = nz ? cand[w] : cw; }
+        if (w0 < 0) break;
+        uint32_t lb = cw & (0u - cw);
+        int rk = 0;
+        for (int w = 0; w < W; w++) rk += popc(row[w] & ((w < w0 ? 0xFFFFFFFFu : 0u) | ((lb - 1u) & eqmask(w, w0))));
+        int e = a + rk;
+        if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) {
+          for (int w = 0; w < W; w++) cand[w] ^= lb & eqmask(w, w0);
+          continue;
+        }
+        vw = w0; hitbit = lb; nb = rk;
+        break;
+      }
+      cnt = nb;
+      if (has_blk && nb > 0) { /* minus the blocked pairs among the first nb of the row */
+        uint32_t xb[W];
+        window(b, n->EW, a, nb, 0u, xb);
+        for (int q = 0; q < W; q++) cnt -= popc(xb[q]);
+      }
+      for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged */
+        int off = (int)((dmo >> (10 * k)) & 0xFFu);
+        if (off == 0xFF || off >= nb) continue;
+        int e = a + off;
+        if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
+        cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
+      }
+    }
+    if (vw < 0) { rule3 = false; return -1; }
+    const int v = vw * 32 + ctz(hitbit);
+    rule3 = !is_dc && !devbit(n->o_reach, v);
+    return v;
+  }
+  /* the exploit slot an attack uses: zero-day remap (volt:1131-1146); -1 = no such exploit */
+  CYG_HD int resolve_exploit(int raw, uint32_t zday_draw) {
+    const cyg_config& c = n->cfg;
+    if (c.zero_day && !(raw >= 0 && raw < 32 && ((c.zero_day_mask >> raw) & 1u))) /* volt:1135-1136 */
+      raw = select_in_word(c.zero_day_mask, (int)below(zday_draw, (uint32_t)popc(c.zero_day_mask)));
+    return (raw >= 0 && raw < c.n_exploits) ? raw : -1; /* ids are strings: an int never matches (volt:1141) */
+  }
+  CYG_HD bool needs_zday_draw(int raw) {
+    const cyg_config& c = n->cfg;
+    return c.zero_day && !(raw >= 0 && raw < 32 && ((c.zero_day_mask >> raw) & 1u));
+  }
+
   CYG_HD void attacker_act(const Act& a, int atype, double& cost) {
     const cyg_config& c = n->cfg;
     if (c.base_line == CYG_BL_NO_ATTACK) return;
@@ -1062,94 +1151,25 @@ struct Env {
       for (int w = 0; w < W; w++) { comp[w] = pl(P_COMP, w); known[w] = pl(P_KNOWN, w); }
       for (int xi = 0; xi < a.n_ex; xi++) {
         int raw = a.ex(xi);
-        if (c.zero_day && !(raw >= 0 && raw < 32 && ((c.zero_day_mask >> raw) & 1u))) { /* volt:1135-1136 */
-          int cnt = popc(c.zero_day_mask);
-          raw = select_in_word(c.zero_day_mask, (int)below(zday.next(rng), (uint32_t)cnt));
-        }
-        if (!(raw >= 0 && raw < c.n_exploits)) continue; /* ids are strings: an int never matches (volt:1141) */
+        raw = resolve_exploit(raw, needs_zday_draw(raw) ? zday.next(rng) : 0u);
+        if (raw < 0) continue;
         uint32_t kv[W], dcby[W]; /* known & vulnerable to this exploit; compromised_by additions */
         for (int w = 0; w < W; w++) { kv[w] = known[w] & m_vuln(raw, w); dcby[w] = 0; }
         uint32_t todo[W];
         for (int w = 0; w < W; w++) todo[w] = src[w];
-        {
-          for (;;) {
-            const int s = pop_lowest(todo);
-            if (s < 0) break;
+        for (;;) {
+          const int s = pop_lowest(todo);
+          if (s < 0) break;
+          int cnt;
+          bool rule3;
+          const int v = attack_source(s, comp, kv, has_blk, nx, cnt, rule3);
+          logs += (uint32_t)cnt + (v >= 0 ? 1u : 0u);
+          if (v >= 0) {
             const bool is_dc = devbit(n->o_dc, s);
-            const uint32_t dmo = T(n->o_dmulti + 2 * s);
-            int vw = -1;
-            uint32_t hitbit = 0;
-            int cnt; /* hops logged before the hit */
-            if (nx > 0 || (dmo >> 31)) {
-              /* general form: materialise the unblocked row (extra edges, > 2 multi-edges in the row) */
-              uint32_t row[W];
-              live_row(s, has_blk, nx, row);
-              uint32_t cand_w = 0;
-              for (int w = W - 1; w >= 0; w--) {
-                uint32_t cand = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
-                bool nz = cand != 0;
-                vw = nz ? w : vw;
-                cand_w = nz ? cand : cand_w;
-              }
-              hitbit = cand_w & (0u - cand_w);
-              cnt = 0;
-              const bool multi = devbit(n->o_rowmulti, s);
-              for (int w = 0; w < W; w++) {
-                uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
-                uint32_t m = row[w] & bm;
-                cnt += popc(m);
-                if (multi) cnt += popc(m & tc[n->o_mlo + s * W + w]) + 2 * popc(m & tc[n->o_mhi + s * W + w]);
-              }
-            } else {
-              /* edge-id form: the pair (s, v) is bit row_ptr[s] + rank of v in adj[s] of the blocked bitset */
-              uint32_t row[W], cand[W];
-              const int a = row_ptr(s);
-              int deg = 0;
-              for (int w = 0; w < W; w++) {
-                row[w] = adj(s, w);
-                deg += popc(row[w]);
-                cand[w] = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
-              }
-              int nb = deg; /* pairs walked before the hit (all of them when nothing is hit) */
-              const uint32_t* b = blocked();
-              for (;;) { /* first candidate whose edge is not blocked (volt:1157-1159) */
-                int w0 = -1;
-                uint32_t cw = 0;
-                for (int w = W - 1; w >= 0; w--) { bool nz = cand[w] != 0; w0 = nz ? w : w0; cw = nz ? cand[w] : cw; }
-                if (w0 < 0) break;
-                uint32_t lb = cw & (0u - cw);
-                int rk = 0;
-                for (int w = 0; w < W; w++) rk += popc(row[w] & ((w < w0 ? 0xFFFFFFFFu : 0u) | ((lb - 1u) & eqmask(w, w0))));
-                int e = a + rk;
-                if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) {
-                  for (int w = 0; w < W; w++) cand[w] ^= lb & eqmask(w, w0);
-                  continue;
-                }
-                vw = w0; hitbit = lb; nb = rk;
-                break;
-              }
-              cnt = nb;
-              if (has_blk && nb > 0) { /* minus the blocked pairs among the first nb of the row */
-                uint32_t xb[W];
-                window(b, n->EW, a, nb, 0u, xb);
-                for (int q = 0; q < W; q++) cnt -= popc(xb[q]);
-              }
-              for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged (volt:1161) */
-                int off = (int)((dmo >> (10 * k)) & 0xFFu);
-                if (off == 0xFF || off >= nb) continue;
-                int e = a + off;
-                if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
-                cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
-              }
-            }
-            /* log_communication once per hop walked (volt:1161): all repeats of the neighbours before the hit, +1 */
-            logs += (uint32_t)cnt + (vw >= 0 ? 1u : 0u);
-            if (vw >= 0) {
-              for (int w = 0; w < W; w++) {
-                uint32_t hb = hitbit & eqmask(w, vw);
-                comp[w] |= hb;
-                dcby[w] |= is_dc ? hb : 0u;
-              }
+            for (int w = 0; w < W; w++) {
+              uint32_t hb = (1u << (v & 31)) & eqmask(w, v >> 5);
+              comp[w] |= hb;
+              dcby[w] |= is_dc ? hb : 0u;
             }
           }
         }

@@ -104,16 +104,24 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
   p.off_recs = smem_take(o, (size_t)NB * S * 4);
   p.off_out = smem_take(o, (size_t)NB * 2 * 4); /* phase B -> C carry: action cost, topology-dirty flag */
   p.off_perm = smem_take(o, (size_t)NB * 2);
-  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 3) * 4); /* key histogram / run ends + two task counters */
+  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 4) * 4); /* key histogram / run ends + three task counters */
   p.off_bar = smem_take(o, 8);
   p.total = o;
   return p;
 }
 
+/* CTA-level phase timestamps (profiling build -DCYG_CTA_TIMING: thread 0 writes clock64 at the phase boundaries) */
+#ifdef CYG_CTA_TIMING
+#define CYG_CTA_MARK(i) do { if (p.dbg_cycles && threadIdx.x == 0) p.dbg_cycles[(size_t)blockIdx.x * 8 + (i)] = (unsigned long long)clock64(); } while (0)
+#else
+#define CYG_CTA_MARK(i) do { } while (0)
+#endif
+
 template <int W>
 __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>(cyg_smem);
   const int NB = p.block_envs, NT = blockDim.x, tid = threadIdx.x; /* NB envs, NT >= NB threads */
+  CYG_CTA_MARK(0);
   const int S = p.net.S, M = p.net.M;
   const int env0 = blockIdx.x * NB;
   const int nb = min(NB, p.B - env0);
@@ -137,8 +145,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     bulk_g2s(s_tab, p.net.blob, tab_bytes, bar);
     if (bulk_ok) bulk_g2s(s_rec, g_rec, rec_bytes, bar);
   }
-  if (tid < CYG_NKEYS + 3) s_cnt[tid] = 0;
+  if (tid < CYG_NKEYS + 4) s_cnt[tid] = 0;
   __syncthreads(); /* mbarrier initialised, counters zeroed */
+  CYG_CTA_MARK(1);
 
   /* ---- sort the block's envs by the action type they will execute (needs only the action headers, so it
    *      overlaps the bulk copies): a warp then runs ONE branch of the 14 defender / 3+X attacker actions ---- */
@@ -165,6 +174,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   }
   mbar_wait(bar, 0);
   __syncthreads();
+  CYG_CTA_MARK(2);
 
   /* ---- phase A, thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or
    *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
 #endif
     const int mode = (int)((act[0] >> 8) & 1u);
     int atype = e.step_pre(act, p.flags);
-    deferred = coop_ok && Coop<W>::is_heavy(mode, atype);
+    deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && p.net.cfg.base_line == CYG_BL_NO_ATTACK);
     if (!deferred) {
       double cost = 0.0;
       bool dirty = false;
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     }
 #ifdef CYG_PHASE_TIMING
     if (p.dbg_cycles) for (int i = 0; i < 8; i++) p.dbg_cycles[(size_t)env * 8 + i] = (unsigned long long)(ph[i] - t_begin);
-#else
+#elif !defined(CYG_CTA_TIMING)
     if (p.dbg_cycles) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
 #endif
   }
@@ -215,7 +225,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
    *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
   if (coop_ok) {
     __syncthreads();
-    if (tid == 0) { s_cnt[CYG_NKEYS + 1] = 0; s_cnt[CYG_NKEYS + 2] = 0; } /* task counters */
+  CYG_CTA_MARK(3);
+    if (tid == 0) { s_cnt[CYG_NKEYS + 1] = 0; s_cnt[CYG_NKEYS + 2] = 0; s_cnt[CYG_NKEYS + 3] = 0; } /* task counters */
     __syncthreads();
     /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
      * groups were measured slower (the groups of a warp diverge and no longer issue together). */
@@ -249,7 +260,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (lg == 0) e.load_costs();
         Coop<W>::template flip<G>(e, a, task < n9 ? 9 : 6, cost, dirty);
         if (lg == 0) {
-#ifndef CYG_PHASE_TIMING
+#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
           if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
 #endif
 #ifdef CYG_COUNT_ROUNDS
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (lane == 0) e.load_costs();
         Coop<W>::defender(e, a, atype, cost, dirty);
         if (lane == 0) {
-#ifndef CYG_PHASE_TIMING
+#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
           if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0); /* heavy envs: phase-B cycles */
 #endif
           e.store_costs();
@@ -313,7 +324,42 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         __syncwarp();
       }
     }
+    /* B3: attacker exploit + lateral movement (key 16|1), one env per warp */
+    if (p.net.cfg.base_line != CYG_BL_NO_ATTACK) {
+      const int lo = (int)s_cnt[17], ntasks = (int)s_cnt[18] - lo;
+      for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 3], 1u);
+        task = __shfl_sync(0xFFFFFFFFu, task, 0);
+        if (task >= ntasks) break;
+        const int el_b = s_perm[lo + task];
+        const int env_b = env0 + el_b;
+        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
+                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+        e.resume_epoch();
+        uint32_t act[4 + W];
+        {
+          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+        }
+        typename Env<W, true>::Act a;
+        Env<W, true>::decode(act, act + 4, nullptr, a);
+        long long tb0 = p.dbg_cycles ? clock64() : 0;
+        Coop<W>::attack(e, a);
+        if (lane == 0) {
+#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
+          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
+#endif
+          s_out[el_b] = 0.f;
+          s_out[NB + el_b] = __int_as_float(0);
+        }
+        __syncwarp();
+      }
+    }
     __syncthreads();
+  CYG_CTA_MARK(4);
     /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
     if (deferred) {
       Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
@@ -321,12 +367,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       e.resume_epoch();
       float raw, shaped;
       int32_t done;
-      e.step_post(CYG_MODE_DEFENDER, (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
+      e.step_post((int)((p.hdr[(size_t)env * 4] >> 8) & 1u), (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
                   p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
       p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
     }
   }
   __syncthreads();
+  CYG_CTA_MARK(5);
 
   /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
   if (p.obs && p.obs_mode) {
@@ -342,6 +389,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   if (bulk_ok) {
     fence_proxy_async(); /* generic-proxy writes to smem -> visible to the async proxy */
     __syncthreads();
+  CYG_CTA_MARK(6);
     if (tid == 0) {
       bulk_s2g(g_rec, s_rec, rec_bytes);
       bulk_commit_wait_read();
