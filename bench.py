@@ -234,28 +234,20 @@ def main():
     clocks = sampler.stop()
     errs = int(max(int(s.error_flags().max().item()) for s in sets))
 
-    # ---- e2e: through VectorCyberDefenseEnv with HOST buffers (pinned), H2D + step + D2H every step ----
+    # ---- e2e: the public host-buffer call VectorCyberDefenseEnv.step_host(): every step copies that step's actions
+    #      from pinned host memory, launches the kernel, reads (raw, shaped, done) back and synchronises ----
     e2e = None
     if not a.no_e2e:
         Ke = max(10, min(K, 100))
-        host = []
+        env = sets[0]
+        act_host, out_host = env.host_buffers()
+        host_actions = []
         for mode in (0, 1):
             ab = ring[mode][0]
-            host.append((ab.hdr.cpu().pin_memory(), ab.mask.cpu().pin_memory()))
-        d_hdr = torch.empty_like(ring[0][0].hdr)
-        d_mask = torch.empty_like(ring[0][0].mask)
-        out_host = torch.empty(3, B, dtype=torch.float32).pin_memory()
-        env = sets[0]
+            host_actions.append(torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory())
 
         def e2e_step(i):
-            h, m = host[i & 1]
-            d_hdr.copy_(h, non_blocking=True)
-            d_mask.copy_(m, non_blocking=True)
-            raw, shaped, done = env.step(ActionBatch(d_hdr, d_mask))
-            out_host[0].copy_(raw, non_blocking=True)
-            out_host[1].copy_(shaped, non_blocking=True)
-            out_host[2].copy_(done.view(torch.float32), non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the caller reads rewards / done before the next action
+            env.step_host(host_actions[i & 1])       # this step's actions live in the caller's pinned host memory
 
         for i in range(3):
             e2e_step(i)
@@ -267,7 +259,7 @@ def main():
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)
-        e2e = (ems, Ke, host[0][0].numel() * 4 + host[0][1].numel() * 4, 3 * B * 4)
+        e2e = (ems, Ke, act_host.numel() * 4, out_host.numel() * 4)
 
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

@@ -90,9 +90,11 @@ class VectorCyberDefenseEnv:
         K.check(self.L.cyg_bind(self.h, _ptr(self._state)))
         self.records = self._state[: self.B * self.S].view(self.B, self.S)
         self.scalars = self.records[:, : K.NSCAL]  # live view of the 16 CYG_S_* scalars of every env
-        self.raw = torch.zeros(self.B, dtype=torch.float32, device=self.device)
-        self.shaped = torch.zeros(self.B, dtype=torch.float32, device=self.device)
-        self.done = torch.zeros(self.B, **i32)
+        # raw | shaped | done share one buffer so that a host caller reads all three with ONE device->host copy
+        self._out = torch.zeros(3, self.B, dtype=torch.float32, device=self.device)
+        self.raw, self.shaped = self._out[0], self._out[1]
+        self.done = self._out[2].view(torch.int32)
+        self._host = None
         self._stream = stream
         self._obs = {}
         self._pre = None
@@ -198,6 +200,37 @@ class VectorCyberDefenseEnv:
         K.check(self.L.cyg_step(self.h, C.byref(a), flags, C.byref(o), self._s()))
         self._hold = (hdr, mask, order)
         return self.raw, self.shaped, self.done
+
+    # ---- host-buffer front end: what a CPU-side caller (the reference's rollout loops) uses ----
+    def host_buffers(self):
+        """Pinned host staging: actions [B, 4 + W] int32 (hdr | mask) in, results [3, B] float32 (raw | shaped | done
+        bits) out.  Allocated once."""
+        if self._host is None:
+            self._host = dict(
+                act=torch.empty(self.B, 4 + self.W, dtype=torch.int32).pin_memory(),
+                out=torch.empty(3, self.B, dtype=torch.float32).pin_memory(),
+                d_act=torch.empty(self.B, 4 + self.W, dtype=torch.int32, device=self.device),
+                d_hdr=torch.empty(self.B, 4, dtype=torch.int32, device=self.device),
+                d_mask=torch.empty(self.B, self.W, dtype=torch.int32, device=self.device))
+        return self._host["act"], self._host["out"]
+
+    def step_host(self, act=None, flags=0):
+        """step() with HOST buffers: one pinned host->device copy of the actions (`act`, a pinned [B, 4 + W] int32
+        tensor of the caller's, default host_buffers()[0]), the kernel,
+        one device->host copy of (raw, shaped, done) into host_buffers()[1], then a stream synchronise (the caller
+        reads the rewards before choosing the next action).  Returns (raw, shaped, done) as host tensor views."""
+        if self._host is None:
+            self.host_buffers()
+        h = self._host
+        stream = self._stream if self._stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            h["d_act"].copy_(h["act"] if act is None else act, non_blocking=True)
+            h["d_hdr"].copy_(h["d_act"][:, :4])
+            h["d_mask"].copy_(h["d_act"][:, 4:])
+            self._step([ActionBatch(h["d_hdr"], h["d_mask"])], flags, 0, False)
+            h["out"].copy_(self._out, non_blocking=True)
+        stream.synchronize()
+        return h["out"][0], h["out"][1], h["out"][2].view(torch.int32)
 
     def _obs_buf(self, mode):
         if mode not in self._obs:
