@@ -16,7 +16,7 @@ _DEPS = [_SRC, os.path.join(_HERE, "csrc", "cyg_core.cuh"), os.path.join(_HERE, 
          os.path.join(os.path.dirname(_HERE), "include", "cygym_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]  # split-compile: ptxas of the kernels in parallel
 
 NSCAL = 16
 ATYPE_NONE = 0x80

@@ -66,7 +66,8 @@ enum {
 };
 #define CYG_REC_PLANES 16 /* word offset of plane 0 inside a record */
 #define CYG_CKI_REMOVED 0x40000000u /* internal checkpoint word, spare bit: Device.removed_before (never read by step) */
-#define CYG_MAX_W 4       /* M <= 128 for the bit-matrix kernels */
+#define CYG_MAX_W 4       /* M <= 128: the shared-memory bit-matrix step kernel (W = ceil(M/32) words per plane) */
+#define CYG_BIG_W 64      /* 128 < M <= 2048: planes padded to 64 words, stepped by the generic global-memory kernel */
 
 /* ---- shared network tables + derived sizes -------------------------------------------------
  * All tables live in ONE blob of uint32 words (cyg_tables.h); the Net holds word OFFSETS into it.  The step
@@ -75,6 +76,7 @@ enum {
 struct Net {
   cyg_config cfg;
   int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in;
+  int Wm;                     /* ceil(M/32): words per device mask in the C-ABI arrays (== W unless the planes are padded) */
   double inv_M;               /* 1.0 / M */
   uint32_t hot_words;         /* prefix of the blob that a CTA stages in shared memory */
   /* hot tables */
@@ -624,7 +626,7 @@ struct Env {
   /* device_indices as a set: the first n_dev bits of the mask (what the reference loop visits) */
   CYG_HD void listed(const Act& a, uint32_t* l) {
     int nl = 0;
-    for (int w = 0; w < W; w++) { l[w] = a.mask[w] & m_valid(w); nl += popc(l[w]); }
+    for (int w = 0; w < W; w++) { l[w] = (w < n->Wm ? a.mask[w] : 0u) & m_valid(w); nl += popc(l[w]); }
     if (a.n_dev >= nl) return;
     int keep = a.n_dev < 0 ? 0 : a.n_dev, seen = 0; /* inconsistent header: fewer entries than mask bits */
     for (int w = 0; w < W; w++) {
@@ -809,7 +811,7 @@ struct Env {
       for (int k = 0; k < 2; k++) {
         int off = (int)((dm >> (10 * k)) & 0xFFu);
         int ex = (int)((dm >> (8 + 10 * k)) & 3u);
-        bool valid = off != 0xFF && !stop && direct < 0 && wbit(x, off & 0x7F);
+        bool valid = off != 0xFF && !stop && direct < 0 && wbit(x, off);
         int lo = wrank(x, off) + extra_before;
         if (valid) {
           if (r < lo) stop = true;
@@ -1483,10 +1485,12 @@ struct Env {
     }
     CYG_MARK(5);
     if (pre_masks) { /* the `state` step() returns is the pre-evolve view (volt:1306) */
+      const int Wm = n->Wm;
       for (int w = 0; w < W; w++) {
-        pre_masks[0 * W + w] = pl(P_COMP, w);
-        pre_masks[1 * W + w] = pl(P_KNOWN, w);
-        pre_masks[2 * W + w] = pl(P_NYA, w);
+        if (w >= Wm) break;
+        pre_masks[0 * Wm + w] = pl(P_COMP, w);
+        pre_masks[1 * Wm + w] = pl(P_KNOWN, w);
+        pre_masks[2 * Wm + w] = pl(P_NYA, w);
       }
     }
     if (!skip_work || grouped) {
@@ -1570,7 +1574,7 @@ struct Env {
     hdr[1] = (uint32_t)(ex & 0xFF);
     hdr[2] = (uint32_t)ndev;
     hdr[3] = (uint32_t)app;
-    for (int w = 0; w < W; w++) mask[w] = pick[w];
+    for (int w = 0; w < W; w++) if (w < n->Wm) mask[w] = pick[w];
   }
 };
 

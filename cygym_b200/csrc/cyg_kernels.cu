@@ -399,6 +399,25 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   }
 }
 
+/* ---- large networks (128 < M <= 2048, BASELINE.json config C4): the adjacency bit matrix (M x 64 words) exceeds
+ *      shared memory, so this first correct path steps one env per thread straight on the records in global
+ *      memory with the tables read through L2.  Same transition code (cyg_core.cuh), no staging, no sort. ---- */
+template <int W>
+__global__ void __launch_bounds__(64) cyg_step_generic_kernel(const __grid_constant__ StepParams p) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  const int M = p.net.M;
+  Env<W, false> e(&p.net, p.recs + (size_t)env * p.net.S, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+                  (uint32_t)(p.env_id0 + env));
+  const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
+  float raw, shaped;
+  int32_t done;
+  const int Wm = p.net.Wm;
+  e.step(p.hdr + (size_t)env * 4, p.mask + (size_t)env * Wm, ord, (size_t)p.B * 4, (size_t)p.B * Wm, (size_t)p.B * p.order_stride,
+         p.G, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * Wm : nullptr);
+  p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+}
+
 /* ---- randomize_compromise_and_ownership: thread per env on the global record ---- */
 struct SimpleParams {
   Net net;
@@ -415,13 +434,8 @@ __global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.B) return;
   if (p.env_mask && !p.env_mask[env]) return;
-  uint32_t rec[CYG_REC_PLANES + 20 * W]; /* scalars + planes are all randomize touches */
-  uint32_t* g = p.recs + (size_t)env * p.net.S;
-  const int nw = CYG_REC_PLANES + p.net.NP * W;
-  for (int i = 0; i < nw; i++) rec[i] = g[i];
-  Env<W> e(&p.net, rec, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
   e.randomize();
-  for (int i = 0; i < nw; i++) g[i] = rec[i];
 }
 
 template <int W>
@@ -436,7 +450,7 @@ __global__ void cyg_sample_kernel(const __grid_constant__ SimpleParams p) {
   e.sample_action(p.mode, h, m);
   g[CYG_S_EPOCH] = rec[CYG_S_EPOCH];
   for (int i = 0; i < 4; i++) p.hdr[(size_t)env * 4 + i] = h[i];
-  for (int w = 0; w < W; w++) p.mask[(size_t)env * W + w] = m[w];
+  for (int w = 0; w < W; w++) if (w < p.net.Wm) p.mask[(size_t)env * p.net.Wm + w] = m[w];
 }
 
 /* ---- canonical <-> internal conversion: one warp per env, ballots build the planes ---- */
@@ -579,7 +593,8 @@ struct DeviceGuard {
     case 1: { constexpr int KW = 1; STMT; } break; \
     case 2: { constexpr int KW = 2; STMT; } break; \
     case 3: { constexpr int KW = 3; STMT; } break; \
-    default: { constexpr int KW = 4; STMT; } break; \
+    case 4: { constexpr int KW = 4; STMT; } break; \
+    default: { constexpr int KW = CYG_BIG_W; STMT; } break; \
   }
 
 static int pick_block_envs(const cyg_env_s* h, int requested) {
@@ -597,15 +612,19 @@ static int pick_block_envs(const cyg_env_s* h, int requested) {
 
 template <int W>
 static int configure_step(cyg_env_s* h) {
-  SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
-  h->smem_bytes = sp.total;
-  if (sp.total > 227 * 1024) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
-  /* opt in to the device maximum once (handles with different block sizes share the kernel) */
-  int max_optin = 0;
-  CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  if ((int)sp.total > max_optin) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
-  CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-  return CYG_OK;
+  if constexpr (W > CYG_MAX_W) { /* generic global-memory kernel: no staging */
+    h->smem_bytes = 0;
+    return CYG_OK;
+  } else {
+    SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
+    h->smem_bytes = sp.total;
+    /* opt in to the device maximum once (handles with different block sizes share the kernel) */
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    if ((int)sp.total > max_optin) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
+    CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
+    return CYG_OK;
+  }
 }
 
 extern "C" {
@@ -724,7 +743,21 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   int threads = ((2 * h->NB + 31) / 32) * 32;
   if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
   if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
-  DISPATCH_W(h->W, (cyg_step_kernel<KW><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p)));
+  if (h->W > CYG_MAX_W) {
+    cyg_step_generic_kernel<CYG_BIG_W><<<(h->B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p);
+    if (out->obs) { /* post-evolve observation rows: a second launch on the generic path */
+      h->launches++;
+      CU(cudaGetLastError());
+      return cyg_observe(h, out->obs_mode, out->obs, stream);
+    }
+  } else {
+    switch (h->W) {
+      case 1: cyg_step_kernel<1><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
+      case 2: cyg_step_kernel<2><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
+      case 3: cyg_step_kernel<3><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
+      default: cyg_step_kernel<4><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
+    }
+  }
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

@@ -38,20 +38,20 @@ inline size_t tb_alloc(TableBlob& b, size_t nwords) {
 /* Returns "" on success, else an error message. */
 inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, TableBlob& b) {
   const int M = cfg.M, E = cfg.E, X = cfg.X;
-  if (M < 1 || M > 32 * CYG_MAX_W) return "M must be in 1..128 for the bit-matrix kernels (larger networks: CSR-tiled path, not built yet)";
+  if (M < 1 || M > 32 * CYG_BIG_W) return "M must be in 1..2048";
   if (E < 0 || E > 65535) return "E out of range";
   if (X < 1 || X > 6) return "X (MaxExploits) must be in 1..6";
   if (cfg.n_exploits < 0 || cfg.n_exploits > X) return "n_exploits must be in 0..X";
   if (cfg.xcap < 0 || cfg.xcap > 4095) return "xcap out of range";
   if (cfg.evolve_period < 1) return "evolve_period must be >= 1";
   if (cfg.wl_period_max < 1) return "wl_period_max must be >= 1";
-  const int W = (M + 31) / 32;
+  const int W = M <= 32 * CYG_MAX_W ? (M + 31) / 32 : CYG_BIG_W; /* large networks: planes padded to 64 words */
   const int EW = E > 0 ? (E + 31) / 32 : 1;
   if (hn.row_ptr[0] != 0 || hn.row_ptr[M] != E) return "row_ptr must start at 0 and end at E";
   Net& n = b.net;
   memset(&n, 0, sizeof(n));
   n.cfg = cfg;
-  n.M = M; n.W = W; n.E = E; n.EW = EW;
+  n.M = M; n.W = W; n.E = E; n.EW = EW; n.Wm = (M + 31) / 32;
   n.ncby = cfg.n_exploits > 0 ? cfg.n_exploits : 1;
   n.NP = P_CBY0 + n.ncby;
   n.off_blocked = CYG_REC_PLANES + n.NP * W;

@@ -63,11 +63,11 @@ static void step_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, u
     import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL,
                   ckpt + (size_t)b * n.M);
     const uint32_t* h = hdr + (size_t)b * 4;
-    const uint32_t* m = mask + (size_t)b * W;
+    const uint32_t* m = mask + (size_t)b * n.Wm;
     const uint16_t* o = order ? order + (size_t)b * order_stride : nullptr;
     Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
-    int atype = e.step(h, m, o, (size_t)B * 4, (size_t)B * W, (size_t)B * order_stride, G, flags, raw + b, shaped + b,
-                       done + b, pre_masks ? pre_masks + (size_t)b * 3 * W : nullptr);
+    int atype = e.step(h, m, o, (size_t)B * 4, (size_t)B * n.Wm, (size_t)B * order_stride, G, flags, raw + b, shaped + b,
+                       done + b, pre_masks ? pre_masks + (size_t)b * 3 * n.Wm : nullptr);
     if (exec_atype) exec_atype[b] = atype;
     export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL,
                   ckpt + (size_t)b * n.M);
@@ -96,7 +96,7 @@ static void sample_w(Emu* em, int B, int env_id0, uint32_t* scal, int mode, uint
   for (int b = 0; b < B; b++) {
     for (int i = 0; i < CYG_NSCAL; i++) rec[i] = scal[(size_t)b * CYG_NSCAL + i];
     Env<W> e(&n, rec.data(), nullptr, nullptr, (uint32_t)(env_id0 + b));
-    e.sample_action(mode, hdr + (size_t)b * 4, mask + (size_t)b * W);
+    e.sample_action(mode, hdr + (size_t)b * 4, mask + (size_t)b * n.Wm);
     for (int i = 0; i < CYG_NSCAL; i++) scal[(size_t)b * CYG_NSCAL + i] = rec[i];
   }
 }
@@ -118,7 +118,8 @@ static void observe_w(Emu* em, int B, const uint32_t* dev, int obs_mode, float* 
     case 1: fn<1>(__VA_ARGS__); break;              \
     case 2: fn<2>(__VA_ARGS__); break;              \
     case 3: fn<3>(__VA_ARGS__); break;              \
-    default: fn<4>(__VA_ARGS__); break;             \
+    case 4: fn<4>(__VA_ARGS__); break;              \
+    default: fn<CYG_BIG_W>(__VA_ARGS__); break;     \
   }
 
 extern "C" {

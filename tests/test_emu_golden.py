@@ -24,6 +24,8 @@ def test_device_source_replays_golden(path):
     (100, 8, 32, 80, dict(p_add=0.5, p_attacker=0.4, lambda_events=1.5)),
     (33, 2, 32, 80, dict(zero_day=1, zero_day_mask=0b10)),
     (128, 4, 16, 60, {}),
+    (300, 8, 160, 12, {}),                    # > 128 device slots: the 64-word generic layout
+    (2000, 64, 3, 16, {}),                    # BASELINE.json config C4 shape
 ])
 def test_device_source_matches_oracle_on_random_rollouts(M, subnets, B, T, kw):
     from cygym_b200 import synthetic_network

@@ -90,6 +90,12 @@ def test_ragged_batch_and_odd_sizes():
     _rollout_vs_oracle(1, 1, 5, 20, num_of_device=1)
 
 
+def test_c4_large_network_2000_devices_64_subnets():
+    """BASELINE.json config C4: the adjacency bit matrix exceeds shared memory -> generic global-memory kernel."""
+    _rollout_vs_oracle(2000, 64, 1024, 12, obs_every=5, xcap=256)  # ~100 attacker-owned devices: up to 198 hub-star edges
+    _rollout_vs_oracle(300, 8, 200, 30)
+
+
 def test_evolving_topology_with_attacker_arrivals():
     _rollout_vs_oracle(60, 3, 512, 80, xcap=160, p_add=0.5, p_attacker=0.4, lambda_events=1.5)
 
@@ -203,5 +209,5 @@ def test_errors_are_loud():
     rc = env.L.cyg_step(env.h, C.byref(a), 0, C.byref(o), None)
     assert rc == K.E_INVAL and b"null" in env.L.cyg_last_error()
     with pytest.raises(K.CygError):
-        big = synthetic_network(200, n_subnets=4, seed=1)
-        VectorCyberDefenseEnv(big, 4)
+        net.cfg["evolve_period"] = 0
+        VectorCyberDefenseEnv(net, 4)
