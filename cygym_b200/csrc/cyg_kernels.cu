@@ -87,6 +87,8 @@ struct StepParams {
 };
 
 #define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
+#define CYG_TMA_STORE 1 /* records go back with one bulk store; plain coalesced stores measured the same (the
+                          write-back is bound by the per-SM path to L2: ~16k cycles for 210 KB either way) */
 #define CYG_MAX_BLOCK_ENVS 512   /* envs per CTA */
 #define CYG_MAX_BLOCK_THREADS 896 /* threads per CTA: 72 registers per thread at one CTA per SM.  A CTA runs twice as
                                     many threads as envs: phases A / C use one thread per env, the warp-per-env phase
@@ -385,17 +387,29 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     }
   }
 
-  /* ---- write the block's records back: one bulk store ---- */
-  if (bulk_ok) {
-    fence_proxy_async(); /* generic-proxy writes to smem -> visible to the async proxy */
+  /* ---- write the block's records back ---- */
+#ifdef CYG_TMA_STORE
+  if (bulk_ok) { /* one bulk store; every writer fences generic -> async proxy first */
+    fence_proxy_async();
     __syncthreads();
-  CYG_CTA_MARK(6);
+    CYG_CTA_MARK(6);
     if (tid == 0) {
       bulk_s2g(g_rec, s_rec, rec_bytes);
       bulk_commit_wait_read();
     }
-  } else {
-    for (int i = tid; i < nb * S; i += NT) g_rec[i] = s_rec[i];
+  } else
+#endif
+  {
+    /* coalesced 16-byte stores by all warps (tail blocks whose span is not 16-byte sized / aligned) */
+    if (bulk_ok) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(s_rec);
+      uint4* g4 = reinterpret_cast<uint4*>(g_rec);
+      const int n4 = (int)(rec_bytes >> 4);
+      for (int i = tid; i < n4; i += NT) g4[i] = s4[i];
+    } else {
+      for (int i = tid; i < nb * S; i += NT) g_rec[i] = s_rec[i];
+    }
+    CYG_CTA_MARK(6);
   }
 }
 
