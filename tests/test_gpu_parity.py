@@ -36,13 +36,19 @@ def test_cuda_replays_golden(path):
     assert n == len(g["kind"])
 
 
-def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64, **kw):
+def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64, dense_multi=False, base_line="Nash", **kw):
     import torch
     from cygym_b200 import synthetic_network
     from cygym_b200.vector_env import VectorCyberDefenseEnv, ActionBatch
     net = synthetic_network(M, n_subnets=subnets, seed=seed, **kw)
-    orc, cfg = oracle_for(net, seed=1234, xcap=xcap, env_id0=env_id0)
-    env = VectorCyberDefenseEnv(net, B, seed=1234, env_id0=env_id0, xcap=xcap)
+    if dense_multi:  # ~10 % of the pairs become multi-edges of multiplicity 2..4 (> 2 per list -> the general routines)
+        rng = np.random.default_rng(M)
+        m = net.mult.copy()
+        idx = rng.choice(len(m), size=max(1, len(m) // 10), replace=False)
+        m[idx] = rng.integers(2, 5, size=len(idx))
+        net.mult = m
+    orc, cfg = oracle_for(net, seed=1234, xcap=xcap, env_id0=env_id0, base_line=base_line)
+    env = VectorCyberDefenseEnv(net, B, seed=1234, env_id0=env_id0, xcap=xcap, base_line=base_line)
     so = oracle_state_from_template(orc, net, B)
     for t in range(T):
         mode = t & 1
@@ -98,6 +104,17 @@ def test_c4_large_network_2000_devices_64_subnets():
 
 def test_evolving_topology_with_attacker_arrivals():
     _rollout_vs_oracle(60, 3, 512, 80, xcap=160, p_add=0.5, p_attacker=0.4, lambda_events=1.5)
+
+
+def test_dense_multi_edges_and_other_attributes():
+    """Dense multi-edges (general block/unblock and attack routines inside the warp-per-env phase), workload caps,
+    frequent arrivals, odd evolve periods, every base line."""
+    _rollout_vs_oracle(100, 8, 1024, 50, dense_multi=True)
+    _rollout_vs_oracle(64, 4, 600, 50, dense_multi=True, xcap=200, zero_day=1, zero_day_mask=0b11, p_attacker=0.5, p_add=0.5, lambda_events=1.2)
+    _rollout_vs_oracle(100, 8, 900, 40, workload_period_base=3, workload_period_max=12, workload_cap=5)
+    _rollout_vs_oracle(40, 1, 500, 40, scaling_vulnerability=0, evolve_period=3, default_high=5)
+    for bl in ("No Defense", "Preset", "No Attack"):
+        _rollout_vs_oracle(50, 3, 300, 16, base_line=bl)
 
 
 def test_zero_day_remap():
