@@ -229,6 +229,7 @@ struct Env {
   uint32_t* xtra;  /* extra (attacker hub-star) edges of this env [xcap] (global memory) */
   Rng rng;
   Stream stall;    /* SITE_STALL is shared by every group of a grouped step */
+  int bl;          /* base_line in effect for this env (CYG_BL_*): cfg.base_line unless the caller set one per env */
   double defcost, cleancost;
   long long* phase_t = nullptr; /* profiling builds only */
   int dbg_rounds = 0;           /* profiling builds only */
@@ -236,7 +237,7 @@ struct Env {
   CYG_HD Env(const Net* net, uint32_t* record, uint32_t* ck, uint32_t* xt, uint32_t env_id, uint32_t rec_off = 0,
              uint32_t tab_off = 0)
       : n(net), rec(record), th(net->blob), tc(net->blob), ro(rec_off), to(tab_off), ckpt(ck), xtra(xt), stall(SITE_STALL),
-        defcost(0.0), cleancost(0.0) {
+        bl(net->cfg.base_line), defcost(0.0), cleancost(0.0) {
     rng.k0 = (uint32_t)net->cfg.seed;
     rng.k1 = (uint32_t)(net->cfg.seed >> 32);
     rng.env = env_id;
@@ -1139,7 +1140,7 @@ struct Env {
 
   CYG_HD void attacker_act(const Act& a, int atype, double& cost) {
     const cyg_config& c = n->cfg;
-    if (c.base_line == CYG_BL_NO_ATTACK) return;
+    if (bl == CYG_BL_NO_ATTACK) return;
     if (atype != 1 && atype != 2) return;
     uint32_t src[W]; /* snapshot of compromised-or-owned devices, taken before the loop (volt:1127-1128) */
     int ns = 0;
@@ -1367,17 +1368,17 @@ struct Env {
   /* the action type step() ends up executing: None fill (volt:847-874), clamp into the action space
    * (:879-884), defender forced to the no-op unless base_line == "Nash" (:913-914).  Needs no env state,
    * so the kernel can sort a block's envs by it before their records arrive. */
-  CYG_HD static int exec_type(const cyg_config& c, uint32_t h0) {
+  CYG_HD static int exec_type(const cyg_config& c, uint32_t h0, int base_line) {
     int at = (int)(h0 & 0xFFu);
     int mode = (int)((h0 >> 8) & 1u);
     int atype = at == (int)CYG_ATYPE_NONE ? -1000 : (int)(int8_t)at;
     if (atype == -1000) {
-      if (mode == CYG_MODE_DEFENDER) atype = (c.base_line == CYG_BL_NO_DEFENSE) ? 8 : 7;
-      else atype = (c.base_line == CYG_BL_NO_ATTACK) ? 3 : 2;
+      if (mode == CYG_MODE_DEFENDER) atype = (base_line == CYG_BL_NO_DEFENSE) ? 8 : 7;
+      else atype = (base_line == CYG_BL_NO_ATTACK) ? 3 : 2;
     }
     if (mode == CYG_MODE_DEFENDER) { if (!(atype >= 0 && atype < c.def_space_n)) atype = 8; }
     else { if (!(atype >= 0 && atype < c.att_space_n)) atype = 3; }
-    if (mode == CYG_MODE_DEFENDER && c.base_line != CYG_BL_NASH) atype = 8;
+    if (mode == CYG_MODE_DEFENDER && base_line != CYG_BL_NASH) atype = 8;
     return atype;
   }
 
@@ -1389,7 +1390,7 @@ struct Env {
     begin_epoch();
     CYG_MARK(0);
     if (flags & CYG_STEP_GROUPED) return 0;
-    int atype = exec_type(n->cfg, hdr[0]);
+    int atype = exec_type(n->cfg, hdr[0], bl);
     tick_busyset(); /* volt:904-908 */
     CYG_MARK(1);
     return atype;
@@ -1427,7 +1428,7 @@ struct Env {
         int gt = ga.atype == -1000 ? 0 : ga.atype;
         if (gt == 0) gt = (mode == CYG_MODE_DEFENDER) ? 8 : 3;
         if (mode == CYG_MODE_DEFENDER) {
-          if (c.base_line != CYG_BL_NASH) gt = 8;
+          if (bl != CYG_BL_NASH) gt = 8;
           defender_meta(ga, gt, true, cost, dirty);
           if (gt == 1) {
             double ds = (double)c.def_scale;

@@ -82,6 +82,7 @@ struct StepParams {
   uint32_t* pre_masks;
   float* obs;
   unsigned long long* dbg_cycles; /* optional [B]: SM cycles each env's step took (diagnostics) */
+  const uint8_t* bl_env;          /* optional [B]: base_line per env (CYG_BL_*); NULL = cfg.base_line for all */
   int B, env_id0, G, order_stride, obs_mode, block_envs;
   uint32_t flags;
 };
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   if (tid < nb) {
     if (!grouped) {
       uint32_t h0 = p.hdr[(size_t)(env0 + tid) * 4];
-      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W, true>::exec_type(p.net.cfg, h0) & 15);
+      const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
+      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15);
     }
     atomicAdd(&s_cnt[key + 1], 1u);
   }
@@ -203,8 +205,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     e.phase_t = ph;
 #endif
     const int mode = (int)((act[0] >> 8) & 1u);
+    if (p.bl_env) e.bl = (int)p.bl_env[env];
     int atype = e.step_pre(act, p.flags);
-    deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && p.net.cfg.base_line == CYG_BL_NO_ATTACK);
+    deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
     if (!deferred) {
       double cost = 0.0;
       bool dirty = false;
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         }
         typename Env<W, true>::Act a;
         Env<W, true>::decode(act, act + 4, nullptr, a);
-        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0]);
+        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0], p.bl_env ? (int)p.bl_env[env_b] : p.net.cfg.base_line);
         double cost = 0.0;
         bool dirty = false;
         long long tb0 = p.dbg_cycles ? clock64() : 0;
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       }
     }
     /* B3: attacker exploit + lateral movement (key 16|1), one env per warp */
-    if (p.net.cfg.base_line != CYG_BL_NO_ATTACK) {
+    {
       const int lo = (int)s_cnt[17], ntasks = (int)s_cnt[18] - lo;
       for (;;) {
         int task = 0;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (task >= ntasks) break;
         const int el_b = s_perm[lo + task];
         const int env_b = env0 + el_b;
+        if ((p.bl_env ? (int)p.bl_env[env_b] : p.net.cfg.base_line) == CYG_BL_NO_ATTACK) continue; /* phase A did it */
         Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                        (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
         e.resume_epoch();
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(64) cyg_step_generic_kernel(const __grid_const
   const int M = p.net.M;
   Env<W, false> e(&p.net, p.recs + (size_t)env * p.net.S, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
                   (uint32_t)(p.env_id0 + env));
+  if (p.bl_env) e.bl = (int)p.bl_env[env];
   const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
   float raw, shaped;
   int32_t done;
@@ -577,6 +582,7 @@ struct cyg_env_s {
   uint32_t* state;   /* bound internal buffer: [B][S] records then [B][M] checkpoint words */
   int B, env_id0, device, W, NB, n_sms;
   unsigned long long* dbg_cycles;
+  const uint8_t* bl_env;
   size_t smem_bytes;
   int64_t launches;
 };
@@ -657,7 +663,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   if (!h) return fail(CYG_E_NOMEM, "out of host memory");
   std::string err = build_tables(*cfg, *host_net, h->blob);
   if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
-  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr;
+  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr;
   h->W = h->blob.net.W;
   DeviceGuard g(device);
   if (!g.ok) { delete h; return fail(CYG_E_CUDA, "cudaSetDevice failed"); }
@@ -690,6 +696,12 @@ int cyg_destroy(cyg_handle h) {
 int cyg_set_base_line(cyg_handle h, int32_t base_line) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   h->net.cfg.base_line = base_line;
+  return CYG_OK;
+}
+
+int cyg_set_base_line_per_env(cyg_handle h, const uint8_t* base_line) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  h->bl_env = base_line;
   return CYG_OK;
 }
 
@@ -748,7 +760,7 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   p.recs = h->state; p.ckpt = ckpt_of(h); p.xtra = xtra_of(h);
   p.hdr = a->hdr; p.mask = a->mask; p.order = a->order;
   p.raw = out->raw_reward; p.shaped = out->shaped_reward; p.done = out->done;
-  p.pre_masks = out->pre_masks; p.obs = out->obs; p.dbg_cycles = h->dbg_cycles;
+  p.pre_masks = out->pre_masks; p.obs = out->obs; p.dbg_cycles = h->dbg_cycles; p.bl_env = h->bl_env;
   p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;

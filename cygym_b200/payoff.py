@@ -98,3 +98,60 @@ def evaluate_payoff_matrix(network, def_strategies, att_strategies, n_rollouts, 
     if not reduce:
         return sums
     return reduce_payoff(sums, n_rollouts, steps_per_episode, group=group)
+
+
+def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_rollouts, steps_per_episode=100, seed=0,
+                                   device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True):
+    """Same result as evaluate_payoff_matrix(), with ALL (pair, rollout) combinations in one batch: the flattened
+    index g = pair * n_rollouts + rollout is split contiguously over the ranks (env id == g, so the draw streams
+    do not depend on the number of ranks), every turn is ONE kernel launch, baselines act through the per-env
+    base_line array (cyg_set_base_line_per_env) and fixed-sequence strategies through per-pair action rows gathered
+    to the envs on the device.  Strategies with unsorted / repeated device lists are not handled here (use the
+    per-pair evaluator)."""
+    import torch
+    from .vector_env import ActionBatch, VectorCyberDefenseEnv
+    from . import _capi as K
+    nd, na = len(def_strategies), len(att_strategies)
+    P = nd * na
+    lo, hi = shard_range(P * n_rollouts, rank, world)
+    nloc = hi - lo
+    sums = torch.zeros(P, len(COLUMNS), dtype=torch.float64, device=device)
+    if nloc > 0:
+        M = network.M
+        env = VectorCyberDefenseEnv(network, nloc, device=device, seed=seed, env_id0=lo, xcap=xcap)
+        pair_of_env = (torch.arange(lo, hi, device=device) // n_rollouts)
+        i_of_pair = torch.arange(P, device=device) // na
+        j_of_pair = torch.arange(P, device=device) % na
+        env.randomize_compromise_and_ownership()
+        s = env.scalars
+        for slot in (K.S_STEP, K.S_DEF_STEP, K.S_ATT_STEP, K.S_WORK, K.S_CKPT, K.S_DEFCOST, K.S_CLEANCOST, K.S_REVERT, K.S_SCAN):
+            s[:, slot] = 0
+        bl_pair = torch.full((P,), K.BASE_LINES["Nash"], dtype=torch.uint8, device=device)
+        ret = torch.zeros(2, nloc, dtype=torch.float64, device=device)
+        for t in range(steps_per_episode):
+            mode = t & 1
+            strategies = def_strategies if mode == 0 else att_strategies
+            decided = [st.decide(t) for st in strategies]
+            for a, _ in decided:
+                if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
+                    raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
+            hdr, mask, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
+            which = i_of_pair if mode == 0 else j_of_pair
+            new_bl = torch.tensor([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], dtype=torch.uint8, device=device)[which]
+            bl_pair = torch.where(new_bl == 255, bl_pair, new_bl)   # a strategy that sets no base_line leaves it as it was
+            env.set_base_line_per_env(bl_pair[pair_of_env])
+            sel = which[pair_of_env]
+            ab = ActionBatch(torch.from_numpy(hdr.view(np.int32)).to(device)[sel].contiguous(),
+                             torch.from_numpy(mask.view(np.int32)).to(device)[sel].contiguous())
+            raw, _, _ = env.step(ab)
+            ret[mode] += raw.double()
+        info = env.info()
+        cols = torch.stack([ret[0], ret[1], info["Compromised_devices"].double(), info["work_done"].double(),
+                            info["Scan_count"].double(), info["defensive_cost"].double(), info["checkpoint_count"].double(),
+                            info["revert_count"].double(), info["Edges Blocked"].double(), info["Edges Added"].double()], dim=1)
+        sums.index_add_(0, pair_of_env, cols)
+        env.close()
+    sums = sums.view(nd, na, len(COLUMNS))
+    if not reduce:
+        return sums
+    return reduce_payoff(sums, n_rollouts, steps_per_episode, group=group)

@@ -204,6 +204,10 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
                int32_t env_id0, int32_t device);
 int cyg_destroy(cyg_handle h);
 int cyg_set_base_line(cyg_handle h, int32_t base_line);
+/* Optional base_line PER ENV (device array [B] of CYG_BL_*, read by every following cyg_step; NULL = back to the
+ * handle-wide value).  Lets one batch hold rollouts of different (defender, attacker) strategy pairs, whose
+ * baselines set env.base_line on every turn (do_agent.py:716-719). */
+int cyg_set_base_line_per_env(cyg_handle h, const uint8_t* base_line);
 
 /* uint32 words PER ENV the caller must allocate for the kernels' internal state.  The buffer holds, in this
  * order: B records of S words (16 scalars + bit-planes + the blocked-edge bitset in out- and in-list order;

@@ -59,3 +59,11 @@ def test_payoff_matrix_matches_oracle_and_shards():
     both = reduce_payoff(parts[0] + parts[1], N, T).cpu().numpy()
     assert np.allclose(both, got, rtol=1e-12, atol=1e-9)
     assert torch.cuda.is_available()
+    # all pairs x rollouts in ONE batch (per-env base_line, one launch per turn): identical sums, any sharding
+    from cygym_b200.payoff import evaluate_payoff_matrix_batched
+    one = evaluate_payoff_matrix_batched(net, defs, atts, N, steps_per_episode=T, seed=seed, xcap=xcap).cpu().numpy()
+    assert np.allclose(one, got, rtol=1e-12, atol=1e-9), np.abs(one - got).max()
+    parts3 = [evaluate_payoff_matrix_batched(net, defs, atts, N, steps_per_episode=T, seed=seed, xcap=xcap, rank=r, world=3, reduce=False)
+              for r in range(3)]
+    three = reduce_payoff(parts3[0] + parts3[1] + parts3[2], N, T).cpu().numpy()
+    assert np.allclose(three, got, rtol=1e-12, atol=1e-9)
