@@ -44,6 +44,8 @@ class CygConfig(C.Structure):
         ("work_scale", C.c_float), ("comp_scale", C.c_float), ("def_scale", C.c_float), ("gamma", C.c_float),
         ("thr_p_add", C.c_uint64), ("thr_p_attacker", C.c_uint64),
         ("poisson_tab", C.c_uint32 * 16), ("tri_tab", C.c_uint32 * 8), ("seed", C.c_uint64),
+        ("turbo_frac_clients", C.c_double), ("turbo_frac_servers", C.c_double), ("turbo_max_clients", C.c_int32),
+        ("turbo_max_servers", C.c_int32), ("turbo_ramp_steps", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -153,4 +155,9 @@ def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=
     for i, t in enumerate(DT.triangular_ceil_table(tri_mode, tri_high)):
         c.tri_tab[i] = t
     c.seed = seed
+    c.turbo_frac_clients = cfg.get("turbo_fraction_clients", 0.05)
+    c.turbo_frac_servers = cfg.get("turbo_fraction_servers", 0.02)
+    c.turbo_max_clients = cfg.get("turbo_max_clients", 200)
+    c.turbo_max_servers = cfg.get("turbo_max_servers", 40)
+    c.turbo_ramp_steps = cfg.get("turbo_ramp_steps", 200)
     return c

@@ -903,7 +903,7 @@ struct Env {
       case 5: /* volt:1020-1069 with an untrained detector: every prediction is "D" */
         scal(CYG_S_SCAN) += (uint32_t)na;
         if (scal(CYG_S_LOGS) > 0) {
-          if (scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR;
+          if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] */
           cost += -0.5 * ds * na;
           defcost += 0.5 * ds * na;
         }
@@ -970,7 +970,7 @@ struct Env {
         case 5:
           scal(CYG_S_SCAN)++;
           if (scal(CYG_S_LOGS) > 0) {
-            if (scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR;
+            if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] */
             cost += -0.5 * ds;
             defcost += 0.5 * ds;
           }
@@ -1218,6 +1218,17 @@ struct Env {
     const cyg_config& c = n->cfg;
     if (n_active <= 0) return;                                  /* volt:205-207 */
     if (c.wl_cap >= 0 && num_loads > c.wl_cap) num_loads = c.wl_cap; /* volt:210-211 */
+    if (c.turbo) { /* cap + ramp (volt:219-231) */
+      int frac_cap = (int)((server ? c.turbo_frac_servers : c.turbo_frac_clients) * (double)n_active);
+      if (frac_cap < 1) frac_cap = 1;
+      int hard_cap = server ? c.turbo_max_servers : c.turbo_max_clients;
+      double ramp = (double)scal(CYG_S_STEP) / (double)(c.turbo_ramp_steps > 1 ? c.turbo_ramp_steps : 1);
+      if (ramp > 1.0) ramp = 1.0;
+      int base = frac_cap < hard_cap ? frac_cap : hard_cap;
+      int turbo_cap = (int)rint((double)base * ramp); /* Python round(): half to even */
+      if (turbo_cap < 1) turbo_cap = 1;
+      if (num_loads > turbo_cap) num_loads = turbo_cap;
+    }
     if (num_loads > n_active) num_loads = n_active;             /* volt:234 */
     if (num_loads <= 0) return;
     uint32_t cand[W];

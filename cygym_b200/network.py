@@ -34,6 +34,7 @@ DEFAULT_CFG = dict(
     default_high=3, lambda_events=0.7, p_add=0.1, p_attacker=0.0, evolve_period=2,
     workload_period_base=50, workload_period_max=200, workload_cap=-1, scaling_vulnerability=1, turbo=0,
     zero_day=0, zero_day_mask=0, def_space_n=14,
+    turbo_fraction_clients=0.05, turbo_fraction_servers=0.02, turbo_max_clients=200, turbo_max_servers=40, turbo_ramp_steps=200,
 )
 
 

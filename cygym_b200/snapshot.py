@@ -127,6 +127,8 @@ def from_reference_env(env):
     scal = np.zeros(NSCAL, np.uint32)
     scal[0] = env.step_num
     fl = (1 if env.checkpoint is not None else 0) | (2 if has_sets else 0)
+    if getattr(env.simulator.detector, "trained", False):
+        fl |= 4  # CYG_FL_DET_TRAINED
     for i, exp in enumerate(exploits):
         if exp.discovered:
             fl |= 1 << (8 + i)
@@ -153,6 +155,9 @@ def from_reference_env(env):
         workload_cap=(-1 if env.workload_cap is None else int(env.workload_cap)),
         scaling_vulnerability=int(bool(env.scaling_vulnerability)), turbo=int(bool(env.turbo)),
         zero_day=int(bool(env.zero_day)), zero_day_mask=zd, att_space_n=int(env.attacker_action_space.n),
-        def_space_n=int(env.defender_action_space.n), n_app_ids=int(env.get_num_app_indices()))
+        def_space_n=int(env.defender_action_space.n), n_app_ids=int(env.get_num_app_indices()),
+        turbo_fraction_clients=float(env.turbo_fraction_clients), turbo_fraction_servers=float(env.turbo_fraction_servers),
+        turbo_max_clients=int(env.turbo_max_clients), turbo_max_servers=int(env.turbo_max_servers),
+        turbo_ramp_steps=int(env.turbo_ramp_steps))
     template = dict(dev=dev, ckpt=ckpt, blocked=blocked, extra=np.zeros(0, np.uint32), scal=scal)
     return Network(row_ptr, col, mult, dev_static, os_val, ver_val, cfg, template)

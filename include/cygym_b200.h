@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CYG_ABI_VERSION 1
+#define CYG_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define CYG_OK 0
@@ -153,6 +153,13 @@ typedef struct cyg_config {
   uint32_t poisson_tab[16];  /* np.random.poisson(lambda_events): #{j: x >= tab[j]} (CyberDefenseEnv.py:668) */
   uint32_t tri_tab[8];       /* ceil(triangular): min(tri_high, 1 + #{v: x >= tab[v]}) */
   uint64_t seed;             /* Philox key */
+  /* turbo workload throttle (volt_typhoon_env.py:219-231), used when `turbo` != 0 */
+  double turbo_frac_clients; /* turbo_fraction_clients */
+  double turbo_frac_servers; /* turbo_fraction_servers */
+  int32_t turbo_max_clients; /* turbo_max_clients */
+  int32_t turbo_max_servers; /* turbo_max_servers */
+  int32_t turbo_ramp_steps;  /* turbo_ramp_steps */
+  int32_t reserved1;
 } cyg_config;
 
 /* ---- shared network tables (device pointers for the CUDA library) ------- */

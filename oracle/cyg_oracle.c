@@ -242,6 +242,18 @@ static void generate_workloads(env_t* e, int num_loads, int server) { /* CDSimul
   for (int i = 0; i < M; i++) n_active += !(e->dev[i] & CYG_DEV_NYA);
   if (n_active <= 0) return; /* volt:205-207 */
   if (n->cfg.wl_cap >= 0 && num_loads > n->cfg.wl_cap) num_loads = n->cfg.wl_cap; /* volt:210-211 */
+  if (n->cfg.turbo) { /* cap + ramp (volt:219-231) */
+    const cyg_config* c = &n->cfg;
+    int frac_cap = (int)((server ? c->turbo_frac_servers : c->turbo_frac_clients) * (double)n_active);
+    if (frac_cap < 1) frac_cap = 1;
+    int hard_cap = server ? c->turbo_max_servers : c->turbo_max_clients;
+    double ramp = (double)e->scal[CYG_S_STEP] / (double)(c->turbo_ramp_steps > 1 ? c->turbo_ramp_steps : 1);
+    if (ramp > 1.0) ramp = 1.0;
+    int base = frac_cap < hard_cap ? frac_cap : hard_cap;
+    int turbo_cap = (int)rint((double)base * ramp); /* Python round(): half to even */
+    if (turbo_cap < 1) turbo_cap = 1;
+    if (num_loads > turbo_cap) num_loads = turbo_cap;
+  }
   if (num_loads > n_active) num_loads = n_active; /* volt:234 */
   if (num_loads <= 0) return;
   int* cand = (int*)malloc(sizeof(int) * (size_t)M);
@@ -468,7 +480,7 @@ static void defender_per_device(env_t* e, const act_t* a, int atype, acc_t* acc,
       case 5:
         scal[CYG_S_SCAN]++;
         if (scal[CYG_S_LOGS] > 0) { /* window non-empty (volt:1052-1059); untrained detector -> all "D" */
-          if (scal[CYG_S_FLAGS] & CYG_FL_DET_TRAINED) scal[CYG_S_FLAGS] |= CYG_FL_ERR_DETECTOR;
+          if ((scal[CYG_S_FLAGS] & CYG_FL_DET_TRAINED) && !c->turbo) scal[CYG_S_FLAGS] |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] (volt:1055) */
           acc->cost += -0.5 * ds;
           add_defcost(e, 0.5 * ds);
         }

@@ -24,6 +24,8 @@ CASES = {
     "c3_m100_scales": dict(numOfDevice=90, M=100, seed=7, T=100, order_form=True,
                            env_attrs=dict(comp_scale=30, work_scale=2.0, def_scale=0.5)),
     "m33_odd": dict(numOfDevice=25, M=33, seed=8, T=150, randomize_every=11),
+    "c2_m50_turbo": dict(numOfDevice=40, M=50, seed=29, T=200, keep_training=True,
+                         env_attrs=dict(turbo=True, workload_period_base=4, workload_period_max=12, turbo_ramp_steps=40)),
 }
 
 

@@ -381,6 +381,9 @@ def extract_network(env):
         att_space_n=int(env.attacker_action_space.n), def_space_n=int(env.defender_action_space.n),
         min_total_degree=int(deg_tot.min()) if M else 0,
         n_app_ids=int(env.get_num_app_indices()),
+        turbo_fraction_clients=float(env.turbo_fraction_clients), turbo_fraction_servers=float(env.turbo_fraction_servers),
+        turbo_max_clients=int(env.turbo_max_clients), turbo_max_servers=int(env.turbo_max_servers),
+        turbo_ramp_steps=int(env.turbo_ramp_steps),
     )
     return dict(
         row_ptr=_real_np.asarray(row_ptr, dtype=_real_np.int32),
@@ -493,6 +496,8 @@ def extract_state(env, netw, epoch=0):
         fl |= FL_HAS_CKPT
     if has_sets:
         fl |= FL_SETS_INIT
+    if getattr(env.simulator.detector, "trained", False):
+        fl |= 1 << 2  # CYG_FL_DET_TRAINED (CDSimulator.py:693-694)
     for i, exp in enumerate(exploits):
         if exp.discovered:
             fl |= 1 << (FL_DISC_SHIFT + i)

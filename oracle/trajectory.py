@@ -34,7 +34,7 @@ def _policy_ops(rng, T, M, n_logs_fn, grouped_every=9, randomize_every=41, basel
 
 
 def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, grouped_every=9,
-           randomize_every=41, baseline_every=0, none_every=13, env_attrs=None, env_id=0):
+           randomize_every=41, baseline_every=0, none_every=13, env_attrs=None, env_id=0, keep_training=False):
     from . import cyg_oracle as O
     from . import ref_harness as H
 
@@ -82,8 +82,9 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
 
     def fix(a, mode):
         at, ex, devs, app = a
-        if mode == "defender" and at == 10 and len(env.simulator.logger.logs) > 0:
-            at = 8  # trained-IsolationForest branch is out of the kernel's scope
+        if mode == "defender" and at == 10 and len(env.simulator.logger.logs) > 0 and not keep_training:
+            at = 8  # trained-IsolationForest branch is out of the kernel's scope; under turbo the
+            #         detector's predictions are never consulted (volt:1055), so training is harmless there
         if not order_form:
             devs = sorted(devs)
         return (at, ex, devs, app)
@@ -117,7 +118,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
                 at = a[0]
                 if mode == "defender":
                     at = int(rng.choice([0, 1, 1, 2, 3, 8, 10, 11, 1, 5]))
-                    if at == 10 and len(env.simulator.logger.logs) > 0:
+                    if at == 10 and len(env.simulator.logger.logs) > 0 and not keep_training:
                         at = 1
                 groups.append((at, a[1], a[2], a[3]))
             env.mode = mode
