@@ -240,14 +240,14 @@ def main():
     if not a.no_e2e:
         Ke = max(10, min(K, 100))
         env = sets[0]
-        act_host, out_host = env.host_buffers()
+        _, _, out_host = env.host_buffers()
         host_actions = []
         for mode in (0, 1):
             ab = ring[mode][0]
-            host_actions.append(torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory())
+            host_actions.append((ab.hdr.cpu().pin_memory(), ab.mask.cpu().pin_memory()))
 
         def e2e_step(i):
-            env.step_host(host_actions[i & 1])       # this step's actions live in the caller's pinned host memory
+            env.step_host(*host_actions[i & 1])      # this step's actions live in the caller's pinned host memory
 
         for i in range(3):
             e2e_step(i)
@@ -259,7 +259,7 @@ def main():
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)
-        e2e = (ems, Ke, act_host.numel() * 4, out_host.numel() * 4)
+        e2e = (ems, Ke, sum(t.numel() * 4 for t in host_actions[0]), out_host.numel() * 4)
 
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

@@ -95,6 +95,8 @@ class VectorCyberDefenseEnv:
         self.raw, self.shaped = self._out[0], self._out[1]
         self.done = self._out[2].view(torch.int32)
         self._host = None
+        self._graphs = {}
+        self._graph_launches = 0  # step kernels launched through replayed CUDA graphs (not seen by cyg_launch_count)
         self._stream = stream
         self._obs = {}
         self._pre = None
@@ -118,7 +120,7 @@ class VectorCyberDefenseEnv:
 
     @property
     def launch_count(self):
-        return int(self.L.cyg_launch_count(self.h))
+        return int(self.L.cyg_launch_count(self.h)) + self._graph_launches
 
     def set_base_line(self, name):
         self.base_line = name
@@ -210,32 +212,61 @@ class VectorCyberDefenseEnv:
 
     # ---- host-buffer front end: what a CPU-side caller (the reference's rollout loops) uses ----
     def host_buffers(self):
-        """Pinned host staging: actions [B, 4 + W] int32 (hdr | mask) in, results [3, B] float32 (raw | shaped | done
-        bits) out.  Allocated once."""
+        """Pinned host staging, allocated once: action headers [B, 4] and device masks [B, W] (int32) in, results
+        [3, B] float32 (raw | shaped | done bits) out."""
         if self._host is None:
             self._host = dict(
-                act=torch.empty(self.B, 4 + self.W, dtype=torch.int32).pin_memory(),
+                hdr=torch.empty(self.B, 4, dtype=torch.int32).pin_memory(),
+                mask=torch.empty(self.B, self.W, dtype=torch.int32).pin_memory(),
                 out=torch.empty(3, self.B, dtype=torch.float32).pin_memory(),
-                d_act=torch.empty(self.B, 4 + self.W, dtype=torch.int32, device=self.device),
                 d_hdr=torch.empty(self.B, 4, dtype=torch.int32, device=self.device),
                 d_mask=torch.empty(self.B, self.W, dtype=torch.int32, device=self.device))
-        return self._host["act"], self._host["out"]
+        return self._host["hdr"], self._host["mask"], self._host["out"]
 
-    def step_host(self, act=None, flags=0):
-        """step() with HOST buffers: one pinned host->device copy of the actions (`act`, a pinned [B, 4 + W] int32
-        tensor of the caller's, default host_buffers()[0]), the kernel,
-        one device->host copy of (raw, shaped, done) into host_buffers()[1], then a stream synchronise (the caller
-        reads the rewards before choosing the next action).  Returns (raw, shaped, done) as host tensor views."""
+    def _host_ops(self, hdr, mask, flags):
+        h = self._host
+        h["d_hdr"].copy_(hdr, non_blocking=True)
+        h["d_mask"].copy_(mask, non_blocking=True)
+        self._step([ActionBatch(h["d_hdr"], h["d_mask"])], flags, 0, False)
+        h["out"].copy_(self._out, non_blocking=True)
+
+    def step_host(self, hdr=None, mask=None, flags=0, use_graph=True):
+        """step() with HOST buffers: two pinned host->device copies of the actions (`hdr`, `mask`: pinned tensors of
+        the caller's, default the staging buffers of host_buffers()), the kernel, one device->host copy of
+        (raw, shaped, done) into host_buffers()[2], then a stream synchronise (the caller reads the rewards before
+        choosing the next action).  The four operations are captured once per (hdr, mask) buffer pair into a CUDA
+        graph and replayed, so a step costs one graph launch on the host.  Returns (raw, shaped, done) host views."""
         if self._host is None:
             self.host_buffers()
         h = self._host
+        hdr = h["hdr"] if hdr is None else hdr
+        mask = h["mask"] if mask is None else mask
         stream = self._stream if self._stream is not None else torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(stream):
-            h["d_act"].copy_(h["act"] if act is None else act, non_blocking=True)
-            h["d_hdr"].copy_(h["d_act"][:, :4])
-            h["d_mask"].copy_(h["d_act"][:, 4:])
-            self._step([ActionBatch(h["d_hdr"], h["d_mask"])], flags, 0, False)
-            h["out"].copy_(self._out, non_blocking=True)
+        key = (hdr.data_ptr(), mask.data_ptr(), int(flags))
+        graph = self._graphs.get(key) if use_graph else None
+        if use_graph and graph is None and key not in self._graphs:
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(stream)
+                saved, self._stream = self._stream, None  # launches go to the capturing (current) stream
+                try:
+                    with torch.cuda.graph(g, stream=side):
+                        self._host_ops(hdr, mask, flags)
+                finally:
+                    self._stream = saved
+                stream.wait_stream(side)
+                self._graphs[key] = graph = g
+            except Exception:
+                self._graphs[key] = None  # capture not possible here: stay on the eager path for this buffer pair
+                torch.cuda.synchronize(self.device)
+        if graph is not None:
+            with torch.cuda.stream(stream):
+                graph.replay()
+            self._graph_launches += 1
+        else:
+            with torch.cuda.stream(stream):
+                self._host_ops(hdr, mask, flags)
         stream.synchronize()
         return h["out"][0], h["out"][1], h["out"][2].view(torch.int32)
 

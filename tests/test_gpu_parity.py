@@ -228,3 +228,27 @@ def test_errors_are_loud():
     with pytest.raises(K.CygError):
         net.cfg["evolve_period"] = 0
         VectorCyberDefenseEnv(net, 4)
+
+
+def test_step_host_matches_device_step():
+    """The host-buffer call (pinned H2D + kernel + D2H, CUDA-graph replayed) gives the same transition as step()."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    net = synthetic_network(100, n_subnets=8, seed=2)
+    B = 3000
+    a = VectorCyberDefenseEnv(net, B, seed=9)
+    b = VectorCyberDefenseEnv(net, B, seed=9)
+    hdr_h, mask_h, out_h = b.host_buffers()
+    for t in range(12):
+        ab = a.sample_actions(t & 1)
+        b.sample_actions(t & 1)          # keeps the draw epochs of the two envs aligned
+        torch.cuda.synchronize()
+        r = [x.clone() for x in a.step(ab)]
+        hdr_h.copy_(ab.hdr.cpu()); mask_h.copy_(ab.mask.cpu())
+        raw, shaped, done = b.step_host(use_graph=(t >= 2))   # eager first, then captured + replayed
+        assert torch.equal(raw, r[0].cpu()) and torch.equal(shaped, r[1].cpu()) and torch.equal(done, r[2].cpu()), t
+    ca, cb = a.export_state(), b.export_state()
+    for k in ca:
+        assert torch.equal(ca[k], cb[k]), k
+    assert b.launch_count >= 12
