@@ -118,23 +118,9 @@ struct Coop {
         const int idx = pos + lg;
         const bool valid = idx < na;
         const int d = valid ? e.select_nth(act, idx) : 0;
-        const bool gen = valid && (((e.T(e.n->o_dmulti + 2 * d) | e.T(e.n->o_dmulti + 2 * d + 1)) >> 31) != 0);
-        const uint32_t genm = __ballot_sync(gm, gen) >> gbase;
-        if (genm & 1u) { /* > 2 multi-edges in one of the lists of the FIRST device of the round: general routine */
-          int f = 0;
-          if (lg == 0) {
-            Stream st(site);
-            st.skip(e.rng, kbase);
-            f = e.flip_incident_general(d, want, st) ? 1 : 0;
-          }
-          f = __shfl_sync(gm, f, gbase);
-          cnt += (uint32_t)f; kbase += (uint32_t)f; pos += 1;
-          __syncwarp(gm);
-          continue;
-        }
         typename E::Pool P;
         int total = 0;
-        if (valid && !gen) total = e.flip_pool(d, want, P);
+        if (valid) total = e.flip_pool(d, want, P);
         const bool nonempty = total > 0;
         const uint32_t nem = __ballot_sync(gm, nonempty) >> gbase;
         int eid = 0, other = -1;
@@ -159,7 +145,7 @@ struct Coop {
           }
           if (nonempty && in_round && rank > lg) target = 1u << rank;
         }
-        uint32_t conf = __reduce_or_sync(gm, target) | genm;
+        uint32_t conf = __reduce_or_sync(gm, target);
         int c = conf ? (__ffs((int)conf) - 1) : G;
         const int nvalid = (na - pos) < G ? (na - pos) : G;
         if (c > nvalid) c = nvalid;

@@ -826,20 +826,48 @@ struct Env {
   }
   /* the pool of one device: windows over its out-edges and in-edges whose blocked flag == want */
   struct Pool {
-    int a, c0, to, ti;
+    int a, c0, lo, li, to, ti;
     uint32_t dmo, dmi;
     uint32_t xo[W], xi[W];
   };
-  CYG_HD bool flip_needs_general(int d) { /* extra edges in this env, or > 2 multi-edges in one of d's lists */
-    return n_extra() > 0 || ((T(n->o_dmulti + 2 * d) | T(n->o_dmulti + 2 * d + 1)) >> 31);
+  CYG_HD bool flip_needs_general(int d) { /* only envs with extra (hub-star) edges need the neighbour-id walk */
+    return n_extra() > 0;
+  }
+  /* lists with more than two multi-edges (bit 31 of the packed entry): weights from the edge-order multiplicity
+   * bitsets e_mlo / e_mhi (out-list order) and ei_mlo / ei_mhi (in-list order) instead of the packed entries */
+  CYG_HD int wweight_bits(const uint32_t* x, uint32_t off_lo, uint32_t off_hi, int a, int len) {
+    uint32_t lo[W], hi[W];
+    window(Tp(off_lo), n->EW, a, len, 0u, lo);
+    window(Tp(off_hi), n->EW, a, len, 0u, hi);
+    int c = 0;
+    for (int q = 0; q < W; q++) c += popc(x[q]) + popc(x[q] & lo[q]) + 2 * popc(x[q] & hi[q]);
+    return c;
+  }
+  CYG_HD int wselect_bits(const uint32_t* x, uint32_t off_lo, uint32_t off_hi, int a, int len, int r) {
+    uint32_t lo[W], hi[W];
+    window(Tp(off_lo), n->EW, a, len, 0u, lo);
+    window(Tp(off_hi), n->EW, a, len, 0u, hi);
+    int pos = -1;
+    for (int q = 0; q < W; q++) {
+      uint32_t m = x[q];
+      while (m && pos < 0) {
+        int sb = ctz(m);
+        m &= m - 1;
+        int wt = 1 + (int)((lo[q] >> sb) & 1u) + 2 * (int)((hi[q] >> sb) & 1u);
+        if (r < wt) pos = q * 32 + sb; else r -= wt;
+      }
+    }
+    return pos;
   }
   CYG_HD int flip_pool(int d, bool want, Pool& P) { /* returns the multiplicity-weighted pool size */
     P.dmo = T(n->o_dmulti + 2 * d); P.dmi = T(n->o_dmulti + 2 * d + 1);
     const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
     P.a = row_ptr(d); P.c0 = in_ptr(d);
-    window(blocked(), n->EW, P.a, row_ptr(d + 1) - P.a, flipw, P.xo);
-    window(blocked_in(), n->EW, P.c0, in_ptr(d + 1) - P.c0, flipw, P.xi);
-    P.to = wweight(P.xo, P.dmo); P.ti = wweight(P.xi, P.dmi);
+    P.lo = row_ptr(d + 1) - P.a; P.li = in_ptr(d + 1) - P.c0;
+    window(blocked(), n->EW, P.a, P.lo, flipw, P.xo);
+    window(blocked_in(), n->EW, P.c0, P.li, flipw, P.xi);
+    P.to = (P.dmo >> 31) ? wweight_bits(P.xo, n->o_emlo, n->o_emhi, P.a, P.lo) : wweight(P.xo, P.dmo);
+    P.ti = (P.dmi >> 31) ? wweight_bits(P.xi, n->o_eimlo, n->o_eimhi, P.c0, P.li) : wweight(P.xi, P.dmi);
     return P.to + P.ti;
   }
   /* pool element holding weight unit r: returns the base edge id, `other` = the far endpoint of that edge */
@@ -847,7 +875,13 @@ struct Env {
     const bool from_out = r < P.to;
     uint32_t xs[W];
     for (int q = 0; q < W; q++) xs[q] = from_out ? P.xo[q] : P.xi[q];
-    int pos = wselect(xs, from_out ? P.dmo : P.dmi, from_out ? r : r - P.to);
+    const uint32_t dm = from_out ? P.dmo : P.dmi;
+    const int rr = from_out ? r : r - P.to;
+    int pos;
+    if (dm >> 31)
+      pos = from_out ? wselect_bits(xs, n->o_emlo, n->o_emhi, P.a, P.lo, rr) : wselect_bits(xs, n->o_eimlo, n->o_eimhi, P.c0, P.li, rr);
+    else
+      pos = wselect(xs, dm, rr);
     int j_in = P.c0 + (from_out ? 0 : pos);
     int e = from_out ? P.a + pos : in_eid(j_in);
     other = from_out ? col(e) : in_src(j_in);
@@ -1059,8 +1093,8 @@ struct Env {
     const uint32_t dmo = T(n->o_dmulti + 2 * s);
     int vw = -1;
     uint32_t hitbit = 0;
-    if (nx > 0 || (dmo >> 31)) {
-      /* general form: materialise the unblocked row (extra edges, > 2 multi-edges in the row) */
+    if (nx > 0) {
+      /* general form: materialise the unblocked row (envs with extra edges) */
       uint32_t row[W];
       live_row(s, has_blk, nx, row);
       uint32_t cand_w = 0;
@@ -1113,12 +1147,21 @@ struct Env {
         window(b, n->EW, a, nb, 0u, xb);
         for (int q = 0; q < W; q++) cnt -= popc(xb[q]);
       }
-      for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged */
-        int off = (int)((dmo >> (10 * k)) & 0xFFu);
-        if (off == 0xFF || off >= nb) continue;
-        int e = a + off;
-        if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
-        cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
+      if (dmo >> 31) { /* more than two multi-edges in the row: repeats from the multiplicity bitsets */
+        uint32_t xu[W], lo[W], hi[W];
+        window(b, n->EW, a, nb, has_blk ? 0xFFFFFFFFu : 0u, xu); /* unblocked pairs among the first nb */
+        if (!has_blk) for (int q = 0; q < W; q++) { int rem = nb - 32 * q; xu[q] = rem <= 0 ? 0u : (rem >= 32 ? 0xFFFFFFFFu : lowmask(rem)); }
+        window(Tp(n->o_emlo), n->EW, a, nb, 0u, lo);
+        window(Tp(n->o_emhi), n->EW, a, nb, 0u, hi);
+        for (int q = 0; q < W; q++) cnt += popc(xu[q] & lo[q]) + 2 * popc(xu[q] & hi[q]);
+      } else {
+        for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged */
+          int off = (int)((dmo >> (10 * k)) & 0xFFu);
+          if (off == 0xFF || off >= nb) continue;
+          int e = a + off;
+          if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
+          cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
+        }
       }
     }
     if (vw < 0) { rule3 = false; return -1; }
