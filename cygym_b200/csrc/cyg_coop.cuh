@@ -80,8 +80,8 @@ struct Coop {
     const int j = e.out2in(eid);
     uint32_t* bo = e.blocked() + (eid >> 5);
     uint32_t* bi = e.blocked_in() + (j >> 5);
-    if (b) { atomicOr(bo, 1u << (eid & 31)); atomicOr(bi, 1u << (j & 31)); }
-    else { atomicAnd(bo, ~(1u << (eid & 31))); atomicAnd(bi, ~(1u << (j & 31))); }
+    if (b) { atomicOr(bo, 1u << (eid & 31)); atomicOr(bi, 1u << (j & 31)); atomicAdd(&e.nblk(), 1u); }
+    else { atomicAnd(bo, ~(1u << (eid & 31))); atomicAnd(bi, ~(1u << (j & 31))); atomicSub(&e.nblk(), 1u); }
   }
 
   /* block (6) / unblock (9) one incident edge per listed active device, in listed order.

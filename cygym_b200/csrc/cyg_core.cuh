@@ -9,6 +9,7 @@
  *   [off_blocked, off_blocked + EW)  blocked-edge bitset over base CSR edge ids (out-list order)
  *   [off_blocked_in, ... + EW)       the same bits permuted into in-list order, so that the in-edges of a
  *                                    device are a contiguous bit range too (block / unblock, volt:485-511)
+ *   [off_aux]                        number of blocked base pairs (derived; spares the scans a walk over the bitset)
  * (the rarely used per-env extra attacker hub-star edges and the per-device checkpoint words
  * live in side arrays in global memory and are touched only by the actions that need them)
  *
@@ -75,7 +76,7 @@ enum {
  * constant-bank operand, and reads the hot prefix of the blob [0, hot_words) from its shared-memory copy. */
 struct Net {
   cyg_config cfg;
-  int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in;
+  int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in, off_aux;
   int Wm;                     /* ceil(M/32): words per device mask in the C-ABI arrays (== W unless the planes are padded) */
   double inv_M;               /* 1.0 / M */
   uint32_t hot_words;         /* prefix of the blob that a CTA stages in shared memory */
@@ -281,6 +282,7 @@ struct Env {
   CYG_HD uint32_t& pl(int p, int w) { return R(CYG_REC_PLANES + p * W + w); }
   CYG_HD uint32_t* blocked() { return &R(n->off_blocked); }
   CYG_HD uint32_t* blocked_in() { return &R(n->off_blocked_in); }
+  CYG_HD uint32_t& nblk() { return R(n->off_aux); } /* number of blocked base pairs */
   CYG_HD uint32_t* extra() { return xtra; }
   CYG_HD int n_extra() { return (int)(R(CYG_S_PREV_X) >> 16); }
 
@@ -383,9 +385,8 @@ struct Env {
 
   /* ---- topology: base bit rows + blocked bitset + extra edges ---------------- */
   CYG_HD bool any_blocked() {
+    if (nblk() != 0) return true;
     uint32_t o = 0;
-    const uint32_t* b = blocked();
-    for (int i = 0; i < n->EW; i++) o |= b[i];
     int nx = n_extra();
     const uint32_t* x = extra();
     for (int j = 0; j < nx; j++) o |= x[j] & CYG_X_BLOCKED;
@@ -476,8 +477,9 @@ struct Env {
   }
   CYG_HD void set_base_blocked(int e, bool b) { /* both orders of the bitset */
     int j = out2in(e);
-    if (b) { blocked()[e >> 5] |= 1u << (e & 31); blocked_in()[j >> 5] |= 1u << (j & 31); }
-    else { blocked()[e >> 5] &= ~(1u << (e & 31)); blocked_in()[j >> 5] &= ~(1u << (j & 31)); }
+    const uint32_t was = (blocked()[e >> 5] >> (e & 31)) & 1u;
+    if (b) { blocked()[e >> 5] |= 1u << (e & 31); blocked_in()[j >> 5] |= 1u << (j & 31); nblk() += 1u - was; }
+    else { blocked()[e >> 5] &= ~(1u << (e & 31)); blocked_in()[j >> 5] &= ~(1u << (j & 31)); nblk() -= was; }
   }
   /* flip the blocked flag of edge (u, v) */
   CYG_HD void set_edge_blocked(int u, int v, bool b) {
@@ -495,6 +497,7 @@ struct Env {
   CYG_HD void rebuild_cache() {
     uint32_t *b = blocked(), *bi = blocked_in();
     for (int i = 0; i < n->EW; i++) { b[i] = 0; bi[i] = 0; }
+    nblk() = 0;
     int nx = n_extra();
     uint32_t* x = extra();
     for (int j = 0; j < nx; j++) x[j] &= ~CYG_X_BLOCKED;
@@ -1182,7 +1185,6 @@ struct Env {
   }
 
   CYG_HD void attacker_act(const Act& a, int atype, double& cost) {
-    const cyg_config& c = n->cfg;
     if (bl == CYG_BL_NO_ATTACK) return;
     if (atype != 1 && atype != 2) return;
     uint32_t src[W]; /* snapshot of compromised-or-owned devices, taken before the loop (volt:1127-1128) */

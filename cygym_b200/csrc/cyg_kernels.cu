@@ -522,9 +522,11 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     if (lane == CYG_S_FLAGS) v |= err;
     rec[lane] = v;
   }
+  uint32_t nblk = 0;
   for (int i = lane; i < n.EW; i += 32) {
     const uint32_t* bo = p.blocked + (size_t)warp * n.EW;
     rec[n.off_blocked + i] = bo[i];
+    nblk += (uint32_t)__popc(bo[i]);
     uint32_t bi = 0; /* the same bits in in-list order */
     for (int j = 0; j < 32 && i * 32 + j < n.E; j++) {
       int jj = i * 32 + j;
@@ -533,8 +535,9 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     }
     rec[n.off_blocked_in + i] = bi;
   }
+  nblk = __reduce_add_sync(0xFFFFFFFFu, nblk);
   for (int i = lane; i < n.cfg.xcap; i += 32) p.xtra_int[(size_t)warp * n.cfg.xcap + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
-  for (int i = n.off_blocked_in + n.EW + lane; i < n.S; i += 32) rec[i] = 0u;
+  for (int i = n.off_aux + lane; i < n.S; i += 32) rec[i] = (i == n.off_aux) ? nblk : 0u;
 }
 
 template <int W>

@@ -56,7 +56,8 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   n.NP = P_CBY0 + n.ncby;
   n.off_blocked = CYG_REC_PLANES + n.NP * W;
   n.off_blocked_in = n.off_blocked + EW;
-  int S = n.off_blocked_in + EW;
+  n.off_aux = n.off_blocked_in + EW;
+  int S = n.off_aux + 1;
   if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
   n.S = S;
   b.words.clear();

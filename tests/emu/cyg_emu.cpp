@@ -35,7 +35,7 @@ static void import_env(const Net& n, uint32_t* rec, const uint32_t* dev, const u
     import_device<W>(&n, rec, d, dev[d]);
     if (ckpt) ckpt[d] = (ckpt[d] & ~CYG_CKI_REMOVED) | ((dev[d] & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u);
   }
-  for (int i = 0; i < n.EW; i++) rec[n.off_blocked + i] = blocked[i];
+  for (int i = 0; i < n.EW; i++) { rec[n.off_blocked + i] = blocked[i]; rec[n.off_aux] += (uint32_t)__builtin_popcount(blocked[i]); }
   for (int j = 0; j < n.E; j++) {
     int e = (int)((n.blob[n.o_in_eid + (j >> 1)] >> ((j & 1) * 16)) & 0xFFFFu);
     if ((blocked[e >> 5] >> (e & 31)) & 1u) rec[n.off_blocked_in + (j >> 5)] |= 1u << (j & 31);
