@@ -244,10 +244,10 @@ def main():
         host_actions = []
         for mode in (0, 1):
             ab = ring[mode][0]
-            host_actions.append((ab.hdr.cpu().pin_memory(), ab.mask.cpu().pin_memory()))
+            host_actions.append(torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory())  # [B, 4 + W] rows: hdr | mask
 
         def e2e_step(i):
-            env.step_host(*host_actions[i & 1])      # this step's actions live in the caller's pinned host memory
+            env.step_host(act=host_actions[i & 1])   # this step's actions live in the caller's pinned host memory
 
         for i in range(3):
             e2e_step(i)
@@ -259,7 +259,7 @@ def main():
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)
-        e2e = (ems, Ke, sum(t.numel() * 4 for t in host_actions[0]), out_host.numel() * 4)
+        e2e = (ems, Ke, host_actions[0].numel() * 4, out_host.numel() * 4)
 
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device=dev)

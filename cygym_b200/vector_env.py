@@ -219,18 +219,24 @@ class VectorCyberDefenseEnv:
                 hdr=torch.empty(self.B, 4, dtype=torch.int32).pin_memory(),
                 mask=torch.empty(self.B, self.W, dtype=torch.int32).pin_memory(),
                 out=torch.empty(3, self.B, dtype=torch.float32).pin_memory(),
+                d_act=torch.empty(self.B, 4 + self.W, dtype=torch.int32, device=self.device),
                 d_hdr=torch.empty(self.B, 4, dtype=torch.int32, device=self.device),
                 d_mask=torch.empty(self.B, self.W, dtype=torch.int32, device=self.device))
         return self._host["hdr"], self._host["mask"], self._host["out"]
 
     def _host_ops(self, hdr, mask, flags):
         h = self._host
-        h["d_hdr"].copy_(hdr, non_blocking=True)
-        h["d_mask"].copy_(mask, non_blocking=True)
+        if mask is None:  # combined [B, 4 + W] rows: ONE host->device copy, split on the device
+            h["d_act"].copy_(hdr, non_blocking=True)
+            h["d_hdr"].copy_(h["d_act"][:, :4])
+            h["d_mask"].copy_(h["d_act"][:, 4:])
+        else:
+            h["d_hdr"].copy_(hdr, non_blocking=True)
+            h["d_mask"].copy_(mask, non_blocking=True)
         self._step([ActionBatch(h["d_hdr"], h["d_mask"])], flags, 0, False)
         h["out"].copy_(self._out, non_blocking=True)
 
-    def step_host(self, hdr=None, mask=None, flags=0, use_graph=True):
+    def step_host(self, hdr=None, mask=None, flags=0, use_graph=True, act=None):
         """step() with HOST buffers: two pinned host->device copies of the actions (`hdr`, `mask`: pinned tensors of
         the caller's, default the staging buffers of host_buffers()), the kernel, one device->host copy of
         (raw, shaped, done) into host_buffers()[2], then a stream synchronise (the caller reads the rewards before
@@ -239,10 +245,13 @@ class VectorCyberDefenseEnv:
         if self._host is None:
             self.host_buffers()
         h = self._host
-        hdr = h["hdr"] if hdr is None else hdr
-        mask = h["mask"] if mask is None else mask
+        if act is not None:  # pinned [B, 4 + W] int32 rows (hdr | mask): one larger copy moves faster than two small ones
+            hdr, mask = act, None
+        else:
+            hdr = h["hdr"] if hdr is None else hdr
+            mask = h["mask"] if mask is None else mask
         stream = self._stream if self._stream is not None else torch.cuda.current_stream(self.device)
-        key = (hdr.data_ptr(), mask.data_ptr(), int(flags))
+        key = (hdr.data_ptr(), 0 if mask is None else mask.data_ptr(), int(flags))
         graph = self._graphs.get(key) if use_graph else None
         if use_graph and graph is None and key not in self._graphs:
             try:

@@ -248,7 +248,16 @@ def test_step_host_matches_device_step():
         hdr_h.copy_(ab.hdr.cpu()); mask_h.copy_(ab.mask.cpu())
         raw, shaped, done = b.step_host(use_graph=(t >= 2))   # eager first, then captured + replayed
         assert torch.equal(raw, r[0].cpu()) and torch.equal(shaped, r[1].cpu()) and torch.equal(done, r[2].cpu()), t
+    # combined [B, 4 + W] rows in the caller's own pinned buffer (one host->device copy)
+    ab = a.sample_actions(0)
+    b.sample_actions(0)
+    torch.cuda.synchronize()
+    r = [x.clone() for x in a.step(ab)]
+    rows = torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory()
+    for _ in range(1):
+        raw, shaped, done = b.step_host(act=rows)
+    assert torch.equal(raw, r[0].cpu()) and torch.equal(done, r[2].cpu())
     ca, cb = a.export_state(), b.export_state()
     for k in ca:
         assert torch.equal(ca[k], cb[k]), k
-    assert b.launch_count >= 12
+    assert b.launch_count >= 13
