@@ -51,14 +51,27 @@ struct Coop {
     const uint32_t range = (uint32_t)(high - low + 1);
     uint32_t kw = k_base;
     bool over = false;
+    /* one Philox block per lane = draws [4 (k_base/4 + lane), +4): 128 draws cover every device of a W <= 4 env, so a
+     * device fetches its draw from lane (k - k_base_aligned) / 4 by shuffle instead of running its own Philox */
+    uint32_t blk[4];
+    philox4x32_10(e.rng.env, e.rng.epoch, (uint32_t)SITE_STALL, (k_base >> 2) + (uint32_t)lane, e.rng.k0, e.rng.k1, blk);
+    const uint32_t k_al = k_base & ~3u;
 #pragma unroll
     for (int w = 0; w < W; w++) {
       const uint32_t aw = A[w];
       if (aw == 0) continue; /* uniform */
       const bool on = ((aw >> lane) & 1u) != 0;
+      const uint32_t k = kw + (uint32_t)popc(aw & lanes_below(lane));
+      const uint32_t rel = k - k_al; /* < 128 + 3 */
+      const int from = (int)(rel >> 2) & 31;
+      const uint32_t x0 = __shfl_sync(CYG_FULL, blk[0], from), x1 = __shfl_sync(CYG_FULL, blk[1], from);
+      const uint32_t x2 = __shfl_sync(CYG_FULL, blk[2], from), x3 = __shfl_sync(CYG_FULL, blk[3], from);
+      const uint32_t j = rel & 3u;
+      uint32_t x = j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3;
       uint32_t v = 0;
       if (on) {
-        v = (uint32_t)low + below(draw_at(e.rng, SITE_STALL, kw + (uint32_t)popc(aw & lanes_below(lane))), range);
+        if (rel >= 128u) x = draw_at(e.rng, SITE_STALL, k); /* only when k_base is not a multiple of 4 */
+        v = (uint32_t)low + below(x, range);
         if (v > CYG_BUSY_MAX) { v = CYG_BUSY_MAX; over = true; }
       }
       const uint32_t r0 = __ballot_sync(CYG_FULL, v & 1u), r1 = __ballot_sync(CYG_FULL, v & 2u);
@@ -109,49 +122,81 @@ struct Coop {
         }
       }
     } else {
+      /* Windows of 32 listed devices.  Lane i speculates the pick of device pos + i on the state at the start of the
+       * window; a pick is wrong only if a LOWER lane flips an edge that ends at this lane's device (that edge leaves
+       * the pool).  Each pass tells every lane which lower lanes currently do that ("attackers"), the lane drops those
+       * edges from its start-of-window pool and picks again; the picks are a function of the lower lanes' picks only,
+       * so the pass where nothing changes is the sequential walk's outcome (lane 0 is right after pass 1, lane i
+       * after pass i + 1 at the latest; ~3 passes in practice) and all 32 flips commit at once.  The draw index of a
+       * device = draws consumed + non-empty pools below it: lane l holds draw kbase + l and lanes fetch theirs by
+       * shuffle, so a pool running empty mid-window only shifts the fetch. */
       int pos = 0;
       uint32_t kbase = 0;
-      while (pos < na) { /* uniform within the group */
+      while (pos < na) { /* uniform */
 #ifdef CYG_COUNT_ROUNDS
         e.dbg_rounds++;
 #endif
         const int idx = pos + lg;
         const bool valid = idx < na;
         const int d = valid ? e.select_nth(act, idx) : 0;
-        typename E::Pool P;
-        int total = 0;
-        if (valid) total = e.flip_pool(d, want, P);
-        const bool nonempty = total > 0;
-        const uint32_t nem = __ballot_sync(gm, nonempty) >> gbase;
-        int eid = 0, other = -1;
-        if (nonempty) {
-          uint32_t x = draw_at(e.rng, site, kbase + (uint32_t)popc(nem & lanes_below(lg)));
-          eid = e.flip_pick(P, (int)below(x, (uint32_t)total), other);
-        }
-        /* devices of this round as a mask; a pick whose far endpoint is the device of a HIGHER lane invalidates it */
-        uint32_t target = 0;
-        {
-          int rank = 0;
-          bool in_round = false;
+        typename E::Pool P0, P;
+        e.flip_windows(d, want, P0);
+        if (!valid) {
 #pragma unroll
-          for (int w = 0; w < W; w++) {
-            const uint32_t mine = valid ? ((1u << (d & 31)) & eqmask(w, d >> 5)) : 0u;
-            const uint32_t rm = __reduce_or_sync(gm, mine);
-            if (other >= 0) {
-              const uint32_t ob = (1u << (other & 31)) & eqmask(w, other >> 5);
-              in_round = in_round || ((rm & ob) != 0);
-              rank += popc(rm & ((w < (other >> 5)) ? 0xFFFFFFFFu : 0u)) + popc(rm & (ob - 1u) & eqmask(w, other >> 5));
-            }
-          }
-          if (nonempty && in_round && rank > lg) target = 1u << rank;
+          for (int q = 0; q < W; q++) { P0.xo[q] = 0; P0.xi[q] = 0; }
         }
-        uint32_t conf = __reduce_or_sync(gm, target);
-        int c = conf ? (__ffs((int)conf) - 1) : G;
-        const int nvalid = (na - pos) < G ? (na - pos) : G;
-        if (c > nvalid) c = nvalid;
-        if (nonempty && lg < c) set_blocked_atomic(e, eid, !want);
-        const uint32_t done = (uint32_t)popc(nem & lanes_below(c));
-        cnt += done; kbase += done; pos += c;
+        P = P0;
+        const uint32_t xd = draw_at(e.rng, site, kbase + (uint32_t)lg);
+        int eid = -2, other = -1;
+        uint32_t nem = 0;
+        bool had_att = false; /* some lane's pool of the current pass had edges removed (uniform) */
+        for (;;) {
+#ifdef CYG_COUNT_ROUNDS
+          e.dbg_rounds += 0x10000;
+#endif
+          const int total = e.flip_weigh(P);
+          const bool nonempty = total > 0;
+          nem = __ballot_sync(gm, nonempty);
+          const uint32_t x = __shfl_sync(gm, xd, popc(nem & lanes_below(lg)));
+          int neid = -1, nother = -1;
+          if (nonempty) neid = e.flip_pick(P, (int)below(x, (uint32_t)total), nother);
+          const bool changed = __any_sync(gm, neid != eid);
+          eid = neid; other = nother;
+          if (!changed) break;
+          /* victim of this lane's pick: the lane (above this one) whose device is the far endpoint */
+          int vl = -1;
+          if (nonempty) {
+            const int ow = other >> 5;
+            const uint32_t ob = 1u << (other & 31);
+            uint32_t in = 0;
+            int rank = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+              in |= act[w] & ob & eqmask(w, ow);
+              rank += popc(act[w] & (w < ow ? 0xFFFFFFFFu : (ob - 1u) & eqmask(w, ow)));
+            }
+            const int l = rank - pos;
+            if (in != 0 && l > lg && l < 32) vl = l;
+          }
+          const uint32_t bv = __ballot_sync(gm, vl >= 0);
+          if (bv == 0 && !had_att) break; /* nobody is touched and the picks came from untouched pools: final */
+          uint32_t att = bv;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const uint32_t bk = __ballot_sync(gm, vl >= 0 && ((vl >> k) & 1));
+            att &= ((lg >> k) & 1) ? bk : ~bk;
+          }
+          had_att = bv != 0;
+          P = P0;
+          while (__any_sync(gm, att != 0)) {
+            const int from = att ? (__ffs((int)att) - 1) : lg;
+            const int ej = __shfl_sync(gm, eid, from);
+            if (att) { e.pool_remove(P, ej); att &= att - 1u; }
+          }
+        }
+        if (eid >= 0) set_blocked_atomic(e, eid, !want);
+        const uint32_t done = (uint32_t)popc(nem);
+        cnt += done; kbase += done; pos += 32;
         __syncwarp(gm);
       }
     }

@@ -862,16 +862,36 @@ struct Env {
     }
     return pos;
   }
-  CYG_HD int flip_pool(int d, bool want, Pool& P) { /* returns the multiplicity-weighted pool size */
+  /* the two halves of flip_pool: the windows (state at the time of the call) and their weights (the cooperative
+   * block / unblock of cyg_coop.cuh edits the windows between the two) */
+  CYG_HD void flip_windows(int d, bool want, Pool& P) {
     P.dmo = T(n->o_dmulti + 2 * d); P.dmi = T(n->o_dmulti + 2 * d + 1);
     const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
     P.a = row_ptr(d); P.c0 = in_ptr(d);
     P.lo = row_ptr(d + 1) - P.a; P.li = in_ptr(d + 1) - P.c0;
     window(blocked(), n->EW, P.a, P.lo, flipw, P.xo);
     window(blocked_in(), n->EW, P.c0, P.li, flipw, P.xi);
+  }
+  CYG_HD int flip_weigh(Pool& P) {
     P.to = (P.dmo >> 31) ? wweight_bits(P.xo, n->o_emlo, n->o_emhi, P.a, P.lo) : wweight(P.xo, P.dmo);
     P.ti = (P.dmi >> 31) ? wweight_bits(P.xi, n->o_eimlo, n->o_eimhi, P.c0, P.li) : wweight(P.xi, P.dmi);
     return P.to + P.ti;
+  }
+  CYG_HD int flip_pool(int d, bool want, Pool& P) { /* returns the multiplicity-weighted pool size */
+    flip_windows(d, want, P);
+    return flip_weigh(P);
+  }
+  /* drop base edge `eid` (incident to the pool's device) from the pool windows */
+  CYG_HD void pool_remove(Pool& P, int eid) {
+    const int po = eid - P.a;
+    const bool is_out = (unsigned)po < (unsigned)P.lo;
+    const int pp = is_out ? po : out2in(eid) - P.c0;
+    const uint32_t bit = 1u << (pp & 31);
+    for (int q = 0; q < W; q++) {
+      const uint32_t m = bit & eqmask(q, pp >> 5);
+      P.xo[q] &= ~(is_out ? m : 0u);
+      P.xi[q] &= ~(is_out ? 0u : m);
+    }
   }
   /* pool element holding weight unit r: returns the base edge id, `other` = the far endpoint of that edge */
   CYG_HD int flip_pick(const Pool& P, int r, int& other) {

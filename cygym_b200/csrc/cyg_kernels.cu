@@ -87,7 +87,9 @@ struct StepParams {
   uint32_t flags;
 };
 
-#define CYG_NKEYS 32 /* (mode, executed action type) sort keys */
+#define CYG_NKEYS 48 /* sort keys: (mode, executed action type) in 0..31; 32..47 = block / unblock envs of a plain step
+                        bucketed by listed-device count, longest first (the warp-per-env tasks of phase B run in that order) */
+#define CYG_KEY_FLIP0 32
 #define CYG_TMA_STORE 1 /* records go back with one bulk store; plain coalesced stores measured the same (the
                           write-back is bound by the per-SM path to L2: ~16k cycles for 210 KB either way) */
 #define CYG_MAX_BLOCK_ENVS 512   /* envs per CTA */
@@ -95,9 +97,13 @@ struct StepParams {
                                     many threads as envs: phases A / C use one thread per env, the warp-per-env phase
                                     B all 28 warps (it is latency-bound; more warps in flight is what it needs) */
 
+/* named barrier `id` over `nthreads` threads: arrive does not wait (producer side), sync does */
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
-  size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_bar, total;
+  size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_def, off_bar, total;
 };
 __host__ __device__ inline size_t smem_take(size_t& o, size_t bytes) { size_t r = o; o += (bytes + 15) & ~(size_t)15; return r; }
 __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB) {
@@ -108,6 +114,7 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
   p.off_out = smem_take(o, (size_t)NB * 2 * 4); /* phase B -> C carry: action cost, topology-dirty flag */
   p.off_perm = smem_take(o, (size_t)NB * 2);
   p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 4) * 4); /* key histogram / run ends + three task counters */
+  p.off_def = smem_take(o, (size_t)(CYG_MAX_BLOCK_ENVS / 32) * 4); /* bit pos: perm[pos] is finished by phases B / C, not A */
   p.off_bar = smem_take(o, 8);
   p.total = o;
   return p;
@@ -116,8 +123,11 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
 /* CTA-level phase timestamps (profiling build -DCYG_CTA_TIMING: thread 0 writes clock64 at the phase boundaries) */
 #ifdef CYG_CTA_TIMING
 #define CYG_CTA_MARK(i) do { if (p.dbg_cycles && threadIdx.x == 0) p.dbg_cycles[(size_t)blockIdx.x * 8 + (i)] = (unsigned long long)clock64(); } while (0)
+/* per-warp timestamps inside phase B (after the block/unblock, deposit and attack task loops): slots of 4 behind the CTA marks */
+#define CYG_WARP_MARK(i) do { if (p.dbg_cycles && (threadIdx.x & 31) == 0) p.dbg_cycles[2048 + ((size_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * 4 + (i)] = (unsigned long long)clock64(); } while (0)
 #else
 #define CYG_CTA_MARK(i) do { } while (0)
+#define CYG_WARP_MARK(i) do { } while (0)
 #endif
 
 template <int W>
@@ -134,6 +144,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   float* s_out = (float*)(smem + sp.off_out);
   uint16_t* s_perm = (uint16_t*)(smem + sp.off_perm);
   uint32_t* s_cnt = (uint32_t*)(smem + sp.off_cnt);
+  uint32_t* s_def = (uint32_t*)(smem + sp.off_def);
   uint64_t* bar = (uint64_t*)(smem + sp.off_bar);
   const bool grouped = (p.flags & CYG_STEP_GROUPED) != 0;
 
@@ -159,7 +170,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     if (!grouped) {
       uint32_t h0 = p.hdr[(size_t)(env0 + tid) * 4];
       const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
-      key = (int)(((h0 >> 8) & 1u) << 4) | (Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15);
+      const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
+      key = (int)(((h0 >> 8) & 1u) << 4) | xt;
+      if (p.order == nullptr && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
+        int nd = (int)p.hdr[(size_t)(env0 + tid) * 4 + 2];
+        nd = nd < 0 ? 0 : (nd > 127 ? 127 : nd);
+        key = CYG_KEY_FLIP0 + 2 * (7 - (nd >> 4)) + (key == 9 ? 1 : 0);
+      }
     }
     atomicAdd(&s_cnt[key + 1], 1u);
   }
@@ -184,31 +201,40 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
    *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
   const int lane = tid & 31;
   const bool coop_ok = !grouped && p.order == nullptr;
+  const bool lower = (tid & ~31) < nb; /* warps that own envs in the thread-per-env phases */
   bool deferred = false;
-  int el = 0, env = 0;
-  if (tid < nb) {
-    el = s_perm[tid];
-    env = env0 + el;
+  const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
+  uint32_t dmask = 0;
+  {
     Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
                    (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
     uint32_t act[4 + W]; /* this env's action (group 0), in registers */
-    {
-      uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env * 4);
-      act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
-#pragma unroll
-      for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env * W + w];
-    }
     const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
-    long long t_begin = p.dbg_cycles ? clock64() : 0;
+    long long t_begin = 0;
 #ifdef CYG_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     e.phase_t = ph;
 #endif
-    const int mode = (int)((act[0] >> 8) & 1u);
-    if (p.bl_env) e.bl = (int)p.bl_env[env];
-    int atype = e.step_pre(act, p.flags);
-    deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
-    if (!deferred) {
+    int mode = 0, atype = 0;
+    if (tid < nb) {
+      uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env * 4);
+      act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+      for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env * W + w];
+      t_begin = p.dbg_cycles ? clock64() : 0;
+      mode = (int)((act[0] >> 8) & 1u);
+      if (p.bl_env) e.bl = (int)p.bl_env[env];
+      atype = e.step_pre(act, p.flags);
+      deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
+    }
+    if (coop_ok) {
+      /* every env has its epoch open and its busy tick done: the warps that own no env start phase B right away
+       * (named barrier 1: the owning warps only arrive), the owning warps join after their thread-per-env work */
+      dmask = __ballot_sync(0xFFFFFFFFu, deferred);
+      if (lower) { if (lane == 0) s_def[tid >> 5] = dmask; named_bar_arrive(1, NT); }
+      else named_bar_sync(1, NT);
+    }
+    if (tid < nb && !deferred) {
       double cost = 0.0;
       bool dirty = false;
       if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
@@ -219,33 +245,43 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
       p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
     }
+    if (tid < nb) {
 #ifdef CYG_PHASE_TIMING
-    if (p.dbg_cycles) for (int i = 0; i < 8; i++) p.dbg_cycles[(size_t)env * 8 + i] = (unsigned long long)(ph[i] - t_begin);
+      if (p.dbg_cycles) for (int i = 0; i < 8; i++) p.dbg_cycles[(size_t)env * 8 + i] = (unsigned long long)(ph[i] - t_begin);
 #elif !defined(CYG_CTA_TIMING)
-    if (p.dbg_cycles) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
+      if (p.dbg_cycles) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
 #endif
+    }
   }
 
   /* ---- phase B, warp per env: clean / revert / upgrade / block / unblock with 32 lanes on the listed devices.
    *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
   if (coop_ok) {
-    __syncthreads();
   CYG_CTA_MARK(3);
-    if (tid == 0) { s_cnt[CYG_NKEYS + 1] = 0; s_cnt[CYG_NKEYS + 2] = 0; s_cnt[CYG_NKEYS + 3] = 0; } /* task counters */
-    __syncthreads();
+    if (lower) {
+      /* the envs this warp just finished go home now (coalesced 4-byte stores, one record at a time): their
+       * write-back drains while phase B runs, and the end of the kernel only has the deferred records left */
+      __syncwarp();
+      for (int j = 0; j < 32; j++) {
+        const int pos = (tid & ~31) + j;
+        if (pos >= nb || ((dmask >> j) & 1u)) continue;
+        const int el_s = s_perm[pos];
+        for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
+      }
+    }
     /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
      * groups were measured slower (the groups of a warp diverge and no longer issue together). */
     {
       constexpr int G = 32;
       const int lg = lane % G, gbase = lane - lg;
       const uint32_t gm = (G == 32) ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << gbase);
-      const int lo9 = (int)s_cnt[9], n9 = (int)s_cnt[10] - lo9, lo6 = (int)s_cnt[6], n6 = (int)s_cnt[7] - lo6;
+      const int lof = (int)s_cnt[CYG_KEY_FLIP0], nf = (int)s_cnt[CYG_NKEYS] - lof; /* keys 32..47 are one run of perm[] */
       for (;;) {
         int task = 0;
         if (lg == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 1], 1u);
         task = __shfl_sync(gm, task, gbase);
-        if (task >= n9 + n6) break;
-        const int el_b = s_perm[task < n9 ? lo9 + task : lo6 + (task - n9)];
+        if (task >= nf) break;
+        const int el_b = s_perm[lof + task];
         const int env_b = env0 + el_b;
         Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                        (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
@@ -263,7 +299,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         bool dirty = false;
         long long tb0 = p.dbg_cycles ? clock64() : 0;
         if (lg == 0) e.load_costs();
-        Coop<W>::template flip<G>(e, a, task < n9 ? 9 : 6, cost, dirty);
+        Coop<W>::template flip<G>(e, a, (int)(act[0] & 0xFFu), cost, dirty); /* flip keys only hold executed types 6 / 9 == the header's */
         if (lg == 0) {
 #if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
           if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
@@ -279,6 +315,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       }
     }
     __syncwarp();
+    CYG_WARP_MARK(0);
     /* B2: clean / revert / upgrade (keys 1, 3, 4), one env per warp: 32 lanes = the 32 devices of a plane word */
     {
       const int heavy_keys[3] = {1, 3, 4};
@@ -329,6 +366,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         __syncwarp();
       }
     }
+    CYG_WARP_MARK(1);
     /* B3: attacker exploit + lateral movement (key 16|1), one env per warp */
     {
       const int lo = (int)s_cnt[17], ntasks = (int)s_cnt[18] - lo;
@@ -364,6 +402,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         __syncwarp();
       }
     }
+    CYG_WARP_MARK(2);
     __syncthreads();
   CYG_CTA_MARK(4);
     /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
@@ -392,6 +431,14 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   }
 
   /* ---- write the block's records back ---- */
+  if (coop_ok) { /* the records of phase A are on their way already: one warp per deferred record */
+    for (int pos = tid >> 5; pos < nb; pos += NT >> 5) {
+      if (!((s_def[pos >> 5] >> (pos & 31)) & 1u)) continue;
+      const int el_s = s_perm[pos];
+      for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
+    }
+    CYG_CTA_MARK(6);
+  } else
 #ifdef CYG_TMA_STORE
   if (bulk_ok) { /* one bulk store; every writer fences generic -> async proxy first */
     fence_proxy_async();
@@ -611,6 +658,9 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+#ifdef CYG_FAST_BUILD /* profiling builds: only the W = 4 kernels (config C3) are instantiated */
+#define DISPATCH_W(W_, STMT) { constexpr int KW = 4; STMT; }
+#else
 #define DISPATCH_W(W_, STMT)                     \
   switch (W_) {                                  \
     case 1: { constexpr int KW = 1; STMT; } break; \
@@ -619,6 +669,7 @@ struct DeviceGuard {
     case 4: { constexpr int KW = 4; STMT; } break; \
     default: { constexpr int KW = CYG_BIG_W; STMT; } break; \
   }
+#endif
 
 static int pick_block_envs(const cyg_env_s* h, int requested) {
   /* envs (= threads) per CTA.  One CTA per SM: the bigger the block, the purer the per-warp action types after
@@ -772,6 +823,10 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   int threads = ((2 * h->NB + 31) / 32) * 32;
   if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
   if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
+#ifdef CYG_FAST_BUILD
+  if (h->W != 4) return fail(CYG_E_INVAL, "CYG_FAST_BUILD: W = 4 only");
+  cyg_step_kernel<4><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
+#else
   if (h->W > CYG_MAX_W) {
     cyg_step_generic_kernel<CYG_BIG_W><<<(h->B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p);
     if (out->obs) { /* post-evolve observation rows: a second launch on the generic path */
@@ -787,6 +842,7 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
       default: cyg_step_kernel<4><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
     }
   }
+#endif
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

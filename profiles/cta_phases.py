@@ -25,4 +25,9 @@ for t in range(40):
         print(f"t={t} {'att' if mode else 'def'} launch {e0.elapsed_time(e1) * 1e3:.1f} us; median / max cycles per CTA phase:")
         for i in range(6):
             print(f"   {names[i]:18s} {int(np.median(d[:, i])):8d} {int(d[:, i].max()):8d}")
+        wm = dbg[2048:2048 + 147 * 32 * 4].view(147, 32, 4).cpu().numpy().astype(np.int64)[:, :28, :3]
+        t3 = v[:, 3][:, None]  # phase B start
+        for i, nm in enumerate(["B1 block/unblock", "B2 deposits", "B3 attack"]):
+            endw = wm[:, :, i] - t3
+            print(f"   per-warp end of {nm:18s} (cycles after phase-B start): median {int(np.median(endw)):8d}  min {int(endw.min()):8d}  CTA-max median {int(np.median(endw.max(axis=1))):8d}")
         print(f"   total              {int(np.median(v[:, 6] - v[:, 0])):8d} {int((v[:, 6] - v[:, 0]).max()):8d}  ({np.median(v[:,6]-v[:,0])/1.965e3:.1f} us)")
