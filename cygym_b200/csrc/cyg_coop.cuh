@@ -46,7 +46,7 @@ struct Coop {
 
   /* busy_time = low + below(draw, range) for the devices of A[] (lane-uniform), draws k_base, k_base+1, ... in
    * ascending device order (the set form of _stall, volt:135-138) */
-  static __device__ void deposit(E& e, const uint32_t* A, int low, int high, uint32_t k_base) {
+  static __device__ __forceinline__ void deposit(E& e, const uint32_t* A, int low, int high, uint32_t k_base) {
     const int lane = lane_id();
     const uint32_t range = (uint32_t)(high - low + 1);
     uint32_t kw = k_base;
@@ -101,7 +101,7 @@ struct Coop {
    * A group of G lanes owns the env (the kernel uses G = 32; the first invalid pick of a round is typically 4-6
    * lanes in, but sub-warp groups diverge from each other and were measured slower). */
   template <int G>
-  static __device__ void flip(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
+  static __device__ __forceinline__ void flip(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
     const int lane = lane_id(), lg = lane % G, gbase = lane - lg;
     const uint32_t gm = (G == 32) ? CYG_FULL : (((1u << (G & 31)) - 1u) << gbase);
     const bool want = atype == 9;
@@ -211,7 +211,7 @@ struct Coop {
    * consecutive sources of the snapshot.  A source's scan depends on earlier sources only through isCompromised
    * of its own hit (a "not yet compromised" hit is invalid if a lower lane hit the same device), so a round
    * commits the lanes below the first such lane and restarts from it: bit-identical to the sequential loop. */
-  static __device__ void attack(E& e, const typename E::Act& a) {
+  static __device__ __forceinline__ void attack(E& e, const typename E::Act& a) {
     const int lane = lane_id();
     uint32_t src[W];
     int ns = 0;
@@ -274,7 +274,7 @@ struct Coop {
 
   /* the deposit-type heavy defender actions (clean / revert / upgrade) of a plain set-form step, one warp per env;
    * lane 0 owns cost / dirty / scalars */
-  static __device__ void defender(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
+  static __device__ __forceinline__ void defender(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
     const int lane = lane_id();
     const cyg_config& c = e.n->cfg;
     const double ds = (double)c.def_scale;

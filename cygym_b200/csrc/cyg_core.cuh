@@ -137,7 +137,16 @@ CYG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { /* bits [sh, sh+32)
  * conditional store inside an unrolled loop is merged by the compiler into ONE dynamically indexed access, which
  * forces the whole array out of registers into local memory. */
 CYG_HD uint32_t eqmask(int a, int b) { return a == b ? 0xFFFFFFFFu : 0u; }
-CYG_HD uint32_t lowmask(int nbits) { return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u); }
+CYG_HD uint32_t lowmask(int nbits) { /* the low nbits bits, 0 <= nbits; all ones from 32 up */
+#ifdef __CUDA_ARCH__
+  uint32_t m;
+  asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0), "r"(nbits)); /* one BMSK */
+  return m;
+#else
+  return nbits >= 32 ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+#endif
+}
+CYG_HD uint32_t lowmask0(int nbits) { return lowmask(nbits < 0 ? 0 : nbits); } /* ... and none below 0 */
 CYG_HD float u2f(uint32_t u) {
 #ifdef __CUDA_ARCH__
   return __uint_as_float(u);
@@ -775,6 +784,18 @@ struct Env {
   /* W-word window of bitset b[0, nw): bits [a, a + len) (len <= 32 W), XORed with flipw, zero beyond len */
   CYG_HD void window(const uint32_t* b, int nw, int a, int len, uint32_t flipw, uint32_t* x) {
     int wa = a >> 5, sh = a & 31;
+#ifdef __CUDA_ARCH__
+    if (SM) { /* shared memory: the W words after the bitset are readable (the next bitset, the next record or the
+                 CTA's carry area) and the length mask drops whatever they hold, so no bounds tests */
+      uint32_t lo = b[wa];
+      for (int q = 0; q < W; q++) {
+        uint32_t hi = b[wa + q + 1];
+        x[q] = (funnel_r(lo, hi, sh) ^ flipw) & lowmask0(len - 32 * q);
+        lo = hi;
+      }
+      return;
+    }
+#endif
     uint32_t lo = wa < nw ? b[wa] : 0u;
     for (int q = 0; q < W; q++) {
       uint32_t hi = (wa + q + 1 < nw) ? b[wa + q + 1] : 0u;
@@ -786,15 +807,19 @@ struct Env {
   }
   CYG_HD int wrank(const uint32_t* x, int pos) { /* set bits of the window below position pos */
     int c = 0;
-    for (int q = 0; q < W; q++) {
-      int rem = pos - 32 * q;
-      c += rem <= 0 ? 0 : popc(rem >= 32 ? x[q] : (x[q] & lowmask(rem)));
-    }
+    for (int q = 0; q < W; q++) c += popc(x[q] & lowmask0(pos - 32 * q));
     return c;
   }
   CYG_HD bool wbit(const uint32_t* x, int pos) {
-    uint32_t v = 0;
-    for (int q = 0; q < W; q++) v |= x[q] & eqmask(q, pos >> 5);
+    uint32_t v;
+    if (W == 4) { /* two-level select */
+      const bool h1 = (pos & 64) != 0, h0 = (pos & 32) != 0;
+      const uint32_t a = h1 ? x[2 % W] : x[0], c = h1 ? x[3 % W] : x[1 % W];
+      v = h0 ? c : a;
+    } else {
+      v = 0;
+      for (int q = 0; q < W; q++) v |= x[q] & eqmask(q, pos >> 5);
+    }
     return (v >> (pos & 31)) & 1u;
   }
   /* multiplicity-weighted pool over a window: dm = packed multi-edge entries of the list (Net::o_dmulti) */

@@ -93,13 +93,11 @@ struct StepParams {
 #define CYG_TMA_STORE 1 /* records go back with one bulk store; plain coalesced stores measured the same (the
                           write-back is bound by the per-SM path to L2: ~16k cycles for 210 KB either way) */
 #define CYG_MAX_BLOCK_ENVS 512   /* envs per CTA */
+#ifndef CYG_MAX_BLOCK_THREADS
 #define CYG_MAX_BLOCK_THREADS 896 /* threads per CTA: 72 registers per thread at one CTA per SM.  A CTA runs twice as
                                     many threads as envs: phases A / C use one thread per env, the warp-per-env phase
                                     B all 28 warps (it is latency-bound; more warps in flight is what it needs) */
-
-/* named barrier `id` over `nthreads` threads: arrive does not wait (producer side), sync does */
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif
 
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
@@ -113,7 +111,7 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
   p.off_recs = smem_take(o, (size_t)NB * S * 4);
   p.off_out = smem_take(o, (size_t)NB * 2 * 4); /* phase B -> C carry: action cost, topology-dirty flag */
   p.off_perm = smem_take(o, (size_t)NB * 2);
-  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 4) * 4); /* key histogram / run ends + three task counters */
+  p.off_cnt = smem_take(o, (size_t)(CYG_NKEYS + 7) * 4); /* key histogram / run ends + four task counters + warps past phase A + warps past step_pre */
   p.off_def = smem_take(o, (size_t)(CYG_MAX_BLOCK_ENVS / 32) * 4); /* bit pos: perm[pos] is finished by phases B / C, not A */
   p.off_bar = smem_take(o, 8);
   p.total = o;
@@ -159,7 +157,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     bulk_g2s(s_tab, p.net.blob, tab_bytes, bar);
     if (bulk_ok) bulk_g2s(s_rec, g_rec, rec_bytes, bar);
   }
-  if (tid < CYG_NKEYS + 4) s_cnt[tid] = 0;
+  if (tid < CYG_NKEYS + 7) s_cnt[tid] = 0;
   __syncthreads(); /* mbarrier initialised, counters zeroed */
   CYG_CTA_MARK(1);
 
@@ -168,12 +166,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   int key = 0;
   if (tid < nb) {
     if (!grouped) {
-      uint32_t h0 = p.hdr[(size_t)(env0 + tid) * 4];
+      const uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)(env0 + tid) * 4);
+      const uint32_t h0 = hv.x;
       const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
       const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (p.order == nullptr && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
-        int nd = (int)p.hdr[(size_t)(env0 + tid) * 4 + 2];
+        int nd = (int)hv.z;
         nd = nd < 0 ? 0 : (nd > 127 ? 127 : nd);
         key = CYG_KEY_FLIP0 + 2 * (7 - (nd >> 4)) + (key == 9 ? 1 : 0);
       }
@@ -228,11 +227,15 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
     }
     if (coop_ok) {
-      /* every env has its epoch open and its busy tick done: the warps that own no env start phase B right away
-       * (named barrier 1: the owning warps only arrive), the owning warps join after their thread-per-env work */
+      /* once every env has its epoch open and its busy tick done (s_cnt[CYG_NKEYS + 6] counts the owning warps that
+       * got there) phase B may touch any deferred env: the warps that own no env start it right away, the owning
+       * warps join after their thread-per-env work -- and check the same counter, a warp whose envs are all deferred
+       * gets to phase B before the others are through step_pre */
       dmask = __ballot_sync(0xFFFFFFFFu, deferred);
-      if (lower) { if (lane == 0) s_def[tid >> 5] = dmask; named_bar_arrive(1, NT); }
-      else named_bar_sync(1, NT);
+      if (lower) {
+        __syncwarp();
+        if (lane == 0) { s_def[tid >> 5] = dmask; __threadfence_block(); atomicAdd(&s_cnt[CYG_NKEYS + 6], 1u); }
+      }
     }
     if (tid < nb && !deferred) {
       double cost = 0.0;
@@ -258,17 +261,12 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
    *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
   if (coop_ok) {
   CYG_CTA_MARK(3);
-    if (lower) {
-      /* the envs this warp just finished go home now (coalesced 4-byte stores, one record at a time): their
-       * write-back drains while phase B runs, and the end of the kernel only has the deferred records left */
+    if (lower) { /* this warp's thread-per-env work is done and visible */
       __syncwarp();
-      for (int j = 0; j < 32; j++) {
-        const int pos = (tid & ~31) + j;
-        if (pos >= nb || ((dmask >> j) & 1u)) continue;
-        const int el_s = s_perm[pos];
-        for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
-      }
+      if (lane == 0) { __threadfence_block(); atomicAdd(&s_cnt[CYG_NKEYS + 5], 1u); }
     }
+    if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
+    __syncwarp();
     /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
      * groups were measured slower (the groups of a warp diverge and no longer issue together). */
     {
@@ -403,6 +401,21 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       }
     }
     CYG_WARP_MARK(2);
+    /* B4: the records phase A finished go home (coalesced 4-byte stores, one warp per record; whoever runs out of
+     * tasks first does it): their write-back drains under the tail of phase B and phase C, and the end of the kernel
+     * only has the deferred records left to store.  s_cnt[CYG_NKEYS + 5] counts the owning warps that are past
+     * phase A (nobody waits here in practice). */
+    if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
+    __syncwarp();
+    for (;;) {
+      int pos = 0;
+      if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 1u);
+      pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+      if (pos >= nb) break;
+      if ((s_def[pos >> 5] >> (pos & 31)) & 1u) continue;
+      const int el_s = s_perm[pos];
+      for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
+    }
     __syncthreads();
   CYG_CTA_MARK(4);
     /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */

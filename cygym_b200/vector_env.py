@@ -95,6 +95,7 @@ class VectorCyberDefenseEnv:
         self.raw, self.shaped = self._out[0], self._out[1]
         self.done = self._out[2].view(torch.int32)
         self._host = None
+        self._host_evt = None
         self._graphs = {}
         self._graph_launches = 0  # step kernels launched through replayed CUDA graphs (not seen by cyg_launch_count)
         self._stream = stream
@@ -236,12 +237,17 @@ class VectorCyberDefenseEnv:
         self._step([ActionBatch(h["d_hdr"], h["d_mask"])], flags, 0, False)
         h["out"].copy_(self._out, non_blocking=True)
 
-    def step_host(self, hdr=None, mask=None, flags=0, use_graph=True, act=None):
+    def step_host(self, hdr=None, mask=None, flags=0, use_graph=True, act=None, sync=True):
         """step() with HOST buffers: two pinned host->device copies of the actions (`hdr`, `mask`: pinned tensors of
         the caller's, default the staging buffers of host_buffers()), the kernel, one device->host copy of
         (raw, shaped, done) into host_buffers()[2], then a stream synchronise (the caller reads the rewards before
         choosing the next action).  The four operations are captured once per (hdr, mask) buffer pair into a CUDA
-        graph and replayed, so a step costs one graph launch on the host.  Returns (raw, shaped, done) host views."""
+        graph and replayed, so a step costs one graph launch on the host.  Returns (raw, shaped, done) host views.
+
+        sync=False returns right after the enqueue (the host views are valid after wait_host()): a caller that drives
+        two env groups on two streams (`stream=` of the constructor) chooses the actions of one group while the other
+        group's copies and kernel are in flight -- each group stays closed-loop, the PCIe copies of one overlap the
+        kernel of the other."""
         if self._host is None:
             self.host_buffers()
         h = self._host
@@ -276,7 +282,19 @@ class VectorCyberDefenseEnv:
         else:
             with torch.cuda.stream(stream):
                 self._host_ops(hdr, mask, flags)
-        stream.synchronize()
+        if sync:
+            stream.synchronize()
+        else:
+            if self._host_evt is None:
+                self._host_evt = torch.cuda.Event()
+            self._host_evt.record(stream)
+        return h["out"][0], h["out"][1], h["out"][2].view(torch.int32)
+
+    def wait_host(self):
+        """Block until the last step_host(sync=False) of this env group has delivered its results; returns the host views."""
+        if self._host_evt is not None:
+            self._host_evt.synchronize()
+        h = self._host
         return h["out"][0], h["out"][1], h["out"][2].view(torch.int32)
 
     def _obs_buf(self, mode):

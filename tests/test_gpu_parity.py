@@ -261,3 +261,40 @@ def test_step_host_matches_device_step():
     for k in ca:
         assert torch.equal(ca[k], cb[k]), k
     assert b.launch_count >= 13
+
+
+def test_step_host_two_groups_async():
+    """Two env groups on two streams driven through step_host(sync=False) / wait_host() (the double-buffered rollout
+    loop of bench.py's e2e leg) give the same rewards and states as the synchronous device steps."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    net = synthetic_network(100, n_subnets=8, seed=3)
+    B = 2048
+    ref = [VectorCyberDefenseEnv(net, B, seed=4, env_id0=g * B) for g in range(2)]
+    rows, want = {}, {}
+    for t in range(6):
+        for g in range(2):
+            ab = ref[g].sample_actions(t & 1)
+            torch.cuda.synchronize()
+            want[g, t] = [x.clone().cpu() for x in ref[g].step(ab)]
+            rows[g, t] = torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory()
+    torch.cuda.synchronize()
+    # the same six turns of both groups, interleaved, a group only ever waiting for its own previous step
+    grp = [VectorCyberDefenseEnv(net, B, seed=4, env_id0=g * B, stream=torch.cuda.Stream()) for g in range(2)]
+    torch.cuda.synchronize()
+    for t in range(6):
+        for g in range(2):
+            if t > 0:
+                raw, shaped, done = grp[g].wait_host()
+                w = want[g, t - 1]
+                assert torch.equal(raw, w[0]) and torch.equal(shaped, w[1]) and torch.equal(done, w[2]), (g, t)
+            grp[g].sample_actions(t & 1)  # keeps the draw epochs aligned with the reference envs
+            grp[g].step_host(act=rows[g, t], sync=False)
+    for g in range(2):
+        raw, shaped, done = grp[g].wait_host()
+        assert torch.equal(raw, want[g, 5][0]) and torch.equal(done, want[g, 5][2])
+        ca, cb = ref[g].export_state(), grp[g].export_state()
+        torch.cuda.synchronize()
+        for k in ca:
+            assert torch.equal(ca[k].cpu(), cb[k].cpu()), (g, k)
