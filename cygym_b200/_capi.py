@@ -12,11 +12,12 @@ from . import draw_tables as DT
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CYGYM_B200_LIB") or os.path.join(_HERE, "libcygym_b200.so")  # override: profiling builds only
 _SRC = os.path.join(_HERE, "csrc", "cyg_kernels.cu")
-_DEPS = [_SRC, os.path.join(_HERE, "csrc", "cyg_core.cuh"), os.path.join(_HERE, "csrc", "cyg_tables.h"),
+_DEPS = [_SRC, os.path.join(_HERE, "csrc", "cyg_core.cuh"), os.path.join(_HERE, "csrc", "cyg_coop.cuh"),
+         os.path.join(_HERE, "csrc", "cyg_tables.h"),
          os.path.join(os.path.dirname(_HERE), "include", "cygym_b200.h")]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--split-compile", "0"]  # split-compile: ptxas of the kernels in parallel
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+PLANE_WIDTHS = (1, 2, 3, 4, 64)  # one translation unit of cyg_kernels.cu per plane width W (+ one for the C-ABI)
 
 NSCAL = 16
 ATYPE_NONE = 0x80
@@ -84,17 +85,70 @@ class CygError(RuntimeError):
         self.code = code
 
 
+SPILL_LIMIT = 256   # bytes of spill stores tolerated in the config-C3 step kernel (cyg_step_kernel<4, true>)
+THREAD_CAPS = (896, 768, 640)  # threads per CTA -> 72 / 80 / 93 registers per thread at one CTA per SM
+
+
+def _step_kernel_spill(ptxas_log, mangled="_Z15cyg_step_kernelILi4ELb1EEv10StepParams"):
+    """Bytes of spill stores ptxas reports for the plain-step W = 4 kernel (None when the log has no such entry)."""
+    import re
+    m = re.search(r"Function properties for " + re.escape(mangled) + r"\s+\d+ bytes stack frame, (\d+) bytes spill stores", ptxas_log)
+    return int(m.group(1)) if m else None
+
+
+def compile_units(out_path, widths=PLANE_WIDTHS, extra=(), obj_dir=None, verbose=False):
+    """nvcc -c one object per plane width (in parallel, each without --split-compile: the register allocation of a
+    kernel then does not depend on what else is being compiled) plus the C-ABI unit, then link them into `out_path`.
+    Returns the ptxas -v log of the W = 4 unit."""
+    nvcc = os.environ.get("NVCC", "nvcc")
+    obj_dir = obj_dir or os.path.join(_HERE, "_build")
+    os.makedirs(obj_dir, exist_ok=True)
+    tag = os.path.splitext(os.path.basename(out_path))[0]
+    jobs = []
+    for w in list(widths) + [None]:
+        obj = os.path.join(obj_dir, f"{tag}_{'api' if w is None else 'w%d' % w}.o")
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-Xptxas", "-v", "-c", "-o", obj, _SRC]
+        if w is not None:
+            cmd.insert(-4, f"-DCYG_TU_W={w}")
+            if w > 4:
+                cmd[-4:-4] = ["--split-compile", "0"]  # the generic kernel: compile time matters, its registers do not
+        jobs.append((w, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    logs, objs = {}, []
+    for w, obj, pr in jobs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed (unit {w}):\n" + out + err)
+        logs[w] = err
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-o", out_path] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        for w in logs:
+            print(f"---- unit {w}\n{logs[w]}")
+    return logs.get(4, "")
+
+
 def build(force=False, verbose=False):
-    """Compile cygym_b200/csrc/cyg_kernels.cu for sm_100a into cygym_b200/libcygym_b200.so."""
+    """Compile cygym_b200/csrc/cyg_kernels.cu for sm_100a into cygym_b200/libcygym_b200.so.
+
+    The step kernel runs one CTA per SM with as many warps as the register file allows (896 threads = 72 registers
+    per thread), which leaves ptxas next to a cliff (~50 bytes vs ~2 KB of spills in the warp-per-env routines).  The
+    recipe checks `-Xptxas -v` and, should the config-C3 kernel spill more than SPILL_LIMIT bytes, rebuilds with the
+    next lower thread cap (more registers per thread; the caps measured within a few % of each other on B200)."""
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in _DEPS):
         return LIB_PATH
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _SRC]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    log = ""
+    for cap in THREAD_CAPS:
+        w4 = compile_units(LIB_PATH, extra=[f"-DCYG_MAX_BLOCK_THREADS={cap}"], verbose=verbose)
+        spill = _step_kernel_spill(w4)
+        log += f"[cygym_b200 build] {cap} threads per CTA: cyg_step_kernel<4, plain> spills {spill} bytes\n"
+        if spill is None or spill <= SPILL_LIMIT:
+            break
+    with open(LIB_PATH + ".buildlog", "w") as f:
+        f.write(log)
     if verbose:
-        print(r.stderr)
+        print(log)
     return LIB_PATH
 
 

@@ -1504,14 +1504,25 @@ struct Env {
     scal(CYG_S_DEFCOST) = f2u((float)defcost);
     scal(CYG_S_CLEANCOST) = f2u((float)cleancost);
   }
+  /* the action types the plain-step kernel hands to a whole warp (cyg_coop.cuh) */
+  CYG_HD static bool coop_type(int mode, int atype) {
+    if (mode == CYG_MODE_ATTACKER) return atype == 1;
+    return atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9;
+  }
+  /* LIGHT: a plain (ungrouped, set-form) step whose cooperative types are handled elsewhere -- they return at once
+   * here (the only one that can arrive is the attacker's type 1 under base_line "No Attack", a no-op), which lets the
+   * compiler drop their thread-per-env code from the kernel that never runs it */
+  template <bool LIGHT = false>
   CYG_HD int step_act(const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, size_t hdr_gs, size_t mask_gs,
                       size_t order_gs, int G, uint32_t flags, int atype, double& cost, bool& dirty) {
     const cyg_config& c = n->cfg;
-    const bool grouped = (flags & CYG_STEP_GROUPED) != 0;
+    const bool grouped = LIGHT ? false : (flags & CYG_STEP_GROUPED) != 0;
+    if (LIGHT) order = nullptr;
     load_costs();
     Act a;
     decode(hdr, mask, order, a);
     const int mode = a.mode;
+    if (LIGHT && coop_type(mode, atype)) { store_costs(); return atype; }
     if (!grouped) {
       if (a.atype == -1000) { a.n_dev = 0; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
       if (mode == CYG_MODE_DEFENDER) {

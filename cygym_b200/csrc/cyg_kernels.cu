@@ -1,7 +1,7 @@
 /*
  * cyg_kernels.cu -- sm_100a kernels + the C-ABI of include/cygym_b200.h.
  *
- * cyg_step_kernel<W>: ONE launch per env step (volt_typhoon_env.py:818-1333 / :694-779).
+ * cyg_step_kernel<W, PLAIN>: ONE launch per env step (volt_typhoon_env.py:818-1333 / :694-779).
  *   A CTA owns a block of NB consecutive envs.  Their internal records (cyg_core.cuh) are one
  *   contiguous span of HBM, so the CTA moves them with a single TMA bulk copy into shared
  *   memory (cp.async.bulk + mbarrier), steps them there, and writes them back with a single
@@ -128,7 +128,10 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
 #define CYG_WARP_MARK(i) do { } while (0)
 #endif
 
-template <int W>
+/* PLAIN: one ungrouped action per env, device lists as sets (no order array) -- the hot form: thread-per-env phases
+ * A / C plus the warp-per-env phase B.  !PLAIN: grouped steps and explicit order lists, everything thread-per-env
+ * (the sequential forms of every action live only in this instantiation). */
+template <int W, bool PLAIN>
 __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>(cyg_smem);
   const int NB = p.block_envs, NT = blockDim.x, tid = threadIdx.x; /* NB envs, NT >= NB threads */
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   uint32_t* s_cnt = (uint32_t*)(smem + sp.off_cnt);
   uint32_t* s_def = (uint32_t*)(smem + sp.off_def);
   uint64_t* bar = (uint64_t*)(smem + sp.off_bar);
-  const bool grouped = (p.flags & CYG_STEP_GROUPED) != 0;
+  const bool grouped = PLAIN ? false : (p.flags & CYG_STEP_GROUPED) != 0;
 
   uint32_t* g_rec = p.recs + (size_t)env0 * S;
   const uint32_t rec_bytes = (uint32_t)nb * S * 4u;
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
       const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
-      if (p.order == nullptr && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
+      if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
         int nd = (int)hv.z;
         nd = nd < 0 ? 0 : (nd > 127 ? 127 : nd);
         key = CYG_KEY_FLIP0 + 2 * (7 - (nd >> 4)) + (key == 9 ? 1 : 0);
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   /* ---- phase A, thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or
    *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
   const int lane = tid & 31;
-  const bool coop_ok = !grouped && p.order == nullptr;
+  constexpr bool coop_ok = PLAIN;
   const bool lower = (tid & ~31) < nb; /* warps that own envs in the thread-per-env phases */
   bool deferred = false;
   const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
                    (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
     uint32_t act[4 + W]; /* this env's action (group 0), in registers */
-    const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
+    const uint16_t* ord = (!PLAIN && p.order) ? p.order + (size_t)env * p.order_stride : nullptr;
     long long t_begin = 0;
 #ifdef CYG_PHASE_TIMING
     long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -240,7 +243,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     if (tid < nb && !deferred) {
       double cost = 0.0;
       bool dirty = false;
-      if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
+      if (PLAIN) e.template step_act<true>(act, act + 4, nullptr, 0, 0, 0, 1, p.flags, atype, cost, dirty);
+      else if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
       else e.step_act(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
                       (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
       float raw, shaped;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
 
   /* ---- phase B, warp per env: clean / revert / upgrade / block / unblock with 32 lanes on the listed devices.
    *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
-  if (coop_ok) {
+  if constexpr (PLAIN) {
   CYG_CTA_MARK(3);
     if (lower) { /* this warp's thread-per-env work is done and visible */
       __syncwarp();
@@ -267,6 +271,30 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     }
     if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
     __syncwarp();
+    /* The records phase A finished go home while phase B runs (coalesced 4-byte stores, one warp per record): every
+     * warp sends up to `k` of them after each of its tasks, so the write-back is spread over the phase instead of
+     * hitting the memory system from all SMs at once; the end of the kernel only has the deferred records left.
+     * s_cnt[CYG_NKEYS + 5] = owning warps past phase A (nothing is sent before all of them are),
+     * s_cnt[CYG_NKEYS + 4] = next position of perm[] to look at. */
+    auto send_home = [&](int k, bool wait) {
+      int ready = 0;
+      if (lane == 0) {
+        if (wait) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
+        ready = atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) >= (uint32_t)((nb + 31) >> 5);
+      }
+      ready = __shfl_sync(0xFFFFFFFFu, ready, 0);
+      if (!ready) return;
+      for (int sent = 0; sent < k;) {
+        int pos = 0;
+        if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 1u);
+        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        if (pos >= nb) return;
+        if ((s_def[pos >> 5] >> (pos & 31)) & 1u) continue;
+        const int el_s = s_perm[pos];
+        for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
+        sent++;
+      }
+    };
     /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
      * groups were measured slower (the groups of a warp diverge and no longer issue together). */
     {
@@ -310,6 +338,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
         }
         __syncwarp(gm);
+        send_home(2, false);
       }
     }
     __syncwarp();
@@ -362,6 +391,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
         }
         __syncwarp();
+        send_home(2, false);
       }
     }
     CYG_WARP_MARK(1);
@@ -398,24 +428,11 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(0);
         }
         __syncwarp();
+        send_home(2, false);
       }
     }
     CYG_WARP_MARK(2);
-    /* B4: the records phase A finished go home (coalesced 4-byte stores, one warp per record; whoever runs out of
-     * tasks first does it): their write-back drains under the tail of phase B and phase C, and the end of the kernel
-     * only has the deferred records left to store.  s_cnt[CYG_NKEYS + 5] counts the owning warps that are past
-     * phase A (nobody waits here in practice). */
-    if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
-    __syncwarp();
-    for (;;) {
-      int pos = 0;
-      if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 1u);
-      pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-      if (pos >= nb) break;
-      if ((s_def[pos >> 5] >> (pos & 31)) & 1u) continue;
-      const int el_s = s_perm[pos];
-      for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
-    }
+    send_home(1 << 30, true); /* B4: whatever is left of the finished records */
     __syncthreads();
   CYG_CTA_MARK(4);
     /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
@@ -444,7 +461,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   }
 
   /* ---- write the block's records back ---- */
-  if (coop_ok) { /* the records of phase A are on their way already: one warp per deferred record */
+  if constexpr (PLAIN) { /* the records of phase A are on their way already: one warp per deferred record */
     for (int pos = tid >> 5; pos < nb; pos += NT >> 5) {
       if (!((s_def[pos >> 5] >> (pos & 31)) & 1u)) continue;
       const int el_s = s_perm[pos];
@@ -636,6 +653,79 @@ __global__ void cyg_observe_kernel(const __grid_constant__ ObsParams p) {
 }
 
 /* ===========================================================================
+ * Per-W launch table.  The library is built from several translation units of THIS file: one per plane width W
+ * (-DCYG_TU_W=1|2|3|4|64: the kernels of that width and their launchers, compiled without --split-compile so that the
+ * register allocation of the hot kernels does not depend on what else is in the module) and one with the C-ABI
+ * (no CYG_TU_W: no kernel is instantiated there).
+ * ======================================================================== */
+struct WOps {
+  cudaError_t (*set_smem_optin)(int max_optin);
+  void (*step)(bool plain, int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p);
+  void (*import_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
+  void (*export_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
+  void (*randomize)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
+  void (*sample)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
+  void (*observe)(int blocks, int threads, cudaStream_t st, const ObsParams& p);
+};
+#define CYG_WOPS_NAME2(w) cyg_wops_##w
+#define CYG_WOPS_NAME(w) CYG_WOPS_NAME2(w)
+
+#ifdef CYG_TU_W
+template <int KW>
+struct WImpl {
+  static cudaError_t set_smem_optin(int max_optin) {
+    if constexpr (KW <= CYG_MAX_W) {
+      cudaError_t e = cudaFuncSetAttribute(cyg_step_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+      if (e != cudaSuccess) return e;
+      return cudaFuncSetAttribute(cyg_step_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+    } else {
+      return cudaSuccess;
+    }
+  }
+  static void step(bool plain, int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p) {
+    if constexpr (KW <= CYG_MAX_W) {
+      if (plain) cyg_step_kernel<KW, true><<<blocks, threads, smem, st>>>(p);
+      else cyg_step_kernel<KW, false><<<blocks, threads, smem, st>>>(p);
+    } else {
+      cyg_step_generic_kernel<KW><<<blocks, threads, 0, st>>>(p);
+    }
+  }
+  static void import_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_import_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+  static void export_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_export_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+  static void randomize(int blocks, int threads, cudaStream_t st, const SimpleParams& p) { cyg_randomize_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+  static void sample(int blocks, int threads, cudaStream_t st, const SimpleParams& p) { cyg_sample_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+  static void observe(int blocks, int threads, cudaStream_t st, const ObsParams& p) { cyg_observe_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+};
+extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
+  typedef WImpl<CYG_TU_W> I;
+  static const WOps ops = {I::set_smem_optin, I::step, I::import_state, I::export_state, I::randomize, I::sample, I::observe};
+  return &ops;
+}
+#else /* ---- the C-ABI translation unit ---- */
+extern "C" {
+const WOps* cyg_wops_4(void);
+#ifndef CYG_FAST_BUILD /* profiling builds link the W = 4 unit only (config C3) */
+const WOps* cyg_wops_1(void);
+const WOps* cyg_wops_2(void);
+const WOps* cyg_wops_3(void);
+const WOps* cyg_wops_64(void);
+#endif
+}
+static const WOps* wops(int W) {
+  switch (W) {
+    case 4: return cyg_wops_4();
+#ifndef CYG_FAST_BUILD
+    case 1: return cyg_wops_1();
+    case 2: return cyg_wops_2();
+    case 3: return cyg_wops_3();
+    default: return cyg_wops_64();
+#else
+    default: return nullptr;
+#endif
+  }
+}
+
+/* ===========================================================================
  * C-ABI (include/cygym_b200.h)
  * ======================================================================== */
 struct cyg_env_s {
@@ -671,19 +761,6 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-#ifdef CYG_FAST_BUILD /* profiling builds: only the W = 4 kernels (config C3) are instantiated */
-#define DISPATCH_W(W_, STMT) { constexpr int KW = 4; STMT; }
-#else
-#define DISPATCH_W(W_, STMT)                     \
-  switch (W_) {                                  \
-    case 1: { constexpr int KW = 1; STMT; } break; \
-    case 2: { constexpr int KW = 2; STMT; } break; \
-    case 3: { constexpr int KW = 3; STMT; } break; \
-    case 4: { constexpr int KW = 4; STMT; } break; \
-    default: { constexpr int KW = CYG_BIG_W; STMT; } break; \
-  }
-#endif
-
 static int pick_block_envs(const cyg_env_s* h, int requested) {
   /* envs (= threads) per CTA.  One CTA per SM: the bigger the block, the purer the per-warp action types after
    * the in-CTA sort.  Spread B over the SMs in one wave, bounded by shared memory and 512 threads. */
@@ -697,21 +774,20 @@ static int pick_block_envs(const cyg_env_s* h, int requested) {
   return nb;
 }
 
-template <int W>
 static int configure_step(cyg_env_s* h) {
-  if constexpr (W > CYG_MAX_W) { /* generic global-memory kernel: no staging */
+  if (!wops(h->W)) return fail(CYG_E_INVAL, "this build has no kernels for the network's plane width");
+  if (h->W > CYG_MAX_W) { /* generic global-memory kernel: no staging */
     h->smem_bytes = 0;
     return CYG_OK;
-  } else {
-    SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
-    h->smem_bytes = sp.total;
-    /* opt in to the device maximum once (handles with different block sizes share the kernel) */
-    int max_optin = 0;
-    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    if ((int)sp.total > max_optin) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
-    CU(cudaFuncSetAttribute(cyg_step_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin));
-    return CYG_OK;
   }
+  SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
+  h->smem_bytes = sp.total;
+  /* opt in to the device maximum once (handles with different block sizes share the kernel) */
+  int max_optin = 0;
+  CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  if ((int)sp.total > max_optin) return fail(CYG_E_INVAL, "record block does not fit in shared memory");
+  CU(wops(h->W)->set_smem_optin(max_optin));
+  return CYG_OK;
 }
 
 extern "C" {
@@ -746,7 +822,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   h->NB = pick_block_envs(h, nb_env ? atoi(nb_env) : 0);
   if (h->NB < 1 || h->NB > CYG_MAX_BLOCK_ENVS) { cudaFree(h->d_blob); delete h; return fail(CYG_E_INVAL, "CYG_BLOCK_ENVS must be in 1..512"); }
   int rc = CYG_OK;
-  DISPATCH_W(h->W, rc = configure_step<KW>(h));
+  rc = configure_step(h);
   if (rc != CYG_OK) { cudaFree(h->d_blob); delete h; return rc; }
   *out = h;
   return CYG_OK;
@@ -794,7 +870,7 @@ int cyg_import_state(cyg_handle h, const cyg_state* c, void* stream) {
   DeviceGuard g(h->device);
   ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
-  DISPATCH_W(h->W, (cyg_import_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  wops(h->W)->import_state(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -806,7 +882,7 @@ int cyg_export_state(cyg_handle h, const cyg_state* c, void* stream) {
   DeviceGuard g(h->device);
   ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
-  DISPATCH_W(h->W, (cyg_export_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  wops(h->W)->export_state(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -832,30 +908,21 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
   p.block_envs = h->NB;
+  const bool plain = !(step_flags & CYG_STEP_GROUPED) && a->order == nullptr; /* the hot form: see cyg_step_kernel */
   int blocks = (h->B + h->NB - 1) / h->NB;
   int threads = ((2 * h->NB + 31) / 32) * 32;
   if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
   if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
-#ifdef CYG_FAST_BUILD
-  if (h->W != 4) return fail(CYG_E_INVAL, "CYG_FAST_BUILD: W = 4 only");
-  cyg_step_kernel<4><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p);
-#else
   if (h->W > CYG_MAX_W) {
-    cyg_step_generic_kernel<CYG_BIG_W><<<(h->B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p);
+    wops(h->W)->step(false, (h->B + 63) / 64, 64, 0, (cudaStream_t)stream, p);
     if (out->obs) { /* post-evolve observation rows: a second launch on the generic path */
       h->launches++;
       CU(cudaGetLastError());
       return cyg_observe(h, out->obs_mode, out->obs, stream);
     }
   } else {
-    switch (h->W) {
-      case 1: cyg_step_kernel<1><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
-      case 2: cyg_step_kernel<2><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
-      case 3: cyg_step_kernel<3><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
-      default: cyg_step_kernel<4><<<blocks, threads, h->smem_bytes, (cudaStream_t)stream>>>(p); break;
-    }
+    wops(h->W)->step(plain, blocks, threads, h->smem_bytes, (cudaStream_t)stream, p);
   }
-#endif
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -867,7 +934,7 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   DeviceGuard g(h->device);
   SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
-  DISPATCH_W(h->W, (cyg_randomize_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  wops(h->W)->randomize(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -880,7 +947,7 @@ int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask
   DeviceGuard g(h->device);
   SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
-  DISPATCH_W(h->W, (cyg_sample_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  wops(h->W)->sample(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -896,7 +963,7 @@ int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream) {
   size_t total = (size_t)h->B * (obs_mode == 2 ? 4 * h->net.M + h->net.cfg.X : 6 * h->net.M);
   int blocks = (int)((total + threads - 1) / threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  DISPATCH_W(h->W, (cyg_observe_kernel<KW><<<blocks, threads, 0, (cudaStream_t)stream>>>(p)));
+  wops(h->W)->observe(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
@@ -911,3 +978,4 @@ int cyg_set_debug_cycles(cyg_handle h, uint64_t* per_env_cycles) {
 }
 
 } /* extern "C" */
+#endif /* CYG_TU_W */
