@@ -239,7 +239,7 @@ def main():
     e2e = None
     if not a.no_e2e:
         Ke = max(10, min(K, 200))
-        groups = sets[:2] if len(sets) >= 2 else sets[:1]
+        groups = sets[:3]  # every env set of the rotation is one group with its own stream
         host_actions = {}
         for gi, env in enumerate(groups):
             env._stream = torch.cuda.Stream(dev)  # one stream per env group

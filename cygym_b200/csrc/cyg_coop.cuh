@@ -282,7 +282,30 @@ struct Coop {
       uint32_t A[W];
       e.clean_mask(a, A);
       __syncwarp();
-      if (lane == 0) e.clean_scalar(A, ds, cost);
+      /* clean_scalar (rewards, discovery flags, state wipe; volt:996-1011) with one lane per (plane, word) */
+      const int ncby = e.n->ncby, items = (5 + ncby) * W;
+      int nc = 0, nu = 0;
+      uint32_t disc = 0;
+      for (int t = lane; t < items; t += 32) {
+        const int pi = t / W, w = t - pi * W;
+        uint32_t aw = 0;
+#pragma unroll
+        for (int q = 0; q < W; q++) aw |= A[q] & eqmask(q, w);
+        const int p = pi == 0 ? P_COMP : pi == 1 ? P_HASWL : pi < 5 ? P_PT0 + (pi - 2) : P_CBY0 + (pi - 5);
+        const uint32_t old = e.pl(p, w);
+        e.pl(p, w) = old & ~aw;
+        if (pi == 0) { nc += popc(aw & old); nu += popc(aw & ~old); }
+        if (pi >= 5 && (old & aw) != 0) disc |= 1u << (pi - 5);
+      }
+      nc = __reduce_add_sync(CYG_FULL, nc);
+      nu = __reduce_add_sync(CYG_FULL, nu);
+      disc = __reduce_or_sync(CYG_FULL, disc);
+      if (lane == 0) {
+        cost += (nc * 0.3 - nu * 0.01) * ds;
+        e.cleancost += (nc * 0.3 + nu * 0.01) * ds;
+        e.defcost += (nc * 0.3 + nu * 0.01) * ds;
+        e.scal(CYG_S_FLAGS) |= disc << CYG_FL_DISC_SHIFT; /* exp.discovered = True */
+      }
       __syncwarp();
       deposit(e, A, 0, c.default_high, 0);
     } else if (atype == 3) {

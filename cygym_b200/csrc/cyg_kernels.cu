@@ -99,6 +99,22 @@ struct StepParams {
                                     B all 28 warps (it is latency-bound; more warps in flight is what it needs) */
 #endif
 
+/* one record from shared to global memory by one warp: 4 bytes per lane, 128 words per round, predicated tail */
+__device__ __forceinline__ void copy_record(uint32_t* dst, const uint32_t* src, int S, int lane) {
+  for (int base = 0; base < S; base += 128) {
+    const int i0 = base + lane, i1 = i0 + 32, i2 = i0 + 64, i3 = i0 + 96;
+    uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    if (i0 < S) v0 = src[i0];
+    if (i1 < S) v1 = src[i1];
+    if (i2 < S) v2 = src[i2];
+    if (i3 < S) v3 = src[i3];
+    if (i0 < S) dst[i0] = v0;
+    if (i1 < S) dst[i1] = v1;
+    if (i2 < S) dst[i2] = v2;
+    if (i3 < S) dst[i3] = v3;
+  }
+}
+
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
   size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_def, off_bar, total;
@@ -276,24 +292,31 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
      * hitting the memory system from all SMs at once; the end of the kernel only has the deferred records left.
      * s_cnt[CYG_NKEYS + 5] = owning warps past phase A (nothing is sent before all of them are),
      * s_cnt[CYG_NKEYS + 4] = next position of perm[] to look at. */
-    auto send_home = [&](int k, bool wait) {
-      int ready = 0;
-      if (lane == 0) {
-        if (wait) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
-        ready = atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) >= (uint32_t)((nb + 31) >> 5);
+    bool home_ready = false; /* this warp has seen every owning warp past phase A */
+    auto copy_home = [&](int pos) { /* one finished record */
+      const int el_s = s_perm[pos];
+      copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
+    };
+    auto send_home = [&](bool all) { /* claim 4 positions of perm[] at a time (all: until none is left) */
+      if (!home_ready) {
+        int ready = 0;
+        if (lane == 0) {
+          if (all) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
+          ready = atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) >= (uint32_t)((nb + 31) >> 5);
+        }
+        home_ready = __shfl_sync(0xFFFFFFFFu, ready, 0) != 0;
+        if (!home_ready) return;
       }
-      ready = __shfl_sync(0xFFFFFFFFu, ready, 0);
-      if (!ready) return;
-      for (int sent = 0; sent < k;) {
+      do {
         int pos = 0;
-        if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 1u);
+        if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 4u);
         pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
         if (pos >= nb) return;
-        if ((s_def[pos >> 5] >> (pos & 31)) & 1u) continue;
-        const int el_s = s_perm[pos];
-        for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
-        sent++;
-      }
+        const uint32_t dw = s_def[pos >> 5] >> (pos & 31); /* pos is a multiple of 4: the 4 bits sit in one word */
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (pos + j < nb && !((dw >> j) & 1u)) copy_home(pos + j);
+      } while (all);
     };
     /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
      * groups were measured slower (the groups of a warp diverge and no longer issue together). */
@@ -338,7 +361,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
         }
         __syncwarp(gm);
-        send_home(2, false);
+        send_home(false);
       }
     }
     __syncwarp();
@@ -391,7 +414,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
         }
         __syncwarp();
-        send_home(2, false);
+        send_home(false);
       }
     }
     CYG_WARP_MARK(1);
@@ -428,11 +451,11 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           s_out[NB + el_b] = __int_as_float(0);
         }
         __syncwarp();
-        send_home(2, false);
+        send_home(false);
       }
     }
     CYG_WARP_MARK(2);
-    send_home(1 << 30, true); /* B4: whatever is left of the finished records */
+    send_home(true); /* B4: whatever is left of the finished records */
     __syncthreads();
   CYG_CTA_MARK(4);
     /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
@@ -465,7 +488,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     for (int pos = tid >> 5; pos < nb; pos += NT >> 5) {
       if (!((s_def[pos >> 5] >> (pos & 31)) & 1u)) continue;
       const int el_s = s_perm[pos];
-      for (int i = lane; i < S; i += 32) g_rec[(size_t)el_s * S + i] = s_rec[el_s * S + i];
+      copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
     }
     CYG_CTA_MARK(6);
   } else
