@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--subnets", type=int, default=8)
     ap.add_argument("--sets", type=int, default=3, help="independent env sets rotated to defeat L2 residency")
     ap.add_argument("--ring", type=int, default=8, help="pre-generated action batches per mode")
+    ap.add_argument("--fuse", type=int, default=4, help="plain steps fused per launch (VectorCyberDefenseEnv.step_many / cyg_step_multi); 1 = one launch per step")
     ap.add_argument("--obs", type=int, default=0, help="fused observation mode inside the step (0 none, 1 defender, 2 attacker)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,22 +217,53 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(Wm):
-        one_step(i)
-    barrier()
+    def timed(fn, n, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        l0 = sum(s.launch_count for s in sets)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(n):
+            fn(warm + i)
+        ev1.record()
+        barrier()
+        return ev0.elapsed_time(ev1), sum(s.launch_count for s in sets) - l0
+
+    F = max(1, a.fuse) if not a.obs else 1
     sampler = ClockSampler(local)
-    sampler.start()
-    l0 = sum(s.launch_count for s in sets)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for i in range(K):
-        one_step(Wm + i)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = sum(s.launch_count for s in sets) - l0
-    clocks = sampler.stop()
+    if F > 1:
+        # the headline leg: F plain steps per launch (alternating defender / attacker turns), the records of a CTA's envs
+        # stay in shared memory between them; every env set gets its own [F, B, ..] action tensors out of the ring
+        K = ((K + F - 1) // F) * F
+        fused = []
+        for s_i in range(a.sets):
+            per_set = []
+            for v in range(2):  # two variants per set so that consecutive launches of a set read different batches
+                hs = [ring[t & 1][(s_i + v * 3 + t // 2) % a.ring].hdr for t in range(F)]
+                mk = [ring[t & 1][(s_i + v * 3 + t // 2) % a.ring].mask for t in range(F)]
+                per_set.append((torch.stack(hs).contiguous(), torch.stack(mk).contiguous()))
+            fused.append(per_set)
+        outs = [(torch.empty(F, B, dtype=torch.float32, device=dev), torch.empty(F, B, dtype=torch.float32, device=dev),
+                 torch.empty(F, B, dtype=torch.int32, device=dev)) for _ in range(a.sets)]
+        torch.cuda.synchronize()
+
+        def one_launch(j):
+            s_i = j % a.sets
+            h_, m_ = fused[s_i][(j // a.sets) & 1]
+            sets[s_i].step_many(h_, m_, out=outs[s_i])
+
+        sampler.start()
+        ms, launches = timed(one_launch, K // F, max(1, (Wm + F - 1) // F))
+        clocks = sampler.stop()
+        K1 = min(K, 600)
+        ms1, _ = timed(one_step, K1, Wm)  # the same workload, one launch per step
+    else:
+        sampler.start()
+        ms, launches = timed(one_step, K, Wm)
+        clocks = sampler.stop()
+        ms1, K1 = ms, K
     errs = int(max(int(s.error_flags().max().item()) for s in sets))
 
     # ---- e2e: the public host-buffer call VectorCyberDefenseEnv.step_host(): every step copies that step's actions
@@ -280,10 +312,10 @@ def main():
         e2e = (ems, Ke, host_actions[0, 0].numel() * 4, out_host.numel() * 4, ems1, max(10, Ke // 2), len(groups))
 
     # ---- max over ranks ----
-    t = torch.tensor([ms, e2e[0] if e2e else 0.0, e2e[4] if e2e else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e[0] if e2e else 0.0, e2e[4] if e2e else 0.0, ms1], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ems, ems1 = float(t[0]), float(t[1]), float(t[2])
+    ms, ems, ems1, ms1 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank == 0:
         peaks = {}
         try:
@@ -302,8 +334,16 @@ def main():
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
-        launch_s = ms * 1e-3 / K
-        achieved = alg * B / launch_s / 1e9
+        traffic_f = None  # the same for a fused launch (its own capture)
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_step_kernel_fused_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("envs_per_launch") == B and tj.get("device_slots") == a.devices and tj.get("steps_per_launch") == F:
+                traffic_f = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        launch_s = ms * 1e-3 / (K // F)      # average duration of one launch (F steps)
+        achieved = alg * B * F / launch_s / 1e9
         value = world * B * K / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -311,12 +351,20 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
                        "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
+                       "steps_per_launch": F,
+                       "fusion": (f"{F} plain steps per launch (step_many / cyg_step_multi): open-loop action batches resident in HBM, records stay in "
+                                  "shared memory between the steps of a launch, so per-step HBM traffic is actions in + rewards out; "
+                                  "single_step_launch below is the same workload at one launch per step") if F > 1 else "one launch per step",
                        "l2_policy": f"rotating {a.sets} env sets ({a.sets * B * (sets[0].S + net.M) * 4 / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
                        "parallelism": f"env-sharded x{world}, no per-step collective", "error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
-                         "launch_us": launch_s * 1e6, "peak_source": peak_src,
-                         "actual_bytes_per_env_step": 2 * sets[0].S * 4 + 4 * (4 + net.W) + 12},
+                         "traffic": traffic if F == 1 else traffic_f, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
+                         "env_steps_per_launch": B * F, "launch_us": launch_s * 1e6, "peak_source": peak_src,
+                         "actual_bytes_per_env_step": (2 * sets[0].S * 4) / F + 4 * (4 + net.W) + 12,
+                         "note": ("algorithmic bytes are SURVEY 8(d)'s per-step figure x env-steps per launch; a fused launch moves less than that "
+                                  "(state in/out once per launch), which 8(d) allows for") if F > 1 else None},
+            "single_step_launch": {"value": world * B * K1 / (ms1 * 1e-3), "unit": UNIT, "launch_us": ms1 * 1e3 / K1, "steps": K1,
+                                   "roofline_frac": alg * B / (ms1 * 1e-3 / K1) / 1e9 / peak, "traffic": traffic},
             "clocks": clocks, "gpu_launches": int(launches),
         }
         if e2e:

@@ -85,6 +85,8 @@ struct StepParams {
   const uint8_t* bl_env;          /* optional [B]: base_line per env (CYG_BL_*); NULL = cfg.base_line for all */
   int B, env_id0, G, order_stride, obs_mode, block_envs;
   uint32_t flags;
+  int T;                /* plain steps fused into this launch (cyg_step_multi): hdr / mask hold T consecutive batches,
+                           raw / shaped / done T consecutive [B] rows; the records stay in shared memory in between */
 };
 
 #define CYG_NKEYS 48 /* sort keys: (mode, executed action type) in 0..31; 32..47 = block / unblock envs of a plain step
@@ -176,8 +178,21 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     bulk_g2s(s_tab, p.net.blob, tab_bytes, bar);
     if (bulk_ok) bulk_g2s(s_rec, g_rec, rec_bytes, bar);
   }
+  const int T = PLAIN ? (p.T < 1 ? 1 : p.T) : 1;
+  const int lane = tid & 31;
+  for (int t = 0; t < T; t++) { /* the steps fused into this launch; the records stay in shared memory */
+  const bool last = t == T - 1;
+  const uint32_t* hdr_t = p.hdr + (size_t)t * p.B * 4 * (PLAIN ? 1 : 0);
+  const uint32_t* mask_t = p.mask + (size_t)t * p.B * W * (PLAIN ? 1 : 0);
+  float* raw_t = p.raw + (size_t)t * p.B;
+  float* shaped_t = p.shaped + (size_t)t * p.B;
+  int32_t* done_t = p.done + (size_t)t * p.B;
+  if (PLAIN && !last && tid < nb) { /* the next step's action rows of this block: into L2 while this step runs */
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(hdr_t + ((size_t)p.B + env0 + tid) * 4));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_t + ((size_t)p.B + env0 + tid) * W));
+  }
   if (tid < CYG_NKEYS + 7) s_cnt[tid] = 0;
-  __syncthreads(); /* mbarrier initialised, counters zeroed */
+  __syncthreads(); /* mbarrier initialised, counters zeroed (t > 0: the previous step is complete) */
   CYG_CTA_MARK(1);
 
   /* ---- sort the block's envs by the action type they will execute (needs only the action headers, so it
@@ -185,7 +200,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   int key = 0;
   if (tid < nb) {
     if (!grouped) {
-      const uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)(env0 + tid) * 4);
+      const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)(env0 + tid) * 4);
       const uint32_t h0 = hv.x;
       const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
       const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
@@ -199,25 +214,36 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     atomicAdd(&s_cnt[key + 1], 1u);
   }
   __syncthreads();
-  if (tid == 0) { /* exclusive prefix over the keys */
-    uint32_t run = 0;
-    for (int k = 1; k <= CYG_NKEYS; k++) { uint32_t c = s_cnt[k]; s_cnt[k] = run; run += c; }
+  if (tid < 32) { /* exclusive prefix over the keys (count of key k sits in s_cnt[k + 1]): one warp, two keys per lane */
+    static_assert(CYG_NKEYS > 32 && CYG_NKEYS <= 64, "two keys per lane");
+    const uint32_t c0 = s_cnt[1 + tid];
+    const uint32_t c1 = tid < CYG_NKEYS - 32 ? s_cnt[33 + tid] : 0u;
+    uint32_t x0 = c0, x1 = c1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, x0, d), y1 = __shfl_up_sync(0xFFFFFFFFu, x1, d);
+      if (tid >= d) { x0 += y0; x1 += y1; }
+    }
+    const uint32_t total0 = __shfl_sync(0xFFFFFFFFu, x0, 31);
+    s_cnt[1 + tid] = x0 - c0;
+    if (tid < CYG_NKEYS - 32) s_cnt[33 + tid] = total0 + x1 - c1;
   }
   __syncthreads();
   if (tid < nb) {
     uint32_t pos = atomicAdd(&s_cnt[key + 1], 1u);
     s_perm[pos] = (uint16_t)tid;
   }
-  if (!bulk_ok) {
-    for (int i = tid; i < nb * S; i += NT) s_rec[i] = g_rec[i];
+  if (t == 0) {
+    if (!bulk_ok) {
+      for (int i = tid; i < nb * S; i += NT) s_rec[i] = g_rec[i];
+    }
+    mbar_wait(bar, 0);
   }
-  mbar_wait(bar, 0);
   __syncthreads();
   CYG_CTA_MARK(2);
 
   /* ---- phase A, thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or
    *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
-  const int lane = tid & 31;
   constexpr bool coop_ok = PLAIN;
   const bool lower = (tid & ~31) < nb; /* warps that own envs in the thread-per-env phases */
   bool deferred = false;
@@ -235,10 +261,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
 #endif
     int mode = 0, atype = 0;
     if (tid < nb) {
-      uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env * 4);
+      uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env * 4);
       act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-      for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env * W + w];
+      for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env * W + w];
       t_begin = p.dbg_cycles ? clock64() : 0;
       mode = (int)((act[0] >> 8) & 1u);
       if (p.bl_env) e.bl = (int)p.bl_env[env];
@@ -261,12 +287,12 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       bool dirty = false;
       if (PLAIN) e.template step_act<true>(act, act + 4, nullptr, 0, 0, 0, 1, p.flags, atype, cost, dirty);
       else if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
-      else e.step_act(p.hdr + (size_t)env * 4, p.mask + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
+      else e.step_act(hdr_t + (size_t)env * 4, mask_t + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
                       (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
       float raw, shaped;
       int32_t done;
       e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-      p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+      raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done;
     }
     if (tid < nb) {
 #ifdef CYG_PHASE_TIMING
@@ -298,6 +324,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
     };
     auto send_home = [&](bool all) { /* claim 4 positions of perm[] at a time (all: until none is left) */
+      if (!last) return; /* fused steps: the records only go home after the last one */
       if (!home_ready) {
         int ready = 0;
         if (lane == 0) {
@@ -337,10 +364,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         e.resume_epoch();
         uint32_t act[4 + W];
         {
-          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
           act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
         }
         typename Env<W, true>::Act a;
         Env<W, true>::decode(act, act + 4, nullptr, a);
@@ -392,10 +419,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         e.resume_epoch();
         uint32_t act[4 + W];
         {
-          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
           act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
         }
         typename Env<W, true>::Act a;
         Env<W, true>::decode(act, act + 4, nullptr, a);
@@ -434,10 +461,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         e.resume_epoch();
         uint32_t act[4 + W];
         {
-          uint4 hv = *reinterpret_cast<const uint4*>(p.hdr + (size_t)env_b * 4);
+          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
           act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = p.mask[(size_t)env_b * W + w];
+          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
         }
         typename Env<W, true>::Act a;
         Env<W, true>::decode(act, act + 4, nullptr, a);
@@ -465,13 +492,14 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       e.resume_epoch();
       float raw, shaped;
       int32_t done;
-      e.step_post((int)((p.hdr[(size_t)env * 4] >> 8) & 1u), (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
+      e.step_post((int)((hdr_t[(size_t)env * 4] >> 8) & 1u), (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
                   p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-      p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+      raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done;
     }
   }
   __syncthreads();
   CYG_CTA_MARK(5);
+  } /* fused steps */
 
   /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
   if (p.obs && p.obs_mode) {
@@ -911,7 +939,24 @@ int cyg_export_state(cyg_handle h, const cyg_state* c, void* stream) {
   return CYG_OK;
 }
 
+static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t step_flags, const cyg_step_out* out, void* stream);
+
 int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_step_out* out, void* stream) {
+  return step_impl(h, a, 1, step_flags, out, stream);
+}
+
+int cyg_step_multi(cyg_handle h, const cyg_actions* a, int32_t n_steps, uint32_t step_flags, const cyg_step_out* out, void* stream) {
+  if (n_steps < 1) return fail(CYG_E_INVAL, "n_steps must be >= 1");
+  if (n_steps > 1) {
+    if (!h || !a || !out) return fail(CYG_E_INVAL, "null argument");
+    if ((step_flags & CYG_STEP_GROUPED) || a->order || a->n_groups != 1) return fail(CYG_E_INVAL, "cyg_step_multi: plain steps only (no groups, no order array)");
+    if (out->obs || out->pre_masks) return fail(CYG_E_INVAL, "cyg_step_multi: no obs / pre_masks outputs");
+    if (h->W > CYG_MAX_W) return fail(CYG_E_INVAL, "cyg_step_multi: networks of at most 128 device slots");
+  }
+  return step_impl(h, a, n_steps, step_flags, out, stream);
+}
+
+static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t step_flags, const cyg_step_out* out, void* stream) {
   if (!h || !a || !out || !a->hdr || !a->mask || !out->raw_reward || !out->shaped_reward || !out->done)
     return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
@@ -930,6 +975,7 @@ int cyg_step(cyg_handle h, const cyg_actions* a, uint32_t step_flags, const cyg_
   p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
+  p.T = n_steps;
   p.block_envs = h->NB;
   const bool plain = !(step_flags & CYG_STEP_GROUPED) && a->order == nullptr; /* the hot form: see cyg_step_kernel */
   int blocks = (h->B + h->NB - 1) / h->NB;

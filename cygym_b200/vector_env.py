@@ -211,6 +211,23 @@ class VectorCyberDefenseEnv:
         self._hold = (hdr, mask, order)
         return self.raw, self.shaped, self.done
 
+    def step_many(self, hdr, mask, flags=0, out=None):
+        """T consecutive plain steps in ONE launch (cyg_step_multi): hdr [T, B, 4], mask [T, B, W] int32 device tensors
+        holding the T action batches (open-loop: fixed sequences, scripted or pre-sampled random policies -- the loop
+        body of simulate_game, do_agent.py:1875-2089).  Returns (raw [T, B], shaped [T, B], done [T, B]); the records
+        never leave shared memory between the steps.  Bit-identical to T step() calls."""
+        T = int(hdr.shape[0])
+        assert hdr.shape == (T, self.B, 4) and mask.shape == (T, self.B, self.W) and hdr.is_contiguous() and mask.is_contiguous()
+        if out is None:
+            out = (torch.empty(T, self.B, dtype=torch.float32, device=self.device),
+                   torch.empty(T, self.B, dtype=torch.float32, device=self.device),
+                   torch.empty(T, self.B, dtype=torch.int32, device=self.device))
+        a = K.CygActions(hdr.data_ptr(), mask.data_ptr(), None, 0, 1)
+        o = K.CygStepOut(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), None, None, 0)
+        K.check(self.L.cyg_step_multi(self.h, C.byref(a), T, flags, C.byref(o), self._s()))
+        self._hold = (hdr, mask, out)
+        return out
+
     # ---- host-buffer front end: what a CPU-side caller (the reference's rollout loops) uses ----
     def host_buffers(self):
         """Pinned host staging, allocated once: action headers [B, 4] and device masks [B, W] (int32) in, results

@@ -233,6 +233,16 @@ int cyg_export_state(cyg_handle h, const cyg_state* canonical, void* stream);
 int cyg_step(cyg_handle h, const cyg_actions* actions, uint32_t step_flags, const cyg_step_out* out,
              void* stream);
 
+/* n_steps consecutive plain step() calls in ONE launch: the loop body of the rollouts that replay fixed action
+ * sequences or scripted / random policies (simulate_game, do_agent.py:1875-2089; Strategy, strategy.py:25-60), where
+ * step t+1's action does not wait for a host-side policy.  actions->hdr / mask hold n_steps consecutive batches
+ * ([n_steps][B][4], [n_steps][B][W]); out->raw_reward / shaped_reward / done receive n_steps consecutive [B] rows.
+ * Every env's record stays in shared memory between the steps.  Plain steps only: no CYG_STEP_GROUPED, no order
+ * array, no obs / pre_masks, networks of at most 128 device slots (CYG_E_INVAL otherwise).  The result is
+ * bit-identical to n_steps cyg_step() calls. */
+int cyg_step_multi(cyg_handle h, const cyg_actions* actions, int32_t n_steps, uint32_t step_flags,
+                   const cyg_step_out* out, void* stream);
+
 /* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
 

@@ -298,3 +298,39 @@ def test_step_host_two_groups_async():
         torch.cuda.synchronize()
         for k in ca:
             assert torch.equal(ca[k].cpu(), cb[k].cpu()), (g, k)
+
+
+def test_step_many_equals_single_steps():
+    """cyg_step_multi: T plain steps fused into one launch (records resident in shared memory) == T cyg_step calls,
+    rewards and states bit for bit; C3 shape with a ragged last CTA, and a one-word network."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    for M, subnets, B, T in ((100, 8, 5000, 7), (30, 2, 777, 5)):
+        net = synthetic_network(M, n_subnets=subnets, seed=5)
+        a = VectorCyberDefenseEnv(net, B, seed=11)  # only here to generate T valid action batches
+        hdrs, masks = [], []
+        for t in range(T):
+            ab = a.sample_actions(t & 1)
+            if (t & 1) == 0:  # detector training is out of scope: defender 10 -> 8
+                ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == 10, (ab.hdr[:, 0] & ~0xFF) | 8, ab.hdr[:, 0])
+            hdrs.append(ab.hdr.clone()); masks.append(ab.mask.clone())
+            a.step(ab)
+        b = VectorCyberDefenseEnv(net, B, seed=11)
+        c = VectorCyberDefenseEnv(net, B, seed=11)
+        hdr = torch.stack(hdrs).contiguous(); mask = torch.stack(masks).contiguous()
+        for t in range(T):
+            c.step(type(ab)(hdr[t], mask[t]))
+        raw, shaped, done = b.step_many(hdr, mask)
+        torch.cuda.synchronize()
+        cw = [x.clone() for x in (c.raw, c.shaped, c.done)]
+        assert torch.equal(raw[T - 1], cw[0]) and torch.equal(shaped[T - 1], cw[1]) and torch.equal(done[T - 1], cw[2])
+        sb, sc = b.export_state(), c.export_state()
+        for k in sb:
+            assert torch.equal(sb[k], sc[k]), (M, k)
+        # and every intermediate reward row
+        d = VectorCyberDefenseEnv(net, B, seed=11)
+        for t in range(T):
+            r = d.step(type(ab)(hdr[t], mask[t]))
+            assert torch.equal(raw[t], r[0]) and torch.equal(shaped[t], r[1]) and torch.equal(done[t], r[2]), (M, t)
+        assert b.error_flags().max().item() == d.error_flags().max().item()
