@@ -74,7 +74,7 @@ class CygStepOut(C.Structure):
                 ("pre_masks", C.c_void_p), ("obs", C.c_void_p), ("obs_mode", C.c_int32)]
 
 
-EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_internal_words",
+EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_set_base_line_per_env_steps", "cyg_internal_words",
            "cyg_bind", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_randomize", "cyg_sample_actions",
            "cyg_observe", "cyg_launch_count", "cyg_set_debug_cycles"]
 
@@ -168,6 +168,7 @@ def lib():
         L.cyg_destroy.argtypes = [C.c_void_p]
         L.cyg_set_base_line.argtypes = [C.c_void_p, C.c_int32]
         L.cyg_set_base_line_per_env.argtypes = [C.c_void_p, C.c_void_p]
+        L.cyg_set_base_line_per_env_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.cyg_internal_words.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.cyg_bind.argtypes = [C.c_void_p, C.c_void_p]
         L.cyg_import_state.argtypes = [C.c_void_p, C.POINTER(CygState), C.c_void_p]

@@ -83,6 +83,7 @@ struct StepParams {
   float* obs;
   unsigned long long* dbg_cycles; /* optional [B]: SM cycles each env's step took (diagnostics) */
   const uint8_t* bl_env;          /* optional [B]: base_line per env (CYG_BL_*); NULL = cfg.base_line for all */
+  int bl_stride;                  /* fused steps: bl_env row of step t starts at t * bl_stride (0: one row for all) */
   int B, env_id0, G, order_stride, obs_mode, block_envs;
   uint32_t flags;
   int T;                /* plain steps fused into this launch (cyg_step_multi): hdr / mask hold T consecutive batches,
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   float* raw_t = p.raw + (size_t)t * p.B;
   float* shaped_t = p.shaped + (size_t)t * p.B;
   int32_t* done_t = p.done + (size_t)t * p.B;
+  const uint8_t* bl_t = p.bl_env ? p.bl_env + (size_t)t * p.bl_stride : nullptr; /* base_line rows may change per step */
   if (PLAIN && !last && tid < nb) { /* the next step's action rows of this block: into L2 while this step runs */
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hdr_t + ((size_t)p.B + env0 + tid) * 4));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_t + ((size_t)p.B + env0 + tid) * W));
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     if (!grouped) {
       const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)(env0 + tid) * 4);
       const uint32_t h0 = hv.x;
-      const int blk = p.bl_env ? (int)p.bl_env[env0 + tid] : p.net.cfg.base_line;
+      const int blk = bl_t ? (int)bl_t[env0 + tid] : p.net.cfg.base_line;
       const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env * W + w];
       t_begin = p.dbg_cycles ? clock64() : 0;
       mode = (int)((act[0] >> 8) & 1u);
-      if (p.bl_env) e.bl = (int)p.bl_env[env];
+      if (bl_t) e.bl = (int)bl_t[env];
       atype = e.step_pre(act, p.flags);
       deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
     }
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         }
         typename Env<W, true>::Act a;
         Env<W, true>::decode(act, act + 4, nullptr, a);
-        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0], p.bl_env ? (int)p.bl_env[env_b] : p.net.cfg.base_line);
+        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
         double cost = 0.0;
         bool dirty = false;
         long long tb0 = p.dbg_cycles ? clock64() : 0;
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (task >= ntasks) break;
         const int el_b = s_perm[lo + task];
         const int env_b = env0 + el_b;
-        if ((p.bl_env ? (int)p.bl_env[env_b] : p.net.cfg.base_line) == CYG_BL_NO_ATTACK) continue; /* phase A did it */
+        if ((bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line) == CYG_BL_NO_ATTACK) continue; /* phase A did it */
         Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                        (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
         e.resume_epoch();
@@ -787,6 +789,7 @@ struct cyg_env_s {
   int B, env_id0, device, W, NB, n_sms;
   unsigned long long* dbg_cycles;
   const uint8_t* bl_env;
+  int bl_rows;       /* rows of [B] codes behind bl_env (cyg_set_base_line_per_env_steps; 1 otherwise) */
   size_t smem_bytes;
   int64_t launches;
 };
@@ -857,7 +860,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   if (!h) return fail(CYG_E_NOMEM, "out of host memory");
   std::string err = build_tables(*cfg, *host_net, h->blob);
   if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
-  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr;
+  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr; h->bl_rows = 1;
   h->W = h->blob.net.W;
   DeviceGuard g(device);
   if (!g.ok) { delete h; return fail(CYG_E_CUDA, "cudaSetDevice failed"); }
@@ -896,6 +899,15 @@ int cyg_set_base_line(cyg_handle h, int32_t base_line) {
 int cyg_set_base_line_per_env(cyg_handle h, const uint8_t* base_line) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   h->bl_env = base_line;
+  h->bl_rows = 1;
+  return CYG_OK;
+}
+
+int cyg_set_base_line_per_env_steps(cyg_handle h, const uint8_t* base_line, int32_t n_rows) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  if (base_line && n_rows < 1) return fail(CYG_E_INVAL, "n_rows must be >= 1");
+  h->bl_env = base_line;
+  h->bl_rows = base_line ? n_rows : 1;
   return CYG_OK;
 }
 
@@ -949,6 +961,7 @@ int cyg_step_multi(cyg_handle h, const cyg_actions* a, int32_t n_steps, uint32_t
   if (n_steps < 1) return fail(CYG_E_INVAL, "n_steps must be >= 1");
   if (n_steps > 1) {
     if (!h || !a || !out) return fail(CYG_E_INVAL, "null argument");
+    if (h->bl_env && h->bl_rows > 1 && h->bl_rows < n_steps) return fail(CYG_E_INVAL, "cyg_step_multi: fewer base_line rows than steps");
     if ((step_flags & CYG_STEP_GROUPED) || a->order || a->n_groups != 1) return fail(CYG_E_INVAL, "cyg_step_multi: plain steps only (no groups, no order array)");
     if (out->obs || out->pre_masks) return fail(CYG_E_INVAL, "cyg_step_multi: no obs / pre_masks outputs");
     if (h->W > CYG_MAX_W) return fail(CYG_E_INVAL, "cyg_step_multi: networks of at most 128 device slots");
@@ -971,7 +984,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   p.recs = h->state; p.ckpt = ckpt_of(h); p.xtra = xtra_of(h);
   p.hdr = a->hdr; p.mask = a->mask; p.order = a->order;
   p.raw = out->raw_reward; p.shaped = out->shaped_reward; p.done = out->done;
-  p.pre_masks = out->pre_masks; p.obs = out->obs; p.dbg_cycles = h->dbg_cycles; p.bl_env = h->bl_env;
+  p.pre_masks = out->pre_masks; p.obs = out->obs; p.dbg_cycles = h->dbg_cycles; p.bl_env = h->bl_env; p.bl_stride = (h->bl_env && h->bl_rows > 1) ? h->B : 0;
   p.B = h->B; p.env_id0 = h->env_id0; p.G = a->n_groups; p.order_stride = a->order_stride;
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;

@@ -101,12 +101,13 @@ def evaluate_payoff_matrix(network, def_strategies, att_strategies, n_rollouts, 
 
 
 def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_rollouts, steps_per_episode=100, seed=0,
-                                   device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True):
+                                   device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True, steps_per_launch=10):
     """Same result as evaluate_payoff_matrix(), with ALL (pair, rollout) combinations in one batch: the flattened
     index g = pair * n_rollouts + rollout is split contiguously over the ranks (env id == g, so the draw streams
-    do not depend on the number of ranks), every turn is ONE kernel launch, baselines act through the per-env
-    base_line array (cyg_set_base_line_per_env) and fixed-sequence strategies through per-pair action rows gathered
-    to the envs on the device.  Strategies with unsorted / repeated device lists are not handled here (use the
+    do not depend on the number of ranks), `steps_per_launch` turns are ONE kernel launch (cyg_step_multi: the records
+    stay in shared memory between the turns), baselines act through per-env base_line rows (one per turn of the
+    launch, cyg_set_base_line_per_env_steps) and fixed-sequence strategies through per-pair action rows gathered to
+    the envs on the device.  Strategies with unsorted / repeated device lists are not handled here (use the
     per-pair evaluator)."""
     import torch
     from .vector_env import ActionBatch, VectorCyberDefenseEnv
@@ -128,23 +129,38 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
             s[:, slot] = 0
         bl_pair = torch.full((P,), K.BASE_LINES["Nash"], dtype=torch.uint8, device=device)
         ret = torch.zeros(2, nloc, dtype=torch.float64, device=device)
-        for t in range(steps_per_episode):
-            mode = t & 1
-            strategies = def_strategies if mode == 0 else att_strategies
-            decided = [st.decide(t) for st in strategies]
-            for a, _ in decided:
-                if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
-                    raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
-            hdr, mask, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
-            which = i_of_pair if mode == 0 else j_of_pair
-            new_bl = torch.tensor([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], dtype=torch.uint8, device=device)[which]
-            bl_pair = torch.where(new_bl == 255, bl_pair, new_bl)   # a strategy that sets no base_line leaves it as it was
-            env.set_base_line_per_env(bl_pair[pair_of_env])
-            sel = which[pair_of_env]
-            ab = ActionBatch(torch.from_numpy(hdr.view(np.int32)).to(device)[sel].contiguous(),
-                             torch.from_numpy(mask.view(np.int32)).to(device)[sel].contiguous())
-            raw, _, _ = env.step(ab)
-            ret[mode] += raw.double()
+        fuse = max(1, int(steps_per_launch)) if network.W <= 4 else 1
+        t0 = 0
+        while t0 < steps_per_episode:
+            # one chunk of turns = ONE launch (cyg_step_multi): per-pair action rows and base_line codes of every turn
+            # of the chunk are packed on the host ([Tc, P, ..], tiny) and gathered to the envs on the device
+            Tc = min(fuse, steps_per_episode - t0)
+            hdr_p, mask_p, bl_p = [], [], []
+            for t in range(t0, t0 + Tc):
+                mode = t & 1
+                strategies = def_strategies if mode == 0 else att_strategies
+                decided = [st.decide(t) for st in strategies]
+                for a, _ in decided:
+                    if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
+                        raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
+                hdr, mask, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
+                which = i_of_pair if mode == 0 else j_of_pair
+                new_bl = torch.tensor([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], dtype=torch.uint8, device=device)[which]
+                bl_pair = torch.where(new_bl == 255, bl_pair, new_bl)   # a strategy that sets no base_line leaves it as it was
+                hdr_p.append(torch.from_numpy(hdr.view(np.int32)).to(device)[which])
+                mask_p.append(torch.from_numpy(mask.view(np.int32)).to(device)[which])
+                bl_p.append(bl_pair)
+            if Tc == 1:
+                env.set_base_line_per_env(bl_p[0][pair_of_env])
+                raw, _, _ = env.step(ActionBatch(hdr_p[0][pair_of_env].contiguous(), mask_p[0][pair_of_env].contiguous()))
+                ret[t0 & 1] += raw.double()
+            else:
+                env.set_base_line_per_env(torch.stack(bl_p)[:, pair_of_env])
+                raw, _, _ = env.step_many(torch.stack(hdr_p)[:, pair_of_env].contiguous(), torch.stack(mask_p)[:, pair_of_env].contiguous())
+                r64 = raw.double()
+                ret[t0 & 1] += r64[0::2].sum(0)
+                ret[(t0 + 1) & 1] += r64[1::2].sum(0)
+            t0 += Tc
         info = env.info()
         cols = torch.stack([ret[0], ret[1], info["Compromised_devices"].double(), info["work_done"].double(),
                             info["Scan_count"].double(), info["defensive_cost"].double(), info["checkpoint_count"].double(),

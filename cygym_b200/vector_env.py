@@ -128,11 +128,16 @@ class VectorCyberDefenseEnv:
         K.check(self.L.cyg_set_base_line(self.h, K.BASE_LINES.get(name, 4)))
 
     def set_base_line_per_env(self, codes):
-        """codes: uint8 device tensor [B] of CYG_BL_* (see _capi.BASE_LINES), or None to go back to the handle-wide value."""
+        """codes: uint8 device tensor [B] of CYG_BL_* (see _capi.BASE_LINES), or [T, B] with one row per step of the
+        next step_many() launches, or None to go back to the handle-wide value."""
         if codes is not None:
             codes = codes.to(self.device, torch.uint8).contiguous()
         self._bl_env = codes
-        K.check(self.L.cyg_set_base_line_per_env(self.h, _ptr(codes)))
+        if codes is not None and codes.dim() == 2:
+            assert codes.shape[1] == self.B
+            K.check(self.L.cyg_set_base_line_per_env_steps(self.h, _ptr(codes), int(codes.shape[0])))
+        else:
+            K.check(self.L.cyg_set_base_line_per_env(self.h, _ptr(codes)))
 
     def _canon_alloc(self):
         u = dict(dtype=torch.int32, device=self.device)

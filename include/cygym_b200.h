@@ -215,6 +215,9 @@ int cyg_set_base_line(cyg_handle h, int32_t base_line);
  * handle-wide value).  Lets one batch hold rollouts of different (defender, attacker) strategy pairs, whose
  * baselines set env.base_line on every turn (do_agent.py:716-719). */
 int cyg_set_base_line_per_env(cyg_handle h, const uint8_t* base_line);
+/* The same with one row per fused step: base_line[n_rows][B]; step t of a cyg_step_multi launch reads row t (the
+ * baselines of the two players set env.base_line on alternating turns), cyg_step reads row 0. */
+int cyg_set_base_line_per_env_steps(cyg_handle h, const uint8_t* base_line, int32_t n_rows);
 
 /* uint32 words PER ENV the caller must allocate for the kernels' internal state.  The buffer holds, in this
  * order: B records of S words (16 scalars + bit-planes + the blocked-edge bitset in out- and in-list order;

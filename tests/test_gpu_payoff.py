@@ -67,3 +67,7 @@ def test_payoff_matrix_matches_oracle_and_shards():
               for r in range(3)]
     three = reduce_payoff(parts3[0] + parts3[1] + parts3[2], N, T).cpu().numpy()
     assert np.allclose(three, got, rtol=1e-12, atol=1e-9)
+    # the turns of a rollout fused 7 / 1 per launch (cyg_step_multi with one base_line row per turn): same sums
+    for spl in (7, 1):
+        alt = evaluate_payoff_matrix_batched(net, defs, atts, N, steps_per_episode=T, seed=seed, xcap=xcap, steps_per_launch=spl).cpu().numpy()
+        assert np.allclose(alt, got, rtol=1e-12, atol=1e-9), (spl, np.abs(alt - got).max())
