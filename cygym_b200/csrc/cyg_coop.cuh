@@ -112,14 +112,105 @@ struct Coop {
     if (na == 0) return;
     if (lg == 0) { cost += -0.5 * ds * na; e.defcost += 0.5 * ds * na; }
     uint32_t cnt = 0;
-    if (e.n_extra() > 0) { /* envs with extra (hub-star) edges: the general sequential walk on one lane */
-      if (lg == 0) {
-        Stream st(site);
+    if (e.n_extra() > 0) {
+      /* envs with extra (hub-star) edges (every env once randomize_compromise_and_ownership moved the owned set): the
+       * same fixed-point passes with the pools in NEIGHBOUR-ID space, as flip_incident_general builds them (out_row /
+       * in_row: base bit rows minus / intersected with the blocked pairs, plus the extra list; weights from the
+       * multiplicity planes).  A pick is the directed pair (u, v); a lower lane's pick touches this lane's device d
+       * as its out-edge (u == d: neighbour v leaves the out pool) or its in-edge (v == d: u leaves the in pool). */
+      int pos = 0;
+      uint32_t kbase = 0;
+      while (pos < na) { /* uniform */
+        const int idx = pos + lg;
+        const bool valid = idx < na;
+        const int d = valid ? e.select_nth(act, idx) : 0;
+        const bool has_blk = e.any_blocked();
+        uint32_t O0[W], I0[W], O[W], I[W];
+        e.out_row(d, has_blk, want, O0);
+        e.in_row(d, has_blk, want, I0);
+#pragma unroll
+        for (int q = 0; q < W; q++) { O0[q] = valid ? O0[q] : 0u; I0[q] = valid ? I0[q] : 0u; O[q] = O0[q]; I[q] = I0[q]; }
+        const bool multi = e.devbit(e.n->o_incmulti, d);
+        const uint32_t *lo = e.tc + e.n->o_mlo + d * W, *hi = e.tc + e.n->o_mhi + d * W;
+        const uint32_t *loT = e.tc + e.n->o_mloT + d * W, *hiT = e.tc + e.n->o_mhiT + d * W;
+        const uint32_t xd = draw_at(e.rng, site, kbase + (uint32_t)lg);
+        int key = -2; /* u | v << 16 of the pick, -1: empty pool */
+        uint32_t nem = 0;
+        bool had_att = false;
         for (;;) {
-          int d = e.pop_lowest(act);
-          if (d < 0) break;
-          if (e.flip_incident(d, want, st)) cnt++;
+          const int to = e.weight_below(O, lo, hi, multi, 32 * W), ti = e.weight_below(I, loT, hiT, multi, 32 * W);
+          const int total = to + ti;
+          const bool nonempty = total > 0;
+          nem = __ballot_sync(gm, nonempty);
+          const uint32_t x = __shfl_sync(gm, xd, popc(nem & lanes_below(lg)));
+          int nkey = -1, other = -1;
+          if (nonempty) {
+            const int r = (int)below(x, (uint32_t)total);
+            if (r < to) { other = e.weighted_select(O, lo, hi, multi, r); nkey = d | (other << 16); }
+            else { other = e.weighted_select(I, loT, hiT, multi, r - to); nkey = other | (d << 16); }
+          }
+          const bool changed = __any_sync(gm, nkey != key);
+          key = nkey;
+          if (!changed) break;
+          int vl = -1;
+          if (nonempty) {
+            const int ow = other >> 5;
+            const uint32_t ob = 1u << (other & 31);
+            uint32_t in = 0;
+            int rank = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+              in |= act[w] & ob & eqmask(w, ow);
+              rank += popc(act[w] & (w < ow ? 0xFFFFFFFFu : (ob - 1u) & eqmask(w, ow)));
+            }
+            const int l = rank - pos;
+            if (in != 0 && l > lg && l < 32) vl = l;
+          }
+          const uint32_t bv = __ballot_sync(gm, vl >= 0);
+          if (bv == 0 && !had_att) break;
+          uint32_t att = bv;
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const uint32_t bk = __ballot_sync(gm, vl >= 0 && ((vl >> k) & 1));
+            att &= ((lg >> k) & 1) ? bk : ~bk;
+          }
+          had_att = bv != 0;
+#pragma unroll
+          for (int q = 0; q < W; q++) { O[q] = O0[q]; I[q] = I0[q]; }
+          while (__any_sync(gm, att != 0)) {
+            const int from = att ? (__ffs((int)att) - 1) : lg;
+            const int kj = __shfl_sync(gm, key, from);
+            if (att) {
+              const int uj = kj & 0xFFFF, vj = kj >> 16;
+              const bool mine_out = uj == d; /* else vj == d */
+              const int nb_id = mine_out ? vj : uj;
+              const uint32_t bit = 1u << (nb_id & 31);
+#pragma unroll
+              for (int q = 0; q < W; q++) {
+                const uint32_t m = bit & eqmask(q, nb_id >> 5);
+                O[q] &= ~(mine_out ? m : 0u);
+                I[q] &= ~(mine_out ? 0u : m);
+              }
+              att &= att - 1u;
+            }
+          }
         }
+        if (key >= 0) { /* commit: base pairs through both orders of the bitset, extra edges in their list */
+          const int u = key & 0xFFFF, v = key >> 16;
+          if ((e.adj(u, v >> 5) >> (v & 31)) & 1u) {
+            set_blocked_atomic(e, e.base_eid(u, v), !want);
+          } else {
+            const int nx = e.n_extra();
+            uint32_t* x = e.extra();
+            const uint32_t k24 = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
+            for (int j = 0; j < nx; j++)
+              if ((x[j] & 0xFFFFFFu) == k24) { if (!want) atomicOr(&x[j], CYG_X_BLOCKED); else atomicAnd(&x[j], ~CYG_X_BLOCKED); break; }
+          }
+        }
+        const uint32_t done = (uint32_t)popc(nem);
+        cnt += done; kbase += done; pos += 32;
+        __threadfence_block();
+        __syncwarp(gm);
       }
     } else {
       /* Windows of 32 listed devices.  Lane i speculates the pick of device pos + i on the state at the start of the
@@ -220,11 +311,9 @@ struct Coop {
     const bool has_blk = e.any_blocked();
     const int nx = e.n_extra();
     __syncwarp();
-    if (nx > 0) { /* envs with extra (hub-star) edges: the sequential loop on one lane */
-      if (lane == 0) { double cost = 0.0; e.attacker_act(a, 1, cost); }
-      __syncwarp();
-      return;
-    }
+    /* envs with extra (hub-star) edges (nx > 0: every env after randomize_compromise_and_ownership moved the owned
+     * set) take attack_source's general form, which materialises the unblocked row of a source from the base bit row,
+     * the blocked pairs and the extra list; nx is per env, so the lanes of the warp stay on one form */
     uint32_t logs_add = 0, zk = 0;
     for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
       int raw = a.ex(xi);
@@ -245,7 +334,7 @@ struct Coop {
         for (int w = 0; w < W; w++) comp[w] = e.pl(P_COMP, w);
         int cnt = 0, v = -1;
         bool rule3 = false;
-        if (valid) v = e.attack_source(s, comp, kv, has_blk, 0, cnt, rule3);
+        if (valid) v = e.attack_source(s, comp, kv, has_blk, nx, cnt, rule3);
         const uint32_t same = __match_any_sync(CYG_FULL, v >= 0 ? v : (0x1000 + lane));
         const bool conflict = valid && rule3 && (same & lanes_below(lane)) != 0;
         const uint32_t conf = __ballot_sync(CYG_FULL, conflict);
