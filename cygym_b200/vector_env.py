@@ -179,7 +179,8 @@ class VectorCyberDefenseEnv:
             row = np.zeros(width, np.uint32)
             src = np.asarray(t[k], np.uint32)
             row[: len(src)] = src
-            canon[k] = np.broadcast_to(row, (self.B, width)).copy()
+            # one row to the device, broadcast there (B x width words never cross PCIe)
+            canon[k] = torch.from_numpy(row.view(np.int32)).to(self.device).unsqueeze(0).expand(self.B, width).contiguous()
         return self.import_state(canon)
 
     # ---- the hot path ----

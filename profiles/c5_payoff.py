@@ -40,13 +40,17 @@ def seq(mode, L):
 defs = [Strategy(baseline_name="No Defense"), Strategy(baseline_name="Preset"), Strategy(baseline_name="Nash")] + \
        [Strategy(actions=seq(0, 5)) for _ in range(ND - 3)]
 atts = [Strategy(baseline_name="No Attack"), Strategy(baseline_name="Nash")] + [Strategy(actions=seq(1, 4)) for _ in range(NA - 2)]
+# a tiny evaluation first: loads the CUDA module and sets the kernel attributes (about 1 s, paid once per process)
+tw = time.perf_counter()
+evaluate_payoff_matrix_batched(net, defs[:2], atts[:2], 8 * world, steps_per_episode=4, seed=1, device=dev, rank=rank, world=world)
 torch.cuda.synchronize()
+warm_s = time.perf_counter() - tw
 t0 = time.perf_counter()
 out = evaluate_payoff_matrix_batched(net, defs, atts, N, steps_per_episode=T, seed=1, device=dev, rank=rank, world=world)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if rank == 0:
-    print(json.dumps({"config": f"C5: {ND}x{NA} pairs x {N} rollouts x {T} steps", "n_gpus": world, "seconds": dt,
+    print(json.dumps({"config": f"C5: {ND}x{NA} pairs x {N} rollouts x {T} steps", "n_gpus": world, "seconds": dt, "first_call_warmup_seconds": warm_s,
                       "env_steps_per_s": ND * NA * N * T / dt, "checksum": float(out.sum().item()),
                       "defender_return_mean": float(out[..., 0].mean().item()), "attacker_return_mean": float(out[..., 1].mean().item())}))
 if world > 1:
