@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--sets", type=int, default=3, help="independent env sets rotated to defeat L2 residency")
     ap.add_argument("--ring", type=int, default=8, help="pre-generated action batches per mode")
     ap.add_argument("--fuse", type=int, default=4, help="plain steps fused per launch (VectorCyberDefenseEnv.step_many / cyg_step_multi); 1 = one launch per step")
+    ap.add_argument("--randomize", action="store_true", help="randomize_compromise_and_ownership() on every env set first (diagnostic: "
+                    "the owned set moves, evolve_network adds extra hub-star edges, and the steps take the kernels' extra-edge forms)")
     ap.add_argument("--obs", type=int, default=0, help="fused observation mode inside the step (0 none, 1 defender, 2 attacker)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -193,6 +195,9 @@ def main():
     # one env set per rotation slot; env ids are globally unique across ranks and sets
     sets = [VectorCyberDefenseEnv(net, B, device=dev, seed=a.seed, env_id0=(rank * a.sets + s) * B, xcap=16)
             for s in range(a.sets)]
+    if a.randomize:
+        for s_ in sets:
+            s_.randomize_compromise_and_ownership()
     # ring of pre-generated action batches (inputs resident in HBM before the timed region)
     ring = {0: [], 1: []}
     for mode in (0, 1):
@@ -351,7 +356,7 @@ def main():
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
                        "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
-                       "steps_per_launch": F,
+                       "randomized_ownership": bool(a.randomize), "steps_per_launch": F,
                        "fusion": (f"{F} plain steps per launch (step_many / cyg_step_multi): open-loop action batches resident in HBM, records stay in "
                                   "shared memory between the steps of a launch, so per-step HBM traffic is actions in + rewards out; "
                                   "single_step_launch below is the same workload at one launch per step") if F > 1 else "one launch per step",
