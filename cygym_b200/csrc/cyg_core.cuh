@@ -1434,20 +1434,47 @@ struct Env {
     /* bidirectional hub-star among active attacker-owned devices, hub = lowest id (:738-774) */
     int hub = -1;
     bool changed = false;
-    for (int w = 0; w < W; w++) {
-      uint32_t oa = pl(P_OWNED, w) & pl(P_ACTSET, w);
-      while (oa) {
-        int i = w * 32 + ctz(oa);
-        oa &= oa - 1;
-        if (hub < 0) { hub = i; continue; }
-        for (int dir = 0; dir < 2; dir++) {
-          int u = dir ? i : hub, v = dir ? hub : i;
-          if (has_edge(u, v)) continue;
-          int nx = n_extra();
-          if (nx >= c.xcap) { scal(CYG_S_FLAGS) |= CYG_FL_ERR_XCAP; continue; }
-          extra()[nx] = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
-          scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFFu) | ((uint32_t)(nx + 1) << 16);
-          changed = true;
+    uint32_t oa[W];
+    for (int w = W - 1; w >= 0; w--) {
+      oa[w] = pl(P_OWNED, w) & pl(P_ACTSET, w);
+      if (oa[w]) hub = w * 32 + ctz(oa[w]);
+    }
+    if (hub >= 0) {
+      /* ONE pass over the extra list (it lives in global memory: the loads are independent and pipeline) instead of
+       * one has_edge() scan per direction and device: the extra out- and in-neighbours of the hub as bit rows */
+      uint32_t xo[W], xi[W];
+      for (int w = 0; w < W; w++) { xo[w] = 0; xi[w] = 0; }
+      {
+        const int nx0 = n_extra();
+        const uint32_t* x = extra();
+        for (int j = 0; j < nx0; j++) {
+          const uint32_t xe = x[j];
+          const int u = (int)(xe & CYG_X_IDMASK), v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+          for (int w = 0; w < W; w++) {
+            xo[w] |= (u == hub) ? ((1u << (v & 31)) & eqmask(w, v >> 5)) : 0u;
+            xi[w] |= (v == hub) ? ((1u << (u & 31)) & eqmask(w, u >> 5)) : 0u;
+          }
+        }
+      }
+      for (int w = 0; w < W; w++) {
+        uint32_t rest = oa[w] & ~((1u << (hub & 31)) & eqmask(w, hub >> 5));
+        /* devices i of this word that lack hub -> i (base row of the hub or an extra edge) or i -> hub */
+        uint32_t need_out = rest & ~(adj(hub, w) | xo[w]);
+        uint32_t need_in = rest & ~xi[w];
+        while (rest) {
+          const int b = ctz(rest);
+          rest &= rest - 1;
+          const int i = w * 32 + b;
+          for (int dir = 0; dir < 2; dir++) {
+            const int u = dir ? i : hub, v = dir ? hub : i;
+            const bool missing = dir ? (((need_in >> b) & 1u) && !((adj(i, hub >> 5) >> (hub & 31)) & 1u)) : (((need_out >> b) & 1u) != 0);
+            if (!missing) continue;
+            int nx = n_extra();
+            if (nx >= c.xcap) { scal(CYG_S_FLAGS) |= CYG_FL_ERR_XCAP; continue; }
+            extra()[nx] = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
+            scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFFu) | ((uint32_t)(nx + 1) << 16);
+            changed = true;
+          }
         }
       }
     }

@@ -15,6 +15,8 @@ from cygym_b200.vector_env import VectorCyberDefenseEnv  # noqa: E402
 B = 65536
 net = synthetic_network(100, n_subnets=8, seed=0)
 env = VectorCyberDefenseEnv(net, B, seed=0)
+if os.environ.get("RANDOMIZE"):
+    env.randomize_compromise_and_ownership()
 dbg = torch.zeros(B * 8, dtype=torch.int64, device="cuda")
 env.L.cyg_set_debug_cycles(env.h, C.c_void_p(dbg.data_ptr()))
 names = ["epoch", "decode+tick", "action", "work", "arrivals", "count+reward", "evolve", "end"]

@@ -14,6 +14,8 @@ from cygym_b200.vector_env import VectorCyberDefenseEnv  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 net = synthetic_network(100, n_subnets=8, seed=0)
 env = VectorCyberDefenseEnv(net, B, seed=0)
+if os.environ.get("RANDOMIZE"):  # extra hub-star edges in every env (the Double-Oracle rollout case)
+    env.randomize_compromise_and_ownership()
 dbg = torch.zeros(B, dtype=torch.int64, device="cuda")
 env.L.cyg_set_debug_cycles(env.h, C.c_void_p(dbg.data_ptr()))
 for t in range(40):
