@@ -1402,8 +1402,9 @@ struct Env {
     int n_act = count(P_ACTSET);
     Stream sp(SITE_EV_POISSON), sadd(SITE_EV_ADD), spick(SITE_EV_PICK), satt(SITE_EV_ATT);
     uint32_t xp = sp.next(rng); /* :668 */
-    int num_events = 0; /* #{j : xp >= tab[j]}; the table is ascending */
-    while (num_events < 16 && xp >= c.poisson_tab[num_events]) num_events++;
+    int num_events = 0; /* #{j : xp >= tab[j]}; the table is ascending: count over all 16 entries with fixed indices
+                           (a walk with a per-thread index serialises the constant-bank loads of a warp) */
+    for (int j = 0; j < 16; j++) num_events += (xp >= c.poisson_tab[j]) ? 1 : 0;
     int floor_n = c.num_of_device > c.min_network_size ? c.num_of_device : c.min_network_size;
     for (int ev = 0; ev < num_events; ev++) {
       uint32_t xa = sadd.next(rng); /* :679 */
@@ -1424,7 +1425,11 @@ struct Env {
         for (int w = 0; w < W; w++) m[w] = pl(P_ACTSET, w);
         int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)n_act));
         setb(P_NYA, node);
+#ifdef __CUDA_ARCH__
+        atomicOr(&ckpt[node], CYG_CKI_REMOVED); /* removed_before: a RED, nobody waits for the global-memory round trip */
+#else
         ckpt[node] |= CYG_CKI_REMOVED; /* removed_before */
+#endif
         drop_wl(node);
         set_field(P_BUSY0, 4, node, 0);
         clrb(P_ACTSET, node);
