@@ -86,7 +86,7 @@ class CygError(RuntimeError):
 
 
 SPILL_LIMIT = 256   # bytes of spill stores tolerated in the config-C3 step kernel (cyg_step_kernel<4, true>)
-THREAD_CAPS = (896, 768, 640)  # threads per CTA -> 72 / 80 / 93 registers per thread at one CTA per SM
+THREAD_CAPS = (640, 512)  # threads per CTA -> 93 / 127 registers per thread at one CTA per SM (640 measured fastest)
 
 
 def _step_kernel_spill(ptxas_log, mangled="_Z15cyg_step_kernelILi4ELb1EEv10StepParams"):
@@ -132,10 +132,10 @@ def compile_units(out_path, widths=PLANE_WIDTHS, extra=(), obj_dir=None, verbose
 def build(force=False, verbose=False):
     """Compile cygym_b200/csrc/cyg_kernels.cu for sm_100a into cygym_b200/libcygym_b200.so.
 
-    The step kernel runs one CTA per SM with as many warps as the register file allows (896 threads = 72 registers
-    per thread), which leaves ptxas next to a cliff (~50 bytes vs ~2 KB of spills in the warp-per-env routines).  The
-    recipe checks `-Xptxas -v` and, should the config-C3 kernel spill more than SPILL_LIMIT bytes, rebuilds with the
-    next lower thread cap (more registers per thread; the caps measured within a few % of each other on B200)."""
+    The step kernel runs one CTA per SM; 640 threads (93 registers per thread, no spills) measured fastest on B200
+    (896 threads / 72 registers sat next to a ptxas cliff: ~90 bytes vs ~2 KB of spills in the warp-per-env routines).
+    The recipe checks `-Xptxas -v` and, should the config-C3 kernel spill more than SPILL_LIMIT bytes, rebuilds with
+    the next lower thread cap (more registers per thread)."""
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in _DEPS):
         return LIB_PATH
     log = ""

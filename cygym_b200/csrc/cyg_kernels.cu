@@ -97,9 +97,10 @@ struct StepParams {
                           write-back is bound by the per-SM path to L2: ~16k cycles for 210 KB either way) */
 #define CYG_MAX_BLOCK_ENVS 512   /* envs per CTA */
 #ifndef CYG_MAX_BLOCK_THREADS
-#define CYG_MAX_BLOCK_THREADS 896 /* threads per CTA: 72 registers per thread at one CTA per SM.  A CTA runs twice as
-                                    many threads as envs: phases A / C use one thread per env, the warp-per-env phase
-                                    B all 28 warps (it is latency-bound; more warps in flight is what it needs) */
+#define CYG_MAX_BLOCK_THREADS 640 /* threads per CTA at one CTA per SM: 20 warps with up to 93 registers each.  Phases A / C
+                                    use one thread per env, the warp-per-env phase B every warp.  Measured with the final
+                                    kernel (4 fused steps / one launch per step): 896 threads (72 registers, 88 B of spills)
+                                    46.4 / 56.6 us, 768: 44.1 / 54.7, 640: 42.5 / 53.7, 576: 43.2 / 55.8, 512: 44.0 / 56.8 */
 #endif
 
 /* one record from shared to global memory by one warp: 4 bytes per lane, 128 words per round, predicated tail */
