@@ -559,6 +559,7 @@ struct Env {
   /* ---- action decoding (include/cygym_b200.h "actions") ---- */
   struct Act {
     int mode, atype, n_ex, n_dev, app_index;
+    int first; /* device_indices[0] carried by a set-form header (hdr[2] >> 16, minus 1); -1: the lowest listed id */
     uint32_t exw;
     const uint32_t* mask;
     const uint16_t* order;
@@ -572,7 +573,8 @@ struct Env {
     a.n_ex = (int)((h0 >> 16) & 0xFFu);
     if (a.n_ex > 4) a.n_ex = 4;
     a.exw = hdr[1];
-    a.n_dev = (int)hdr[2];
+    a.n_dev = (int)(hdr[2] & 0xFFFFu);
+    a.first = (int)(hdr[2] >> 16) - 1;
     a.app_index = (int)hdr[3];
     a.mask = mask;
     a.order = order;
@@ -594,8 +596,9 @@ struct Env {
     it.cur = d + 1;
     return d < M ? d : -1;
   }
-  CYG_HD int first_dev(const Act& a) {
+  CYG_HD int first_dev(const Act& a) { /* device_indices[0] */
     DevIter it;
+    if (!a.order && a.first >= 0 && a.first < n->M) return a.first; /* sample_action's first draw (CyberDefenseEnv.py:565) */
     return a.n_dev > 0 ? next_dev(a, it) : -1;
   }
 
@@ -1011,9 +1014,26 @@ struct Env {
       case 12: { /* acts on device_indices[0] once per listed active device (volt:1102-1109) */
         int dev0 = first_dev(a);
         if (ckpt[dev0] & CYG_CK_VALID) {
-          restore_device(dev0);
-          cost += -1.0 * ds * na;
-          defcost += 1.0 * ds * na;
+          /* the first restore rewrites Not_yet_added of dev0 itself: when dev0 is not the first active listed device
+           * (sample_action's draw order), its own iteration is skipped / taken by the CHECKPOINTED flag */
+          uint32_t l[W];
+          listed(a, l);
+          int before = 0;
+          bool l0 = false, a0 = false;
+          for (int w = 0; w < W; w++) {
+            const uint32_t b0 = (1u << (dev0 & 31)) & eqmask(w, dev0 >> 5);
+            before += popc(act[w] & (w < (dev0 >> 5) ? 0xFFFFFFFFu : ((b0 - 1u) & eqmask(w, dev0 >> 5))));
+            l0 = l0 || (l[w] & b0) != 0;
+            a0 = a0 || (act[w] & b0) != 0;
+          }
+          const int others = na - (a0 ? 1 : 0);
+          const bool cnt0 = before > 0 ? (l0 && !(ckpt[dev0] & CYG_CK_NYA)) : a0;
+          const int total = others + (cnt0 ? 1 : 0);
+          if (total > 0) {
+            restore_device(dev0);
+            cost += -1.0 * ds * total;
+            defcost += 1.0 * ds * total;
+          }
         }
       } break;
       case 13: { /* volt:1111-1123: only the last of the `na` _stall draws survives */
@@ -1556,7 +1576,7 @@ struct Env {
     const int mode = a.mode;
     if (LIGHT && coop_type(mode, atype)) { store_costs(); return atype; }
     if (!grouped) {
-      if (a.atype == -1000) { a.n_dev = 0; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
+      if (a.atype == -1000) { a.n_dev = 0; a.first = -1; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
       if (mode == CYG_MODE_DEFENDER) {
         defender_meta(a, atype, false, cost, dirty);
         if (atype == 1 || atype == 4 || atype == 5 || atype == 6 || atype == 7 || atype == 9 || atype == 12 || atype == 13)
@@ -1697,8 +1717,9 @@ struct Env {
     }
   }
 
-  /* ---- sample_action (CyberDefenseEnv.py:555-578): device_indices as a set ---- */
-  CYG_HD void sample_action(int mode, uint32_t* hdr, uint32_t* mask) {
+  /* ---- sample_action (CyberDefenseEnv.py:555-578): device_indices as a set; the draw order of random.sample is kept
+   *      for device_indices[0] (header field) and, when `order` is given, for the whole list ---- */
+  CYG_HD void sample_action(int mode, uint32_t* hdr, uint32_t* mask, uint16_t* order = nullptr) {
     const cyg_config& c = n->cfg;
     begin_epoch();
     Stream st(SITE_SA_TYPE), sn(SITE_SA_NDEV), sd(SITE_SA_DEVS), sx(SITE_SA_EXP), sa(SITE_SA_APP);
@@ -1707,17 +1728,19 @@ struct Env {
     int ndev = 1 + (int)below(sn.next(rng), (uint32_t)c.num_of_device);
     uint32_t pool[W], pick[W];
     for (int w = 0; w < W; w++) { pool[w] = m_valid(w); pick[w] = 0; }
-    int rem = n->M;
+    int rem = n->M, first = 0;
     for (int j = 0; j < ndev; j++) {
       int d = select_nth(pool, (int)below(sd.next(rng), (uint32_t)rem));
       for (int w = 0; w < W; w++) { uint32_t bw = (1u << (d & 31)) & eqmask(w, d >> 5); pool[w] &= ~bw; pick[w] |= bw; }
       rem--;
+      if (order) order[j] = (uint16_t)d;
+      first = j == 0 ? d : first;
     }
     int ex = (int)below(sx.next(rng), (uint32_t)c.X);
     int app = c.n_app_ids > 0 ? (int)below(sa.next(rng), (uint32_t)c.n_app_ids) : 0;
     hdr[0] = (uint32_t)(atype & 0xFF) | ((uint32_t)mode << 8) | (1u << 16);
     hdr[1] = (uint32_t)(ex & 0xFF);
-    hdr[2] = (uint32_t)ndev;
+    hdr[2] = (uint32_t)ndev | ((uint32_t)(first + 1) << 16); /* device_indices[0] = the first device drawn */
     hdr[3] = (uint32_t)app;
     for (int w = 0; w < W; w++) if (w < n->Wm) mask[w] = pick[w];
   }

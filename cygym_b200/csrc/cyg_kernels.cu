@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
-        int nd = (int)hv.z;
+        int nd = (int)(hv.z & 0xFFFFu);
         nd = nd < 0 ? 0 : (nd > 127 ? 127 : nd);
         key = CYG_KEY_FLIP0 + 2 * (7 - (nd >> 4)) + (key == 9 ? 1 : 0);
       }
@@ -577,6 +577,8 @@ struct SimpleParams {
   uint32_t* hdr;
   uint32_t* mask;
   int B, env_id0, mode;
+  uint16_t* order;  /* optional [B][order_stride]: device_indices in draw order (cyg_sample_actions_ordered) */
+  int order_stride;
 };
 
 template <int W>
@@ -597,7 +599,7 @@ __global__ void cyg_sample_kernel(const __grid_constant__ SimpleParams p) {
   for (int i = 0; i < CYG_NSCAL; i++) rec[i] = g[i];
   Env<W> e(&p.net, rec, nullptr, nullptr, (uint32_t)(p.env_id0 + env));
   uint32_t h[4], m[W];
-  e.sample_action(p.mode, h, m);
+  e.sample_action(p.mode, h, m, p.order ? p.order + (size_t)env * p.order_stride : nullptr);
   g[CYG_S_EPOCH] = rec[CYG_S_EPOCH];
   for (int i = 0; i < 4; i++) p.hdr[(size_t)env * 4 + i] = h[i];
   for (int w = 0; w < W; w++) if (w < p.net.Wm) p.mask[(size_t)env * p.net.Wm + w] = m[w];
@@ -1015,7 +1017,7 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0};
+  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->randomize(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
@@ -1024,11 +1026,17 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
 }
 
 int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream) {
+  return cyg_sample_actions_ordered(h, mode, hdr, mask, nullptr, 0, stream);
+}
+
+int cyg_sample_actions_ordered(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, uint16_t* order, int32_t order_stride,
+                               void* stream) {
   if (!h || !hdr || !mask) return fail(CYG_E_INVAL, "null argument");
+  if (order && order_stride < h->net.cfg.num_of_device) return fail(CYG_E_INVAL, "order_stride must hold numOfDevice entries");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   if (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER) return fail(CYG_E_INVAL, "mode must be 0 or 1");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode};
+  SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode, order, order_stride};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->sample(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;

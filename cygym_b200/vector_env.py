@@ -344,13 +344,21 @@ class VectorCyberDefenseEnv:
             self._hold_mask = env_mask
         K.check(self.L.cyg_randomize(self.h, _ptr(env_mask), self._s()))
 
-    def sample_actions(self, mode, out: ActionBatch = None):
-        """sample_action() of every env (CyberDefenseEnv.py:555-578) as an ActionBatch on the device."""
+    def sample_actions(self, mode, out: ActionBatch = None, want_order=False):
+        """sample_action() of every env (CyberDefenseEnv.py:555-578) as an ActionBatch on the device.  The set form
+        (hdr + mask) carries device_indices[0] of the draw in hdr[:, 2] >> 16; want_order=True also fills `order`
+        [B, M] int16 with the whole list in random.sample's draw order (stepping with it takes the order-form kernel)."""
         m = 1 if mode in (1, "attacker") else 0
         if out is None:
             out = ActionBatch(torch.zeros(self.B, 4, dtype=torch.int32, device=self.device),
                               torch.zeros(self.B, self.W, dtype=torch.int32, device=self.device))
-        K.check(self.L.cyg_sample_actions(self.h, m, _ptr(out.hdr), _ptr(out.mask), self._s()))
+        if want_order:
+            if out.order is None:
+                out.order = torch.zeros(self.B, self.M, dtype=torch.int16, device=self.device)
+            K.check(self.L.cyg_sample_actions_ordered(self.h, m, _ptr(out.hdr), _ptr(out.mask), _ptr(out.order),
+                                                      int(out.order.shape[1]), self._s()))
+        else:
+            K.check(self.L.cyg_sample_actions(self.h, m, _ptr(out.hdr), _ptr(out.mask), self._s()))
         return out
 
     def to_device(self, hdr, mask, order=None):

@@ -110,7 +110,10 @@ enum {
 #define CYG_ATYPE_NONE 0x80u  /* action is None: filled from base_line (volt_typhoon_env.py:847-874) */
 /* hdr[0]: atype (bits 0-7, signed) | mode<<8 (0 defender, 1 attacker) | n_ex<<16 (0..4) */
 /* hdr[1]: exploit_indices[0..3], one signed byte each */
-/* hdr[2]: n_dev (len(device_indices)) */
+/* hdr[2]: n_dev (len(device_indices), bits 0-15) | (device_indices[0] + 1) << 16 -- the high half is optional: 0 means
+ *         "the lowest listed id".  cyg_sample_actions fills it with the first device random.sample drew
+ *         (CyberDefenseEnv.py:565), so that the actions that act on device_indices[0] (10, 11, 12, 13) hit a uniformly
+ *         random device as in the reference; the remaining devices of a set-form list are visited in ascending order */
 /* hdr[3]: app_index (int32) */
 #define CYG_MODE_DEFENDER 0
 #define CYG_MODE_ATTACKER 1
@@ -251,6 +254,11 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
 
 /* Replaces sample_action() (CyberDefenseEnv.py:555-578) for every env; writes hdr[B][4], mask[B][W]. */
 int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream);
+/* The same, also writing device_indices in the DRAW order of random.sample (CyberDefenseEnv.py:565) into
+ * order[B][order_stride] (uint16, order_stride >= numOfDevice): pass it back as cyg_actions.order for a step that
+ * visits the devices exactly in the reference's order. */
+int cyg_sample_actions_ordered(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, uint16_t* order,
+                               int32_t order_stride, void* stream);
 
 /* Replaces _get_defender_state / _get_attacker_state / _get_state (CyberDefenseEnv.py:241/194/146). */
 int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream);

@@ -327,6 +327,7 @@ static void arrivals_if_due(env_t* e) {
 /* ---- action decoding ----------------------------------------------------- */
 typedef struct {
   int mode, atype, n_ex, ex[4], n_dev, app_index;
+  int first; /* device_indices[0] when the set form carries it (hdr[2] >> 16, minus 1), else -1 */
   const uint32_t* mask;
   const uint16_t* order;
 } act_t;
@@ -338,7 +339,8 @@ static void decode(const uint32_t* hdr, const uint32_t* mask, const uint16_t* or
   a->n_ex = (int)((hdr[0] >> 16) & 0xFF);
   if (a->n_ex > 4) a->n_ex = 4;
   for (int i = 0; i < 4; i++) a->ex[i] = (int)(int8_t)((hdr[1] >> (8 * i)) & 0xFF);
-  a->n_dev = (int)hdr[2];
+  a->n_dev = (int)(hdr[2] & 0xFFFFu);
+  a->first = (int)(hdr[2] >> 16) - 1;
   a->app_index = (int)hdr[3];
   a->mask = mask;
   a->order = order;
@@ -351,6 +353,14 @@ static int dev_at(const cyo_t* n, const act_t* a, int i, int* cursor) {
   while (d < M && !((a->mask[d >> 5] >> (d & 31)) & 1)) d++;
   *cursor = d + 1;
   return d < M ? d : -1;
+}
+
+/* device_indices[0]: the order array's first entry, the header's first-drawn device (sample_action keeps the draw
+ * order of random.sample only for this entry; CyberDefenseEnv.py:565), else the lowest listed id */
+static int dev_first(const cyo_t* n, const act_t* a) {
+  int cur = 0;
+  if (!a->order && a->first >= 0 && a->first < n->M) return a->first;
+  return dev_at(n, a, 0, &cur);
 }
 
 typedef struct { double cost; int dirty; } acc_t;
@@ -399,7 +409,6 @@ static void defender_meta(env_t* e, const act_t* a, int atype, int grouped, acc_
   int M = n->M;
   double ds = c->def_scale;
   uint32_t* scal = e->scal;
-  int cur = 0;
   if (atype == 2) {
     scal[CYG_S_CKPT]++;
     scal[CYG_S_FLAGS] |= CYG_FL_HAS_CKPT; /* checkpoint_variables: an alias, not a copy */
@@ -419,7 +428,7 @@ static void defender_meta(env_t* e, const act_t* a, int atype, int grouped, acc_
   } else if (atype == 10) {
     if (!grouped) { /* volt:946-953; the grouped variant has no busy bump (volt:650-659) */
       if (a->n_dev > 0) {
-        int d = dev_at(n, a, 0, &cur);
+        int d = dev_first(n, a);
         e->dev[d] = set_busy(e->dev[d], BUSY(e->dev[d]) + 1);
       } else {
         for (int i = 0; i < M; i++) if (BUSY(e->dev[i]) > 0) e->dev[i] = set_busy(e->dev[i], BUSY(e->dev[i]) + 1);
@@ -428,7 +437,7 @@ static void defender_meta(env_t* e, const act_t* a, int atype, int grouped, acc_
     acc->cost += -1.0 * ds;
     if (scal[CYG_S_LOGS] > 0) scal[CYG_S_FLAGS] |= CYG_FL_DET_TRAINED; /* sklearn fit: out of scope */
   } else if (atype == 11) {
-    int d = dev_at(n, a, 0, &cur); /* host raises ValueError when n_dev == 0 (volt:965-966) */
+    int d = dev_first(n, a); /* host raises ValueError when n_dev == 0 (volt:965-966) */
     uint32_t w = e->dev[d];
     uint32_t k = CYG_CK_VALID;
     if (w & CYG_DEV_COMP) k |= CYG_CK_COMP;
@@ -464,8 +473,8 @@ static void defender_per_device(env_t* e, const act_t* a, int atype, acc_t* acc,
   const cyg_config* c = &n->cfg;
   double ds = c->def_scale;
   uint32_t* scal = e->scal;
-  int cur = 0, cur0 = 0;
-  int dev0 = a->n_dev > 0 ? dev_at(n, a, 0, &cur0) : -1;
+  int cur = 0;
+  int dev0 = a->n_dev > 0 ? dev_first(n, a) : -1;
   for (int i = 0; i < a->n_dev; i++) {
     int d = dev_at(n, a, i, &cur);
     if (d < 0) break;
@@ -632,7 +641,7 @@ static void step_env(env_t* e, const uint32_t* hdr, const uint32_t* mask, const 
     if (atype == -1000) { /* action is None (volt:847-874) */
       if (mode == CYG_MODE_DEFENDER) { atype = (c->base_line == CYG_BL_NO_DEFENSE) ? 8 : 7; }
       else { atype = (c->base_line == CYG_BL_NO_ATTACK) ? 3 : 2; }
-      a.n_dev = 0; a.n_ex = 1; a.ex[0] = 0; a.app_index = 0;
+      a.n_dev = 0; a.first = -1; a.n_ex = 1; a.ex[0] = 0; a.app_index = 0;
     }
     if (mode == CYG_MODE_DEFENDER) { if (!(atype >= 0 && atype < c->def_space_n)) atype = 8; }
     else { if (!(atype >= 0 && atype < c->att_space_n)) atype = 3; }
@@ -773,7 +782,7 @@ static void sample_action_env(env_t* e, int mode, uint32_t* hdr, uint32_t* mask,
   int* pool = (int*)malloc(sizeof(int) * (size_t)M);
   for (int i = 0; i < M; i++) pool[i] = i;
   memset(mask, 0, sizeof(uint32_t) * (size_t)W);
-  int rem = M;
+  int rem = M, first = 0;
   for (int j = 0; j < ndev; j++) {
     uint32_t r = below(draw(&e->rng, SITE_SA_DEVS), (uint32_t)rem);
     int d = pool[r];
@@ -781,13 +790,14 @@ static void sample_action_env(env_t* e, int mode, uint32_t* hdr, uint32_t* mask,
     rem--;
     mask[d >> 5] |= 1u << (d & 31);
     if (order) order[j] = (uint16_t)d;
+    if (j == 0) first = d;
   }
   free(pool);
   int ex = (int)below(draw(&e->rng, SITE_SA_EXP), (uint32_t)c->X);
   int app = c->n_app_ids > 0 ? (int)below(draw(&e->rng, SITE_SA_APP), (uint32_t)c->n_app_ids) : 0;
   hdr[0] = (uint32_t)(atype & 0xFF) | ((uint32_t)mode << 8) | (1u << 16);
   hdr[1] = (uint32_t)(ex & 0xFF);
-  hdr[2] = (uint32_t)ndev;
+  hdr[2] = (uint32_t)ndev | ((uint32_t)(first + 1) << 16); /* device_indices[0] = the first device drawn */
   hdr[3] = (uint32_t)app;
 }
 

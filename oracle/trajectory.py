@@ -49,7 +49,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
     init = H.extract_state(env, netw, ctx.epoch)
     rec = dict(kind=[], mode=[], n_groups=[], hdr=[], mask=[], order=[], baseline=[],
                dev=[], ckpt=[], blocked=[], scal=[], extra=[], n_extra=[], raw=[], shaped=[], done=[], exec_atype=[],
-               pre=[], obs_def=[], obs_att=[])
+               pre=[], obs_def=[], obs_att=[], sa_first=[])
 
     def snap(raw=0.0, shaped=0.0, done=False, ex=0, state=None):
         st = H.extract_state(env, netw, ctx.epoch)
@@ -70,7 +70,10 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
         rec["obs_def"].append(np.asarray(env._get_defender_state(), np.float32))
         rec["obs_att"].append(np.asarray(env._get_attacker_state(), np.float32))
 
-    def push_op(kind, mode, groups, baseline=0):
+    def push_op(kind, mode, groups, baseline=0, firsts=()):
+        sf = np.full(G_MAX, -1, np.int16)
+        sf[:len(firsts)] = firsts
+        rec["sa_first"].append(sf)  # device_indices[0] of each sampled group in the reference's draw order
         hdr = np.zeros((G_MAX, 4), np.uint32); mask = np.zeros((G_MAX, W), np.uint32); order = np.zeros((G_MAX, M), np.uint16)
         for g, a in enumerate(groups):
             h, m, o = O.pack_action(a, mode, M, order_form)
@@ -103,8 +106,9 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
             push_op(OP_STEP, op[1], [None])
             snap(raw, shaped, done, info["executed_atype"], state)
         elif op[0] == "step":
-            a = fix(H.ref_sample_action(env, op[1]), op[1])
-            push_op_args = (OP_STEP, op[1], [a])
+            a0 = H.ref_sample_action(env, op[1])
+            a = fix(a0, op[1])
+            push_op_args = (OP_STEP, op[1], [a], 0, [a0[2][0]])
             # sample_action consumed an epoch on the reference side: record it as an explicit epoch bump
             raw, shaped, done, info, state = H.ref_step(env, op[1], a)
             push_op(*push_op_args)
@@ -112,9 +116,11 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
         else:  # grouped
             mode = op[1]
             ng = int(rng.integers(1, G_MAX + 1))
-            groups = []
+            groups, firsts = [], []
             for _ in range(ng):
-                a = fix(H.ref_sample_action(env, mode), mode)
+                a0 = H.ref_sample_action(env, mode)
+                firsts.append(a0[2][0])
+                a = fix(a0, mode)
                 at = a[0]
                 if mode == "defender":
                     at = int(rng.choice([0, 1, 1, 2, 3, 8, 10, 11, 1, 5]))
@@ -124,7 +130,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
             env.mode = mode
             with ctx.window():
                 state, raw, shaped, done, info, _ = env.step(list(groups))
-            push_op(OP_GROUPED, mode, groups)
+            push_op(OP_GROUPED, mode, groups, 0, firsts)
             snap(float(raw), float(shaped), bool(done), -1, state)
     out = {k: np.asarray(v) for k, v in rec.items()}
     out["n_sample_epochs"] = np.asarray(0)
@@ -142,7 +148,34 @@ class Mismatch(AssertionError):
     pass
 
 
-def replay(g, impl, check_obs=True, rtol=1e-5, label="impl"):
+def _check_sampled(g, t, gi, kind, order_form, got, label):
+    """sample_action() parity: `got` = (hdr[4], mask[W], order[M]) an implementation sampled where the reference's own
+    sample_action() produced the recorded group `gi` of op `t`.  The recorder rewrites two things afterwards (record():
+    fix() turns defender 10 into 8 while the detector has logs; grouped defender steps get a scripted action type), the
+    device list is stored sorted in the set form; `sa_first` keeps device_indices[0] of the draw order."""
+    h, m, o = got
+    rh = np.asarray(g["hdr"][t][gi], np.uint32)
+    mode = int(g["mode"][t])
+    sat, rat = int(h[0]) & 0xFF, int(rh[0]) & 0xFF
+    if kind == OP_STEP and not (sat == rat or (mode == 0 and sat == 10 and rat == 8)):
+        raise Mismatch(f"{label}: op {t}: sample_action type {sat} != recorded {rat}")
+    if (int(h[0]) >> 8) != (int(rh[0]) >> 8) or int(h[1]) != int(rh[1]) or int(h[3]) != int(rh[3]):
+        raise Mismatch(f"{label}: op {t} group {gi}: sample_action header {[hex(int(x)) for x in h]} != {[hex(int(x)) for x in rh]}")
+    nd = int(rh[2])
+    if (int(h[2]) & 0xFFFF) != nd or not np.array_equal(np.asarray(m, np.uint32), np.asarray(g["mask"][t][gi], np.uint32)):
+        raise Mismatch(f"{label}: op {t} group {gi}: sample_action device set differs")
+    first = (int(h[2]) >> 16) - 1
+    if order_form:
+        ro = np.asarray(g["order"][t][gi][:nd])
+        if o is not None and not np.array_equal(np.asarray(o[:nd]), ro):
+            raise Mismatch(f"{label}: op {t} group {gi}: sample_action device order differs")
+        if first != int(ro[0]):
+            raise Mismatch(f"{label}: op {t} group {gi}: device_indices[0] {first} != {int(ro[0])}")
+    elif "sa_first" in g and int(g["sa_first"][t][gi]) >= 0 and first != int(g["sa_first"][t][gi]):
+        raise Mismatch(f"{label}: op {t} group {gi}: device_indices[0] {first} != {int(g['sa_first'][t][gi])}")
+
+
+def replay(g, impl, check_obs=True, rtol=1e-5, label="impl", check_sample=True):
     """Feed golden trajectory `g` (dict / NpzFile) to `impl` and compare after every op.
 
     impl protocol (canonical numpy arrays in, canonical out):
@@ -168,9 +201,14 @@ def replay(g, impl, check_obs=True, rtol=1e-5, label="impl"):
             hdr = np.array(g["hdr"][t][:G])[:, None, :]
             mask = np.array(g["mask"][t][:G])[:, None, :]
             order = np.array(g["order"][t][:G])[:, None, :] if order_form else None
-            # the reference drew each (non-None) action with sample_action(): one epoch per group
-            n_sampled = sum(1 for gi in range(G) if (int(hdr[gi, 0, 0]) & 0xFF) != 0x80) if True else 0
-            impl.bump_epoch(n_sampled)
+            # the reference drew each (non-None) action with sample_action() (CyberDefenseEnv.py:555-578), one epoch per
+            # group: the implementation samples too and must come up with the recorded action
+            sampled = [gi for gi in range(G) if (int(hdr[gi, 0, 0]) & 0xFF) != 0x80]
+            if check_sample and hasattr(impl, "sample_action"):
+                for gi in sampled:
+                    _check_sampled(g, t, gi, kind, order_form, impl.sample_action(int(g["mode"][t])), label)
+            else:
+                impl.bump_epoch(len(sampled))
             out = impl.step(hdr, mask, order, 1 if kind == OP_GROUPED else 0)
             raw, shaped = float(g["raw"][t]), float(g["shaped"][t])
             tol = rtol * max(1.0, abs(raw))
@@ -229,6 +267,10 @@ class OracleImpl:
 
     def bump_epoch(self, n):
         self.st.scal[0, 1] += np.uint32(n)
+
+    def sample_action(self, mode):
+        h, m, o = self.orc.sample_actions(self.st, mode, want_order=True)
+        return h[0], m[0], o[0]
 
     def step(self, hdr, mask, order, flags):
         return self.orc.step(self.st, hdr, mask, order, flags=flags, want_pre=True)

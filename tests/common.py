@@ -33,6 +33,12 @@ class CudaImpl:
         if n:
             self.env.scalars[:, 1] += int(n)
 
+    def sample_action(self, mode):
+        ab = self.env.sample_actions(mode, want_order=True)
+        self.torch.cuda.synchronize()
+        return (ab.hdr.cpu().numpy().view(np.uint32)[0], ab.mask.cpu().numpy().view(np.uint32)[0],
+                ab.order.cpu().numpy().view(np.uint16)[0])
+
     def step(self, hdr, mask, order, flags):
         env = self.env
         G = hdr.shape[0]

