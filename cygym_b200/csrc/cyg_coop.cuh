@@ -89,174 +89,211 @@ struct Coop {
     __syncwarp();
   }
 
-  static __device__ __forceinline__ void set_blocked_atomic(E& e, int eid, bool b) {
-    const int j = e.out2in(eid);
-    uint32_t* bo = e.blocked() + (eid >> 5);
-    uint32_t* bi = e.blocked_in() + (j >> 5);
-    if (b) { atomicOr(bo, 1u << (eid & 31)); atomicOr(bi, 1u << (j & 31)); atomicAdd(&e.nblk(), 1u); }
-    else { atomicAnd(bo, ~(1u << (eid & 31))); atomicAnd(bi, ~(1u << (j & 31))); atomicSub(&e.nblk(), 1u); }
-  }
-
-  /* block (6) / unblock (9) one incident edge per listed active device, in listed order.
-   * A group of G lanes owns the env (the kernel uses G = 32; the first invalid pick of a round is typically 4-6
-   * lanes in, but sub-warp groups diverge from each other and were measured slower). */
+  /* block (6) / unblock (9) one incident edge per listed active device, in listed order (volt:1071-1100 -> :485-511).
+   *
+   * The pool of a device is the window [ip[d], ip[d+1]) of the unit bitset (cyg_core.cuh): weight = popcount, pick =
+   * select.  Devices with at most 32 incident units -- all but the few star centres -- hold their window in ONE
+   * register, and a run of up to 32 consecutive listed devices of that kind is a WINDOW of lanes: lane i speculates the
+   * pick of its device on the state at the start of the window; a pick is wrong only if a LOWER lane flips an edge
+   * that ends at this lane's device (that edge leaves the pool).  Each pass tells every lane which lower lanes
+   * currently do that ("attackers"), the lane drops those edges from its start-of-window pool and picks again; the
+   * picks are a function of the lower lanes' picks only, so the pass where nothing changes is the sequential walk's
+   * outcome and all flips commit at once.  A device with more than 32 units ends the window and is done alone, exactly,
+   * by the whole warp (lane l holds word l of its window).  The draw index of a device = draws consumed + non-empty
+   * pools in front of it; lane l computed Philox block l of the site once per task, draws are fetched by shuffle.
+   *
+   * Envs with extra (hub-star) edges keep those in the per-env list (lane j holds extra j): an extra edge sits in its
+   * endpoint's out / in list at its place in ascending neighbour order, so its index in the pool = pool units in front
+   * of that place + pool extras with a smaller far endpoint; a pick that lands on such an index takes the extra edge,
+   * the picks behind it shift by one. */
   template <int G>
   static __device__ __forceinline__ void flip(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
-    const int lane = lane_id(), lg = lane % G, gbase = lane - lg;
-    const uint32_t gm = (G == 32) ? CYG_FULL : (((1u << (G & 31)) - 1u) << gbase);
+    const int lane = lane_id();
     const bool want = atype == 9;
     const int site = want ? SITE_UNBLOCK : SITE_BLOCK;
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
     const double ds = (double)e.n->cfg.def_scale;
     uint32_t act[W];
     const int na = e.listed_active(a, act);
     if (na == 0) return;
-    if (lg == 0) { cost += -0.5 * ds * na; e.defcost += 0.5 * ds * na; }
+    if (lane == 0) { cost += -0.5 * ds * na; e.defcost += 0.5 * ds * na; }
+    const int nx = e.n_extra();
     uint32_t cnt = 0;
-    if (e.n_extra() > 0) {
-      /* envs with extra (hub-star) edges (every env once randomize_compromise_and_ownership moved the owned set): the
-       * same fixed-point passes with the pools in NEIGHBOUR-ID space, as flip_incident_general builds them (out_row /
-       * in_row: base bit rows minus / intersected with the blocked pairs, plus the extra list; weights from the
-       * multiplicity planes).  A pick is the directed pair (u, v); a lower lane's pick touches this lane's device d
-       * as its out-edge (u == d: neighbour v leaves the out pool) or its in-edge (v == d: u leaves the in pool). */
-      int pos = 0;
-      uint32_t kbase = 0;
-      while (pos < na) { /* uniform */
-        const int idx = pos + lg;
-        const bool valid = idx < na;
-        const int d = valid ? e.select_nth(act, idx) : 0;
-        const bool has_blk = e.any_blocked();
-        uint32_t O0[W], I0[W], O[W], I[W];
-        e.out_row(d, has_blk, want, O0);
-        e.in_row(d, has_blk, want, I0);
-#pragma unroll
-        for (int q = 0; q < W; q++) { O0[q] = valid ? O0[q] : 0u; I0[q] = valid ? I0[q] : 0u; O[q] = O0[q]; I[q] = I0[q]; }
-        const bool multi = e.devbit(e.n->o_incmulti, d);
-        const uint32_t *lo = e.tc + e.n->o_mlo + d * W, *hi = e.tc + e.n->o_mhi + d * W;
-        const uint32_t *loT = e.tc + e.n->o_mloT + d * W, *hiT = e.tc + e.n->o_mhiT + d * W;
-        const uint32_t xd = draw_at(e.rng, site, kbase + (uint32_t)lg);
-        int key = -2; /* u | v << 16 of the pick, -1: empty pool */
-        uint32_t nem = 0;
-        bool had_att = false;
+    if (nx > 32) { /* more extra edges than lanes: the sequential form, one lane (rare: many attacker arrivals) */
+      if (lane == 0) {
+        Stream st(site);
         for (;;) {
-          const int to = e.weight_below(O, lo, hi, multi, 32 * W), ti = e.weight_below(I, loT, hiT, multi, 32 * W);
-          const int total = to + ti;
-          const bool nonempty = total > 0;
-          nem = __ballot_sync(gm, nonempty);
-          const uint32_t x = __shfl_sync(gm, xd, popc(nem & lanes_below(lg)));
-          int nkey = -1, other = -1;
-          if (nonempty) {
-            const int r = (int)below(x, (uint32_t)total);
-            if (r < to) { other = e.weighted_select(O, lo, hi, multi, r); nkey = d | (other << 16); }
-            else { other = e.weighted_select(I, loT, hiT, multi, r - to); nkey = other | (d << 16); }
-          }
-          const bool changed = __any_sync(gm, nkey != key);
-          key = nkey;
-          if (!changed) break;
-          int vl = -1;
-          if (nonempty) {
-            const int ow = other >> 5;
-            const uint32_t ob = 1u << (other & 31);
-            uint32_t in = 0;
-            int rank = 0;
-#pragma unroll
-            for (int w = 0; w < W; w++) {
-              in |= act[w] & ob & eqmask(w, ow);
-              rank += popc(act[w] & (w < ow ? 0xFFFFFFFFu : (ob - 1u) & eqmask(w, ow)));
-            }
-            const int l = rank - pos;
-            if (in != 0 && l > lg && l < 32) vl = l;
-          }
-          const uint32_t bv = __ballot_sync(gm, vl >= 0);
-          if (bv == 0 && !had_att) break;
-          uint32_t att = bv;
-#pragma unroll
-          for (int k = 0; k < 5; k++) {
-            const uint32_t bk = __ballot_sync(gm, vl >= 0 && ((vl >> k) & 1));
-            att &= ((lg >> k) & 1) ? bk : ~bk;
-          }
-          had_att = bv != 0;
-#pragma unroll
-          for (int q = 0; q < W; q++) { O[q] = O0[q]; I[q] = I0[q]; }
-          while (__any_sync(gm, att != 0)) {
-            const int from = att ? (__ffs((int)att) - 1) : lg;
-            const int kj = __shfl_sync(gm, key, from);
-            if (att) {
-              const int uj = kj & 0xFFFF, vj = kj >> 16;
-              const bool mine_out = uj == d; /* else vj == d */
-              const int nb_id = mine_out ? vj : uj;
-              const uint32_t bit = 1u << (nb_id & 31);
-#pragma unroll
-              for (int q = 0; q < W; q++) {
-                const uint32_t m = bit & eqmask(q, nb_id >> 5);
-                O[q] &= ~(mine_out ? m : 0u);
-                I[q] &= ~(mine_out ? 0u : m);
-              }
-              att &= att - 1u;
-            }
-          }
+          const int d = e.pop_lowest(act);
+          if (d < 0) break;
+          if (e.flip_incident(d, want, st)) cnt++;
         }
-        if (key >= 0) { /* commit: base pairs through both orders of the bitset, extra edges in their list */
-          const int u = key & 0xFFFF, v = key >> 16;
-          if ((e.adj(u, v >> 5) >> (v & 31)) & 1u) {
-            set_blocked_atomic(e, e.base_eid(u, v), !want);
-          } else {
-            const int nx = e.n_extra();
-            uint32_t* x = e.extra();
-            const uint32_t k24 = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
-            for (int j = 0; j < nx; j++)
-              if ((x[j] & 0xFFFFFFu) == k24) { if (!want) atomicOr(&x[j], CYG_X_BLOCKED); else atomicAnd(&x[j], ~CYG_X_BLOCKED); break; }
-          }
-        }
-        const uint32_t done = (uint32_t)popc(nem);
-        cnt += done; kbase += done; pos += 32;
-        __threadfence_block();
-        __syncwarp(gm);
       }
+      cnt = __shfl_sync(CYG_FULL, cnt, 0);
     } else {
-      /* Windows of 32 listed devices.  Lane i speculates the pick of device pos + i on the state at the start of the
-       * window; a pick is wrong only if a LOWER lane flips an edge that ends at this lane's device (that edge leaves
-       * the pool).  Each pass tells every lane which lower lanes currently do that ("attackers"), the lane drops those
-       * edges from its start-of-window pool and picks again; the picks are a function of the lower lanes' picks only,
-       * so the pass where nothing changes is the sequential walk's outcome (lane 0 is right after pass 1, lane i
-       * after pass i + 1 at the latest; ~3 passes in practice) and all 32 flips commit at once.  The draw index of a
-       * device = draws consumed + non-empty pools below it: lane l holds draw kbase + l and lanes fetch theirs by
-       * shuffle, so a pool running empty mid-window only shifts the fetch. */
+      uint32_t* const bits = e.inc();
+      /* the env's extra edges: lane j holds extra j */
+      uint32_t xe = 0;
+      if (lane < nx) xe = e.extra()[lane];
+      const int xu = (int)(xe & CYG_X_IDMASK), xv = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+      uint32_t xflags = __ballot_sync(CYG_FULL, (xe & CYG_X_BLOCKED) != 0); /* bit j: extra j is blocked */
+      uint32_t lto = 0, lti = 0; /* bit k: extra k has my source and a smaller target / my target and a smaller source */
+      int xpo = 0, xpi = 0;      /* units of xu's out list in front of xv / of xv's in list in front of xu */
+      for (int k = 0; k < nx; k++) { /* uniform */
+        const int ku = __shfl_sync(CYG_FULL, xu, k), kv = __shfl_sync(CYG_FULL, xv, k);
+        lto |= (ku == xu && kv < xv) ? (1u << k) : 0u;
+        lti |= (kv == xv && ku < xu) ? (1u << k) : 0u;
+      }
+      if (lane < nx) { xpo = e.units_before_out(xu, xv); xpi = e.units_before_in(xv, xu); }
+      /* draws of the site: lane l holds Philox block l = draws 4 l .. 4 l + 3 (a W <= 4 env lists at most 128 devices) */
+      uint32_t blk[4];
+      philox4x32_10(e.rng.env, e.rng.epoch, (uint32_t)site, (uint32_t)lane, e.rng.k0, e.rng.k1, blk);
+      auto draw = [&](uint32_t k) -> uint32_t {
+        const int from = (int)(k >> 2) & 31;
+        const uint32_t x0 = __shfl_sync(CYG_FULL, blk[0], from), x1 = __shfl_sync(CYG_FULL, blk[1], from);
+        const uint32_t x2 = __shfl_sync(CYG_FULL, blk[2], from), x3 = __shfl_sync(CYG_FULL, blk[3], from);
+        const uint32_t j = k & 3u;
+        return j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3;
+      };
       int pos = 0;
       uint32_t kbase = 0;
       while (pos < na) { /* uniform */
 #ifdef CYG_COUNT_ROUNDS
         e.dbg_rounds++;
 #endif
-        const int idx = pos + lg;
-        const bool valid = idx < na;
-        const int d = valid ? e.select_nth(act, idx) : 0;
-        typename E::Pool P0, P;
-        e.flip_windows(d, want, P0);
-        if (!valid) {
+        const int idx = pos + lane;
+        const bool valid0 = idx < na;
+        const int d = valid0 ? e.select_nth(act, idx) : 0;
+        const uint32_t di = e.dinfo(d), di1 = e.dinfo(d + 1);
+        const int a0 = (int)(di & 0xFFFFu), no = (int)(di >> 16), nt = (int)(di1 & 0xFFFFu) - a0;
+        const uint32_t bigm = __ballot_sync(CYG_FULL, valid0 && nt > 128);
+        if (bigm & 1u) {
+          /* ---- the device at `pos` has more than 128 units: alone, exactly, lane l on word l of its window ---- */
+          const int d0 = __shfl_sync(CYG_FULL, d, 0), ab = __shfl_sync(CYG_FULL, a0, 0);
+          const int nob = __shfl_sync(CYG_FULL, no, 0), ntb = __shfl_sync(CYG_FULL, nt, 0);
+          uint32_t hx = 0;
+          if (32 * lane < ntb) {
+            const int q0 = ab + 32 * lane;
+            hx = (funnel_r(bits[q0 >> 5], bits[(q0 >> 5) + 1], q0 & 31) ^ flipw) & lowmask0(ntb - 32 * lane);
+          }
+          uint32_t imo = 0, imi = 0;
+          for (int j = 0; j < nx; j++) {
+            const int ju = __shfl_sync(CYG_FULL, xu, j), jv = __shfl_sync(CYG_FULL, xv, j);
+            const bool memb = (((xflags >> j) & 1u) != 0) == want;
+            imo |= (memb && ju == d0) ? (1u << j) : 0u;
+            imi |= (memb && jv == d0) ? (1u << j) : 0u;
+          }
+          const int pc = popc(hx);
+          const int tot = (int)__reduce_add_sync(CYG_FULL, (uint32_t)pc) + popc(imo) + popc(imi);
+          if (tot > 0) { /* uniform */
+            const int r = (int)below(draw(kbase), (uint32_t)tot);
+            int sel = -1, passed = 0;
+            for (int j = 0; j < nx; j++) { /* uniform: imo / imi are */
+              const bool bo = (imo >> j) & 1u, bi = (imi >> j) & 1u;
+              if (!(bo | bi)) continue;
+              const int P = bo ? __shfl_sync(CYG_FULL, xpo, j) : nob + __shfl_sync(CYG_FULL, xpi, j);
+              const int cb = (int)__reduce_add_sync(CYG_FULL, (uint32_t)popc(hx & lowmask0(P - 32 * lane)));
+              const uint32_t lo_j = __shfl_sync(CYG_FULL, lto, j), li_j = __shfl_sync(CYG_FULL, lti, j);
+              const int mi = cb + (bo ? popc(imo & lo_j) : popc(imo) + popc(imi & li_j));
+              if (mi == r) sel = j;
+              passed += mi < r ? 1 : 0;
+            }
+            if (sel >= 0) {
+              if (lane == 0) { if (want) e.extra()[sel] &= ~CYG_X_BLOCKED; else e.extra()[sel] |= CYG_X_BLOCKED; }
+              xflags = want ? (xflags & ~(1u << sel)) : (xflags | (1u << sel));
+            } else {
+              const int rr = r - passed;
+              int incl = pc;
 #pragma unroll
-          for (int q = 0; q < W; q++) { P0.xo[q] = 0; P0.xi[q] = 0; }
+              for (int dd = 1; dd < 32; dd <<= 1) {
+                const int y = __shfl_up_sync(CYG_FULL, incl, dd);
+                if (lane >= dd) incl += y;
+              }
+              const int excl = incl - pc;
+              const bool mine = rr >= excl && rr < incl;
+              int q = mine ? ab + 32 * lane + select_in_word(hx, rr - excl) : 0;
+              const uint32_t mm = __ballot_sync(CYG_FULL, mine);
+              q = __shfl_sync(CYG_FULL, q, __ffs((int)mm) - 1);
+              if (lane == 0) e.set_pair_blocked(q, !want);
+            }
+            cnt++; kbase++;
+          }
+          pos += 1;
+          __threadfence_block();
+          __syncwarp();
+          continue;
         }
-        P = P0;
-        const uint32_t xd = draw_at(e.rng, site, kbase + (uint32_t)lg);
-        int eid = -2, other = -1;
+        /* ---- a window of lanes: the listed devices up to the next big one ---- */
+        const int c = bigm ? (__ffs((int)bigm) - 1) : 32;
+        const bool valid = valid0 && lane < c;
+        const int nwin = min(c, na - pos);
+        uint32_t x0[4] = {0u, 0u, 0u, 0u}; /* the pool window of my device at the start of the window of lanes (up to 128 units) */
+        if (valid) {
+          const int wa = a0 >> 5, sh = a0 & 31;
+          uint32_t lo = bits[wa];
+#pragma unroll
+          for (int i = 0; i < 4; i++) { /* whatever follows the bitset in shared memory is readable and masked off */
+            const uint32_t hi = bits[wa + i + 1];
+            x0[i] = (funnel_r(lo, hi, sh) ^ flipw) & lowmask0(nt - 32 * i);
+            lo = hi;
+          }
+        }
+        uint32_t imo0 = 0, imi0 = 0; /* bit j: extra j is in the pool of my out list / in list at the start of the window */
+        for (int j = 0; j < nx; j++) {
+          const int ju = __shfl_sync(CYG_FULL, xu, j), jv = __shfl_sync(CYG_FULL, xv, j);
+          const bool memb = valid && ((((xflags >> j) & 1u) != 0) == want);
+          imo0 |= (memb && ju == d) ? (1u << j) : 0u;
+          imi0 |= (memb && jv == d) ? (1u << j) : 0u;
+        }
+        const uint32_t xd = draw(kbase + (uint32_t)lane);
+        uint32_t x[4] = {x0[0], x0[1], x0[2], x0[3]}, imo = imo0, imi = imi0;
+        int key = -2;  /* the pick: run start unit of a base pair, 0x10000 | j for extra edge j, -1 none */
+        int tw = 0, mrun = 1;
         uint32_t nem = 0;
         bool had_att = false; /* some lane's pool of the current pass had edges removed (uniform) */
         for (;;) {
 #ifdef CYG_COUNT_ROUNDS
           e.dbg_rounds += 0x10000;
 #endif
-          const int total = e.flip_weigh(P);
-          const bool nonempty = total > 0;
-          nem = __ballot_sync(gm, nonempty);
-          const uint32_t x = __shfl_sync(gm, xd, popc(nem & lanes_below(lg)));
-          int neid = -1, nother = -1;
-          if (nonempty) neid = e.flip_pick(P, (int)below(x, (uint32_t)total), nother);
-          const bool changed = __any_sync(gm, neid != eid);
-          eid = neid; other = nother;
+          const int c0 = popc(x[0]), c1 = popc(x[1]), c2 = popc(x[2]), c3 = popc(x[3]);
+          const int tot = c0 + c1 + c2 + c3 + popc(imo) + popc(imi);
+          nem = __ballot_sync(CYG_FULL, tot > 0);
+          const uint32_t xr = __shfl_sync(CYG_FULL, xd, popc(nem & lanes_below(lane)));
+          int nkey = -1, other = -1, ntw = 0, nm = 1;
+          const int r = tot > 0 ? (int)below(xr, (uint32_t)tot) : 0;
+          int sel = -1, passed = 0;
+          for (int j = 0; j < nx; j++) { /* uniform: does r land on an extra edge, how many extras sit in front of it */
+            const int po_j = __shfl_sync(CYG_FULL, xpo, j), pi_j = __shfl_sync(CYG_FULL, xpi, j);
+            const uint32_t lo_j = __shfl_sync(CYG_FULL, lto, j), li_j = __shfl_sync(CYG_FULL, lti, j);
+            const int ju = __shfl_sync(CYG_FULL, xu, j), jv = __shfl_sync(CYG_FULL, xv, j);
+            const bool bo = (imo >> j) & 1u, bi = (imi >> j) & 1u;
+            if (bo | bi) {
+              const int P = bo ? po_j : no + pi_j;
+              const int mi = popc(x[0] & lowmask0(P)) + popc(x[1] & lowmask0(P - 32)) + popc(x[2] & lowmask0(P - 64)) + popc(x[3] & lowmask0(P - 96)) +
+                             (bo ? popc(imo & lo_j) : popc(imo) + popc(imi & li_j));
+              if (mi == r) { sel = j; other = bo ? jv : ju; }
+              passed += mi < r ? 1 : 0;
+            }
+          }
+          if (tot > 0) {
+            if (sel >= 0) {
+              nkey = 0x10000 | sel;
+            } else {
+              const int rr = r - passed; /* word holding unit rr of the window, branch-free */
+              const bool g1 = rr >= c0, g2 = rr >= c0 + c1, g3 = rr >= c0 + c1 + c2;
+              const uint32_t xw = g3 ? x[3] : g2 ? x[2] : g1 ? x[1] : x[0];
+              const int base = g3 ? c0 + c1 + c2 : g2 ? c0 + c1 : g1 ? c0 : 0;
+              const int q = a0 + 32 * ((g1 ? 1 : 0) + (g2 ? 1 : 0) + (g3 ? 1 : 0)) + select_in_word(xw, rr - base);
+              const uint32_t ui = e.unit(q);
+              nkey = q - unit_off(ui);
+              ntw = unit_twin(ui); nm = unit_m(ui); other = unit_other(ui);
+            }
+          }
+          const bool changed = __any_sync(CYG_FULL, nkey != key);
+          key = nkey; tw = ntw; mrun = nm;
           if (!changed) break;
           /* victim of this lane's pick: the lane (above this one) whose device is the far endpoint */
           int vl = -1;
-          if (nonempty) {
+          if (nkey >= 0) {
             const int ow = other >> 5;
             const uint32_t ob = 1u << (other & 31);
             uint32_t in = 0;
@@ -267,35 +304,62 @@ struct Coop {
               rank += popc(act[w] & (w < ow ? 0xFFFFFFFFu : (ob - 1u) & eqmask(w, ow)));
             }
             const int l = rank - pos;
-            if (in != 0 && l > lg && l < 32) vl = l;
+            if (in != 0 && l > lane && l < nwin) vl = l;
           }
-          const uint32_t bv = __ballot_sync(gm, vl >= 0);
+          const uint32_t bv = __ballot_sync(CYG_FULL, vl >= 0);
           if (bv == 0 && !had_att) break; /* nobody is touched and the picks came from untouched pools: final */
           uint32_t att = bv;
 #pragma unroll
           for (int k = 0; k < 5; k++) {
-            const uint32_t bk = __ballot_sync(gm, vl >= 0 && ((vl >> k) & 1));
-            att &= ((lg >> k) & 1) ? bk : ~bk;
+            const uint32_t bk = __ballot_sync(CYG_FULL, vl >= 0 && ((vl >> k) & 1));
+            att &= ((lane >> k) & 1) ? bk : ~bk;
           }
           had_att = bv != 0;
-          P = P0;
-          while (__any_sync(gm, att != 0)) {
-            const int from = att ? (__ffs((int)att) - 1) : lg;
-            const int ej = __shfl_sync(gm, eid, from);
-            if (att) { e.pool_remove(P, ej); att &= att - 1u; }
+          x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2]; x[3] = x0[3]; imo = imo0; imi = imi0;
+          while (__any_sync(CYG_FULL, att != 0)) {
+            const int from = att ? (__ffs((int)att) - 1) : lane;
+            const int kj = __shfl_sync(CYG_FULL, key, from);
+            const int tj = __shfl_sync(CYG_FULL, tw, from), mj = __shfl_sync(CYG_FULL, mrun, from);
+            if (att) {
+              if (kj & 0x10000) { imo &= ~(1u << (kj & 31)); imi &= ~(1u << (kj & 31)); }
+              else { /* the run [tj, tj + mj) of my window: at most one word boundary */
+                const int pp = tj - a0, sh = pp & 31;
+                const uint32_t m0 = lowmask(mj) << sh, m1 = sh + mj > 32 ? lowmask(mj) >> (32 - sh) : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; i++) x[i] &= ~((m0 & eqmask(i, pp >> 5)) | (m1 & eqmask(i, (pp >> 5) + 1)));
+              }
+              att &= att - 1u;
+            }
           }
         }
-        if (eid >= 0) set_blocked_atomic(e, eid, !want);
+        /* commit: every lane's pick is final */
+        const bool pick_x = key >= 0 && (key & 0x10000) != 0, pick_b = key >= 0 && !pick_x;
+        if (pick_b) {
+          for (int k = 0; k < mrun; k++) {
+            const int q0 = key + k, q1 = tw + k;
+            if (!want) { atomicOr(&bits[q0 >> 5], 1u << (q0 & 31)); atomicOr(&bits[q1 >> 5], 1u << (q1 & 31)); }
+            else { atomicAnd(&bits[q0 >> 5], ~(1u << (q0 & 31))); atomicAnd(&bits[q1 >> 5], ~(1u << (q1 & 31))); }
+          }
+        }
+        if (pick_x) {
+          uint32_t* xp = e.extra() + (key & 0xFFFF);
+          if (!want) atomicOr(xp, CYG_X_BLOCKED); else atomicAnd(xp, ~CYG_X_BLOCKED);
+        }
+        const uint32_t xpicked = __reduce_or_sync(CYG_FULL, pick_x ? (1u << (key & 31)) : 0u);
+        xflags = want ? (xflags & ~xpicked) : (xflags | xpicked);
+        const uint32_t nbase = (uint32_t)popc(__ballot_sync(CYG_FULL, pick_b));
+        if (lane == 0) { if (want) e.nblk() -= nbase; else e.nblk() += nbase; }
         const uint32_t done = (uint32_t)popc(nem);
-        cnt += done; kbase += done; pos += 32;
-        __syncwarp(gm);
+        cnt += done; kbase += done; pos += nwin;
+        __threadfence_block();
+        __syncwarp();
       }
     }
-    if (lg == 0 && cnt) {
+    if (lane == 0 && cnt) {
       e.scal(want ? CYG_S_EADD : CYG_S_EBLK) += cnt;
       dirty = true;
     }
-    __syncwarp(gm);
+    __syncwarp();
   }
 
   /* attacker action 1, exploit + lateral movement (volt:1126-1185), one warp per env: the 32 lanes take 32
@@ -310,10 +374,11 @@ struct Coop {
     for (int w = 0; w < W; w++) { src[w] = e.pl(P_COMP, w) | e.pl(P_OWNED, w); ns += popc(src[w]); }
     const bool has_blk = e.any_blocked();
     const int nx = e.n_extra();
+    /* the env's extra (hub-star) edges (every env after randomize_compromise_and_ownership moved the owned set): lane j
+     * holds extra j; a source's unblocked extra out-neighbours join its candidates as an id-space bit row */
+    uint32_t xe = 0;
+    if (nx <= 32 && lane < nx) xe = e.extra()[lane];
     __syncwarp();
-    /* envs with extra (hub-star) edges (nx > 0: every env after randomize_compromise_and_ownership moved the owned
-     * set) take attack_source's general form, which materialises the unblocked row of a source from the base bit row,
-     * the blocked pairs and the extra list; nx is per env, so the lanes of the warp stay on one form */
     uint32_t logs_add = 0, zk = 0;
     for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
       int raw = a.ex(xi);
@@ -329,12 +394,23 @@ struct Coop {
         const int idx = pos + lane;
         const bool valid = idx < ns;
         const int s = valid ? e.select_nth(src, idx) : 0;
-        uint32_t comp[W];
+        uint32_t comp[W], xrow[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) comp[w] = e.pl(P_COMP, w);
+        for (int w = 0; w < W; w++) { comp[w] = e.pl(P_COMP, w); xrow[w] = 0; }
+        if (nx > 32) {
+          if (valid) e.extra_out_row(s, false, xrow);
+        } else {
+          for (int j = 0; j < nx; j++) { /* uniform */
+            const uint32_t jw = __shfl_sync(CYG_FULL, xe, j);
+            const int jv = (int)((jw >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+            const bool mine = valid && (int)(jw & CYG_X_IDMASK) == s && !(jw & CYG_X_BLOCKED);
+#pragma unroll
+            for (int w = 0; w < W; w++) xrow[w] |= mine ? ((1u << (jv & 31)) & eqmask(w, jv >> 5)) : 0u;
+          }
+        }
         int cnt = 0, v = -1;
         bool rule3 = false;
-        if (valid) v = e.attack_source(s, comp, kv, has_blk, nx, cnt, rule3);
+        if (valid) v = e.attack_source(s, comp, kv, has_blk, nx > 0 ? xrow : (const uint32_t*)nullptr, cnt, rule3);
         const uint32_t same = __match_any_sync(CYG_FULL, v >= 0 ? v : (0x1000 + lane));
         const bool conflict = valid && rule3 && (same & lanes_below(lane)) != 0;
         const uint32_t conf = __ballot_sync(CYG_FULL, conflict);
@@ -356,10 +432,7 @@ struct Coop {
     __syncwarp();
   }
 
-  static __device__ __forceinline__ bool is_heavy(int mode, int atype) {
-    if (mode == CYG_MODE_ATTACKER) return atype == 1;
-    return atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9;
-  }
+  static __device__ __forceinline__ bool is_heavy(E& e, int mode, int atype) { return e.deferred_type(mode, atype); }
 
   /* the deposit-type heavy defender actions (clean / revert / upgrade) of a plain set-form step, one warp per env;
    * lane 0 owns cost / dirty / scalars */

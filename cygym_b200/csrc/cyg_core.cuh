@@ -6,9 +6,12 @@
  *
  *   [0, 16)                          the 16 scalars of include/cygym_b200.h (CYG_S_*)
  *   [16 + p*W, 16 + (p+1)*W)         bit-plane p, W = ceil(M/32) words, bit d = device d
- *   [off_blocked, off_blocked + EW)  blocked-edge bitset over base CSR edge ids (out-list order)
- *   [off_blocked_in, ... + EW)       the same bits permuted into in-list order, so that the in-edges of a
- *                                    device are a contiguous bit range too (block / unblock, volt:485-511)
+ *   [off_inc, off_inc + UW)          blocked-edge bitset in INCIDENCE-UNIT order: device d owns the contiguous bit
+ *                                    range [ip[d], ip[d+1]) -- one bit per out-edge (ascending neighbour id, a pair of
+ *                                    multiplicity m as m adjacent bits: the order of _outnbrs, volt:456-473), then one
+ *                                    per in-edge (ascending source id).  A blocked pair has all its 2m bits set, so the
+ *                                    pool of block / unblock (volt:485-511) is ONE window, its weight a popcount and
+ *                                    the hop count of the lateral-movement scan (volt:1148-1185) a popcount as well
  *   [off_aux]                        number of blocked base pairs (derived; spares the scans a walk over the bitset)
  * (the rarely used per-env extra attacker hub-star edges and the per-device checkpoint words
  * live in side arrays in global memory and are touched only by the actions that need them)
@@ -76,34 +79,32 @@ enum {
  * constant-bank operand, and reads the hot prefix of the blob [0, hot_words) from its shared-memory copy. */
 struct Net {
   cyg_config cfg;
-  int M, W, E, EW, NP, S, ncby, off_blocked, off_blocked_in, off_aux;
+  int M, W, E, EW, NP, S, ncby, off_inc, off_aux;
+  int U2, UW;                 /* incidence units (2 x sum of multiplicities) and the words of their bitset */
   int Wm;                     /* ceil(M/32): words per device mask in the C-ABI arrays (== W unless the planes are padded) */
   double inv_M;               /* 1.0 / M */
   uint32_t hot_words;         /* prefix of the blob that a CTA stages in shared memory */
   /* hot tables */
   uint32_t o_adj;             /* [M][W] out-neighbour bit rows (unique pairs; _outnbrs, volt:456-473) */
   uint32_t o_dc, o_server, o_reach, o_valid; /* [W] masks over devices */
-  uint32_t o_rowmulti;        /* [W] device has an out-pair with multiplicity > 1 */
-  uint32_t o_incmulti;        /* [W] device has an incident (out or in) pair with multiplicity > 1 */
   uint32_t o_napps;           /* [8][W] bit-planes of len(device.apps) */
   uint32_t o_vuln;            /* [X][W] device has an app vulnerability in exploits[e].target */
-  uint32_t o_row_ptr;         /* [M+1] int32 */
-  uint32_t o_col;             /* [E] uint16 */
-  uint32_t o_in_ptr;          /* [M+1] int32 */
-  uint32_t o_in_eid;          /* [E] uint16: base edge id of the j-th in-edge (ascending source) */
-  uint32_t o_out2in;          /* [E] uint16: inverse of in_eid */
-  uint32_t o_in_src;          /* [E] uint16: source device of the j-th in-edge */
+  uint32_t o_dinfo;           /* [M+1] ip[d] | out-units(d) << 16: device d owns units [ip[d], ip[d+1]) */
+  uint32_t o_unit;            /* [U2] twin run start | far endpoint << 16 | (m - 1) << 28 | offset in own run << 30 */
+  uint32_t o_omulti;          /* [M] multi-edge runs of the out list: pair rank | (m-1) << 8, two 10-bit entries (0xFF = none);
+                                 bit 31 = more than two (walk the units) */
   uint32_t o_static;          /* [M] CYG_ST_* */
-  uint32_t o_emlo, o_emhi;    /* [EW] bit e: (mult(e)-1) & 1 / & 2, out-list order */
-  uint32_t o_eimlo, o_eimhi;  /* the same in in-list order */
-  uint32_t o_dmulti;          /* [M][2] multi-edges of a device's out / in list: off1 | (m1-1)<<8 | off2<<10 | (m2-1)<<18, offsets
-                                 relative to the list start (0xFF = none); bit 31 = more than two (generic path) */
   /* cold tables (global memory only) */
-  uint32_t o_mlo, o_mhi;      /* [M][W] bit v of row u: (mult(u,v)-1) & 1 / & 2 */
-  uint32_t o_adjT, o_mloT, o_mhiT; /* [M][W] in-neighbour rows and transposed multiplicity bits */
+  uint32_t o_pair2unit;       /* [E] first out-unit of base pair e (canonical blocked[] <-> units) */
   uint32_t o_os, o_ver;       /* [M] float: os_to_float(d.OS), float(d.version) */
   const uint32_t* blob;       /* the blob in global (device) / host memory */
 };
+
+/* fields of a unit entry (Net::o_unit) */
+CYG_HD int unit_twin(uint32_t u) { return (int)(u & 0xFFFFu); }
+CYG_HD int unit_other(uint32_t u) { return (int)((u >> 16) & 0xFFFu); }
+CYG_HD int unit_m(uint32_t u) { return (int)((u >> 28) & 3u) + 1; }
+CYG_HD int unit_off(uint32_t u) { return (int)(u >> 30); }
 
 CYG_HD int popc(uint32_t x) {
 #ifdef __CUDA_ARCH__
@@ -193,32 +194,28 @@ CYG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 
 struct Rng { uint32_t k0, k1, env, epoch; };
 
-/* sequential reader of one site's draws k = 0, 1, 2, ... inside the current epoch */
+/* sequential reader of one site's draws k = 0, 1, 2, ... inside the current epoch.  `blk` = index of the Philox block
+ * held in b0..b3 (0xFFFFFFFF: none yet): next() computes a block only when the draw index leaves the held one, and
+ * load() fetches block 0 ahead of time so that several streams' Philox rounds overlap instead of chaining. */
 struct Stream {
-  uint32_t k, b0, b1, b2, b3;
+  uint32_t k, blk, b0, b1, b2, b3;
   int site;
-  CYG_HD explicit Stream(int s) : k(0), b0(0), b1(0), b2(0), b3(0), site(s) {}
+  CYG_HD explicit Stream(int s) : k(0), blk(0xFFFFFFFFu), b0(0), b1(0), b2(0), b3(0), site(s) {}
+  CYG_HD void fetch(const Rng& r, uint32_t block) {
+    uint32_t o[4];
+    philox4x32_10(r.env, r.epoch, (uint32_t)site, block, r.k0, r.k1, o);
+    b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
+    blk = block;
+  }
+  CYG_HD void load(const Rng& r) { fetch(r, k >> 2); }
   CYG_HD uint32_t next(const Rng& r) {
-    if ((k & 3u) == 0u) {
-      uint32_t o[4];
-      philox4x32_10(r.env, r.epoch, (uint32_t)site, k >> 2, r.k0, r.k1, o);
-      b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
-    }
+    if ((k >> 2) != blk) fetch(r, k >> 2);
     uint32_t j = k & 3u;
     k++;
     return j == 0 ? b0 : j == 1 ? b1 : j == 2 ? b2 : b3;
   }
   /* continue at draw index k + n (n draws are skipped unread) */
-  CYG_HD void skip(const Rng& r, uint32_t nskip) {
-    if (nskip == 0) return;
-    uint32_t old_blk = (k + 3u) >> 2; /* first block not loaded yet */
-    k += nskip;
-    if ((k & 3u) != 0u && (k >> 2) >= old_blk) {
-      uint32_t o[4];
-      philox4x32_10(r.env, r.epoch, (uint32_t)site, k >> 2, r.k0, r.k1, o);
-      b0 = o[0]; b1 = o[1]; b2 = o[2]; b3 = o[3];
-    }
-  }
+  CYG_HD void skip(const Rng& r, uint32_t nskip) { (void)r; k += nskip; }
 };
 
 /* ---- per-env view over an internal record ---------------------------------
@@ -272,13 +269,10 @@ struct Env {
 #endif
     return th + i;
   }
-  CYG_HD int row_ptr(int i) const { return (int)T(n->o_row_ptr + i); }
-  CYG_HD int in_ptr(int i) const { return (int)T(n->o_in_ptr + i); }
-  CYG_HD int u16(uint32_t off, int i) const { return (int)((T(off + (i >> 1)) >> ((i & 1) * 16)) & 0xFFFFu); }
-  CYG_HD int col(int e) const { return u16(n->o_col, e); }
-  CYG_HD int in_eid(int j) const { return u16(n->o_in_eid, j); }
-  CYG_HD int out2in(int e) const { return u16(n->o_out2in, e); }
-  CYG_HD int in_src(int j) const { return u16(n->o_in_src, j); }
+  CYG_HD uint32_t dinfo(int d) const { return T(n->o_dinfo + d); }
+  CYG_HD int ip(int d) const { return (int)(dinfo(d) & 0xFFFFu); }      /* first unit of device d */
+  CYG_HD int nout(int d) const { return (int)(dinfo(d) >> 16); }        /* its out-units; the in-units follow */
+  CYG_HD uint32_t unit(int q) const { return T(n->o_unit + q); }
   CYG_HD uint32_t adj(int u, int w) const { return T(n->o_adj + u * W + w); }
   CYG_HD uint32_t m_dc(int w) const { return T(n->o_dc + w); }
   CYG_HD uint32_t m_server(int w) const { return T(n->o_server + w); }
@@ -289,8 +283,8 @@ struct Env {
   CYG_HD uint32_t dev_static(int d) const { return T(n->o_static + d); }
   CYG_HD uint32_t& scal(int i) { return R(i); }
   CYG_HD uint32_t& pl(int p, int w) { return R(CYG_REC_PLANES + p * W + w); }
-  CYG_HD uint32_t* blocked() { return &R(n->off_blocked); }
-  CYG_HD uint32_t* blocked_in() { return &R(n->off_blocked_in); }
+  CYG_HD uint32_t* inc() { return &R(n->off_inc); } /* blocked bits in incidence-unit order */
+  CYG_HD bool ubit(int q) { return (inc()[q >> 5] >> (q & 31)) & 1u; }
   CYG_HD uint32_t& nblk() { return R(n->off_aux); } /* number of blocked base pairs */
   CYG_HD uint32_t* extra() { return xtra; }
   CYG_HD int n_extra() { return (int)(R(CYG_S_PREV_X) >> 16); }
@@ -392,7 +386,7 @@ struct Env {
     return wsel * 32 + select_in_word(xw, r - base);
   }
 
-  /* ---- topology: base bit rows + blocked bitset + extra edges ---------------- */
+  /* ---- topology: base bit rows + blocked unit bitset + extra edges ---------------- */
   CYG_HD bool any_blocked() {
     if (nblk() != 0) return true;
     uint32_t o = 0;
@@ -401,81 +395,71 @@ struct Env {
     for (int j = 0; j < nx; j++) o |= x[j] & CYG_X_BLOCKED;
     return o != 0;
   }
-  /* out[] = out-neighbours of u whose edge has blocked-state == want_blocked (unique ids; base + extra) */
-  CYG_HD void out_row(int u, bool has_blk, bool want_blocked, uint32_t* out) {
-    uint32_t bl[W];
-    for (int w = 0; w < W; w++) bl[w] = 0;
-    if (has_blk) {
-      const uint32_t* b = blocked();
-      int a = row_ptr(u), z = row_ptr(u + 1);
-      for (int wi = a >> 5; wi <= (z - 1) >> 5 && a < z; wi++) {
-        uint32_t x = b[wi];
-        if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-        if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-        while (x) {
-          int e = wi * 32 + ctz(x);
-          x &= x - 1;
-          int v = col(e);
-          for (int w = 0; w < W; w++) bl[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
-        }
+  /* units of [a, a + len) whose blocked bit XOR flip is set (flipw = 0: blocked ones, ~0: unblocked ones) */
+  CYG_HD int range_count(int a, int len, uint32_t flipw) {
+    if (len <= 0) return 0;
+    const uint32_t* b = inc();
+    const int z = a + len, wa = a >> 5, wz = (z - 1) >> 5;
+    int c = 0;
+    for (int wi = wa; wi <= wz; wi++) {
+      uint32_t x = b[wi] ^ flipw;
+      if (wi == wa) x &= ~lowmask(a & 31);
+      if (wi == wz) x &= lowmask(((z - 1) & 31) + 1);
+      c += popc(x);
+    }
+    return c;
+  }
+  /* the r-th (0-based) such unit, as an absolute unit index; r < range_count */
+  CYG_HD int range_select(int a, int len, uint32_t flipw, int r) {
+    const uint32_t* b = inc();
+    const int z = a + len, wa = a >> 5, wz = (z - 1) >> 5;
+    for (int wi = wa; wi <= wz; wi++) {
+      uint32_t x = b[wi] ^ flipw;
+      if (wi == wa) x &= ~lowmask(a & 31);
+      if (wi == wz) x &= lowmask(((z - 1) & 31) + 1);
+      const int c = popc(x);
+      if (r < c) return wi * 32 + select_in_word(x, r);
+      r -= c;
+    }
+    return -1;
+  }
+  /* extra units the multi-edge runs add before pair rank rk of u's out list */
+  CYG_HD int multi_before(int u, int rk) {
+    const uint32_t dm = T(n->o_omulti + u);
+    int c = 0;
+    if (!(dm >> 31)) {
+      for (int k = 0; k < 2; k++) {
+        const int off = (int)((dm >> (10 * k)) & 0xFFu);
+        c += (off != 0xFF && off < rk) ? (int)((dm >> (8 + 10 * k)) & 3u) : 0;
       }
+      return c;
     }
-    for (int w = 0; w < W; w++) {
-      uint32_t r = adj(u, w);
-      out[w] = want_blocked ? (r & bl[w]) : (r & ~bl[w]);
-    }
-    int nx = n_extra();
-    const uint32_t* x = extra();
-    for (int j = 0; j < nx; j++) {
-      uint32_t xe = x[j];
-      if ((int)(xe & CYG_X_IDMASK) != u) continue;
-      if (((xe & CYG_X_BLOCKED) != 0) != want_blocked) continue;
-      int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
-      for (int w = 0; w < W; w++) out[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
-    }
+    int q = ip(u);
+    const int a = q;
+    for (int pairs = 0; pairs < rk; pairs++) q += unit_m(unit(q)); /* more than two runs: walk the list, one run per pair */
+    return (q - a) - rk;
   }
-  /* in[] = in-neighbours (sources) of u whose edge has blocked-state == want_blocked */
-  CYG_HD void in_row(int u, bool has_blk, bool want_blocked, uint32_t* in) {
-    uint32_t bl[W];
-    for (int w = 0; w < W; w++) bl[w] = 0;
-    if (has_blk) {
-      const uint32_t* b = blocked();
-      int a = in_ptr(u), z = in_ptr(u + 1);
-      int j = a;
-      for (int w = 0; w < W; w++) { /* the j-th in-edge belongs to the j-th set bit of adjT[u] */
-        uint32_t r = tc[n->o_adjT + u * W + w];
-        while (r) {
-          int s = ctz(r);
-          r &= r - 1;
-          int e = in_eid(j++);
-          if ((b[e >> 5] >> (e & 31)) & 1u) bl[w] |= 1u << s;
-        }
-      }
-      (void)z;
-    }
+  CYG_HD int rank_in_row(int u, int v) { /* out-pairs of u with a neighbour id below v */
+    int rk = 0;
     for (int w = 0; w < W; w++) {
-      uint32_t r = tc[n->o_adjT + u * W + w];
-      in[w] = want_blocked ? (r & bl[w]) : (r & ~bl[w]);
+      const uint32_t r = adj(u, w);
+      rk += popc(r & (w < (v >> 5) ? 0xFFFFFFFFu : (lowmask(v & 31) & eqmask(w, v >> 5))));
     }
-    int nx = n_extra();
-    const uint32_t* x = extra();
-    for (int j = 0; j < nx; j++) {
-      uint32_t xe = x[j];
-      if ((int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK) != u) continue;
-      if (((xe & CYG_X_BLOCKED) != 0) != want_blocked) continue;
-      int s = (int)(xe & CYG_X_IDMASK);
-      for (int w = 0; w < W; w++) in[w] |= (1u << (s & 31)) & eqmask(w, s >> 5);
-    }
+    return rk;
   }
-  CYG_HD int base_eid(int u, int v) { /* edge id of the base pair (u, v); the bit must be set in adj[u] */
-    int e = row_ptr(u);
-    for (int w = 0; w < W; w++) {
-      uint32_t r = adj(u, w);
-      if (w < (v >> 5)) e += popc(r);
-      else if (w == (v >> 5)) e += popc(r & lowmask(v & 31));
-    }
-    return e;
+  /* out-units of u that precede neighbour id v (v itself need not be a neighbour) */
+  CYG_HD int units_before_out(int u, int v) {
+    const int rk = rank_in_row(u, v);
+    return rk + multi_before(u, rk);
   }
+  /* in-units of v whose source id is below u: a walk over the in list (only the extra-edge paths need it) */
+  CYG_HD int units_before_in(int v, int u) {
+    const int a = ip(v) + nout(v), z = ip(v + 1);
+    int c = 0;
+    for (int q = a; q < z; q++) c += unit_other(unit(q)) < u ? 1 : 0;
+    return c;
+  }
+  CYG_HD int unit_of(int u, int v) { return ip(u) + units_before_out(u, v); } /* first out-unit of base pair (u, v) */
   CYG_HD bool has_edge(int u, int v) { /* g.get_eid(u, v) != -1 (CyberDefenseEnv.py:752-770) */
     if ((adj(u, (v >> 5)) >> (v & 31)) & 1u) return true;
     int nx = n_extra();
@@ -484,64 +468,59 @@ struct Env {
     for (int j = 0; j < nx; j++) if ((x[j] & 0xFFFFFFu) == key) return true;
     return false;
   }
-  CYG_HD void set_base_blocked(int e, bool b) { /* both orders of the bitset */
-    int j = out2in(e);
-    const uint32_t was = (blocked()[e >> 5] >> (e & 31)) & 1u;
-    if (b) { blocked()[e >> 5] |= 1u << (e & 31); blocked_in()[j >> 5] |= 1u << (j & 31); nblk() += 1u - was; }
-    else { blocked()[e >> 5] &= ~(1u << (e & 31)); blocked_in()[j >> 5] &= ~(1u << (j & 31)); nblk() -= was; }
-  }
-  /* flip the blocked flag of edge (u, v) */
-  CYG_HD void set_edge_blocked(int u, int v, bool b) {
-    if ((adj(u, (v >> 5)) >> (v & 31)) & 1u) {
-      set_base_blocked(base_eid(u, v), b);
-      return;
+  /* block / unblock the base pair that unit q belongs to: all its units on both sides */
+  CYG_HD void set_pair_blocked(int q, bool b) {
+    const uint32_t ui = unit(q);
+    const int s = q - unit_off(ui), t = unit_twin(ui), m = unit_m(ui);
+    uint32_t* bits = inc();
+    const uint32_t was = (bits[s >> 5] >> (s & 31)) & 1u;
+    for (int k = 0; k < m; k++) {
+      const int q0 = s + k, q1 = t + k;
+      if (b) { bits[q0 >> 5] |= 1u << (q0 & 31); bits[q1 >> 5] |= 1u << (q1 & 31); }
+      else { bits[q0 >> 5] &= ~(1u << (q0 & 31)); bits[q1 >> 5] &= ~(1u << (q1 & 31)); }
     }
-    int nx = n_extra();
-    uint32_t* x = extra();
-    uint32_t key = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
-    for (int j = 0; j < nx; j++)
-      if ((x[j] & 0xFFFFFFu) == key) { if (b) x[j] |= CYG_X_BLOCKED; else x[j] &= ~CYG_X_BLOCKED; return; }
+    if (b) nblk() += 1u - was; else nblk() -= was;
   }
   /* _rebuild_graph_cache (volt:456-483) forgets every block (:476) */
   CYG_HD void rebuild_cache() {
-    uint32_t *b = blocked(), *bi = blocked_in();
-    for (int i = 0; i < n->EW; i++) { b[i] = 0; bi[i] = 0; }
+    uint32_t* b = inc();
+    for (int i = 0; i < n->UW; i++) b[i] = 0;
     nblk() = 0;
     int nx = n_extra();
     uint32_t* x = extra();
     for (int j = 0; j < nx; j++) x[j] &= ~CYG_X_BLOCKED;
   }
-  /* multiplicity-weighted size of row r[] restricted to ids < lim (lim = 32*W: all) */
-  CYG_HD int weight_below(const uint32_t* r, const uint32_t* lo, const uint32_t* hi, bool multi, int lim) {
-    int c = 0;
-    for (int w = 0; w < W; w++) {
-      uint32_t m = r[w];
-      int d = lim - 32 * w;
-      if (d <= 0) m = 0; else if (d < 32) m &= lowmask(d);
-      c += popc(m);
-      if (multi) c += popc(m & lo[w]) + 2 * popc(m & hi[w]);
+  /* id-space rows of the extra edges of device u: xo[] = targets of its extra out-edges whose blocked flag == want_blocked */
+  CYG_HD void extra_out_row(int u, bool want_blocked, uint32_t* xo) {
+    for (int w = 0; w < W; w++) xo[w] = 0;
+    int nx = n_extra();
+    const uint32_t* x = extra();
+    for (int j = 0; j < nx; j++) {
+      const uint32_t xe = x[j];
+      if ((int)(xe & CYG_X_IDMASK) != u) continue;
+      if (((xe & CYG_X_BLOCKED) != 0) != want_blocked) continue;
+      const int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+      for (int w = 0; w < W; w++) xo[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
     }
-    return c;
   }
-  /* id holding the r-th unit of weight of row r[] */
-  CYG_HD int weighted_select(const uint32_t* r, const uint32_t* lo, const uint32_t* hi, bool multi, int rank) {
-    for (int w = 0; w < W; w++) {
-      uint32_t m = r[w];
-      if (!multi) {
-        int c = popc(m);
-        if (rank < c) return w * 32 + select_in_word(m, rank);
-        rank -= c;
-      } else {
-        while (m) {
-          int s = ctz(m);
-          m &= m - 1;
-          int wt = 1 + (int)((lo[w] >> s) & 1u) + 2 * (int)((hi[w] >> s) & 1u);
-          if (rank < wt) return w * 32 + s;
-          rank -= wt;
-        }
+  /* ids of the base out-neighbours of u whose pair is blocked */
+  CYG_HD void blocked_out_ids(int u, uint32_t* bl) {
+    for (int w = 0; w < W; w++) bl[w] = 0;
+    const int a = ip(u), no = nout(u);
+    if (no <= 0) return;
+    const uint32_t* b = inc();
+    const int z = a + no, wa = a >> 5, wz = (z - 1) >> 5;
+    for (int wi = wa; wi <= wz; wi++) {
+      uint32_t x = b[wi];
+      if (wi == wa) x &= ~lowmask(a & 31);
+      if (wi == wz) x &= lowmask(((z - 1) & 31) + 1);
+      while (x) {
+        const int q = wi * 32 + ctz(x);
+        x &= x - 1;
+        const int v = unit_other(unit(q));
+        for (int w = 0; w < W; w++) bl[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
       }
     }
-    return -1;
   }
 
   /* ---- busy tick over _busy_devices (volt:904-908) ---- */
@@ -757,196 +736,130 @@ struct Env {
   }
 
   /* block / unblock one incident edge of d (volt:1071-1080, :1091-1100, :485-511):
-   * pool = out-edges then in-edges whose blocked flag == want, each repeated `multiplicity` times.
-   * General form in neighbour-id space (extra edges, multi-edges). */
+   * pool = out-edges then in-edges whose blocked flag == want, each repeated `multiplicity` times == the units of
+   * [ip[d], ip[d+1]) with that flag: its size is a popcount and the pick a select. */
+  CYG_HD bool flip_incident(int d, bool want, Stream& st) {
+    if (n_extra() > 0) return flip_incident_general(d, want, st);
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu;
+    const int a = ip(d), len = ip(d + 1) - a;
+    const int total = range_count(a, len, flipw);
+    if (total == 0) return false;
+    const int q = range_select(a, len, flipw, (int)below(st.next(rng), (uint32_t)total));
+    set_pair_blocked(q, !want);
+    return true;
+  }
+  /* The same for an env with extra (hub-star) edges: those sit in the per-env list, not in the unit bitset, and enter
+   * the out list / in list at their place in ascending neighbour order.  A merged walk: per list, the extras of d in
+   * ascending far-endpoint id, each preceded by the base units in front of it. */
   CYG_HD bool flip_incident_general(int d, bool want, Stream& st) {
-    bool has_blk = any_blocked();
-    if (want && !has_blk) return false;
-    uint32_t o[W], in[W];
-    out_row(d, has_blk, want, o);
-    in_row(d, has_blk, want, in);
-    bool multi = devbit(n->o_incmulti, d);
-    const uint32_t *lo = tc + n->o_mlo + d * W, *hi = tc + n->o_mhi + d * W, *loT = tc + n->o_mloT + d * W, *hiT = tc + n->o_mhiT + d * W;
-    int to = weight_below(o, lo, hi, multi, 32 * W);
-    int ti = weight_below(in, loT, hiT, multi, 32 * W);
-    int total = to + ti;
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu;
+    const int a = ip(d), no = nout(d), z = ip(d + 1);
+    const int nx = n_extra();
+    uint32_t* x = extra();
+    int nxe = 0;
+    for (int j = 0; j < nx; j++) {
+      const uint32_t xe = x[j];
+      const int u = (int)(xe & CYG_X_IDMASK), v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+      if ((u == d || v == d) && (((xe & CYG_X_BLOCKED) != 0) == want)) nxe++;
+    }
+    const int total = range_count(a, z - a, flipw) + nxe;
     if (total == 0) return false;
     int r = (int)below(st.next(rng), (uint32_t)total);
-    if (r < to) {
-      int v = weighted_select(o, lo, hi, multi, r);
-      set_edge_blocked(d, v, !want);
-    } else {
-      int s = weighted_select(in, loT, hiT, multi, r - to);
-      set_edge_blocked(s, d, !want);
-    }
-    return true;
-  }
-  /* Same pick in EDGE-ID space when the env has no extra edges: the out-edges of d are the contiguous bits
-   * [row_ptr[d], row_ptr[d+1]) of the blocked bitset (ascending neighbour id == pool order) and its in-edges the
-   * bits [in_ptr[d], in_ptr[d+1]) of the in-order copy (ascending source id). */
-  /* W-word window of bitset b[0, nw): bits [a, a + len) (len <= 32 W), XORed with flipw, zero beyond len */
-  CYG_HD void window(const uint32_t* b, int nw, int a, int len, uint32_t flipw, uint32_t* x) {
-    int wa = a >> 5, sh = a & 31;
-#ifdef __CUDA_ARCH__
-    if (SM) { /* shared memory: the W words after the bitset are readable (the next bitset, the next record or the
-                 CTA's carry area) and the length mask drops whatever they hold, so no bounds tests */
-      uint32_t lo = b[wa];
-      for (int q = 0; q < W; q++) {
-        uint32_t hi = b[wa + q + 1];
-        x[q] = (funnel_r(lo, hi, sh) ^ flipw) & lowmask0(len - 32 * q);
-        lo = hi;
-      }
-      return;
-    }
-#endif
-    uint32_t lo = wa < nw ? b[wa] : 0u;
-    for (int q = 0; q < W; q++) {
-      uint32_t hi = (wa + q + 1 < nw) ? b[wa + q + 1] : 0u;
-      uint32_t v = funnel_r(lo, hi, sh) ^ flipw;
-      int rem = len - 32 * q;
-      x[q] = rem <= 0 ? 0u : (rem >= 32 ? v : (v & lowmask(rem)));
-      lo = hi;
-    }
-  }
-  CYG_HD int wrank(const uint32_t* x, int pos) { /* set bits of the window below position pos */
-    int c = 0;
-    for (int q = 0; q < W; q++) c += popc(x[q] & lowmask0(pos - 32 * q));
-    return c;
-  }
-  CYG_HD bool wbit(const uint32_t* x, int pos) {
-    uint32_t v;
-    if (W == 4) { /* two-level select */
-      const bool h1 = (pos & 64) != 0, h0 = (pos & 32) != 0;
-      const uint32_t a = h1 ? x[2 % W] : x[0], c = h1 ? x[3 % W] : x[1 % W];
-      v = h0 ? c : a;
-    } else {
-      v = 0;
-      for (int q = 0; q < W; q++) v |= x[q] & eqmask(q, pos >> 5);
-    }
-    return (v >> (pos & 31)) & 1u;
-  }
-  /* multiplicity-weighted pool over a window: dm = packed multi-edge entries of the list (Net::o_dmulti) */
-  CYG_HD int wweight(const uint32_t* x, uint32_t dm) {
-    int c = 0;
-    for (int q = 0; q < W; q++) c += popc(x[q]);
-    for (int k = 0; k < 2; k++) {
-      int off = (int)((dm >> (10 * k)) & 0xFFu);
-      if (off != 0xFF && wbit(x, off)) c += (int)((dm >> (8 + 10 * k)) & 3u);
-    }
-    return c;
-  }
-  /* window position of the pool element that holds weight unit r (no early exits: the lanes of a warp stay together) */
-  CYG_HD int wselect(const uint32_t* x, uint32_t dm, int r) {
-    int extra_before = 0, direct = -1;
-    if ((dm & 0x3FFFFu) != (0xFFu | (0xFFu << 10))) { /* the list has multi-edges */
-      bool stop = false;
-      for (int k = 0; k < 2; k++) {
-        int off = (int)((dm >> (10 * k)) & 0xFFu);
-        int ex = (int)((dm >> (8 + 10 * k)) & 3u);
-        bool valid = off != 0xFF && !stop && direct < 0 && wbit(x, off);
-        int lo = wrank(x, off) + extra_before;
-        if (valid) {
-          if (r < lo) stop = true;
-          else if (r <= lo + ex) direct = off;
-          else extra_before += ex;
+    for (int side = 0; side < 2; side++) { /* out list, then in list */
+      int cursor = side ? a + no : a;
+      const int end = side ? z : a + no;
+      int last = -1;
+      for (;;) { /* next extra of this side in ascending far-endpoint id */
+        int best = -1, bid = 0x7FFFFFFF;
+        for (int j = 0; j < nx; j++) {
+          const uint32_t xe = x[j];
+          const int u = (int)(xe & CYG_X_IDMASK), v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+          if ((side ? v : u) != d || (((xe & CYG_X_BLOCKED) != 0) != want)) continue;
+          const int far_id = side ? u : v;
+          if (far_id > last && far_id < bid) { bid = far_id; best = j; }
         }
+        if (best < 0) break;
+        last = bid;
+        const int p = side ? a + no + units_before_in(d, bid) : a + units_before_out(d, bid);
+        const int cb = range_count(cursor, p - cursor, flipw);
+        if (r < cb) { set_pair_blocked(range_select(cursor, p - cursor, flipw, r), !want); return true; }
+        r -= cb;
+        cursor = p;
+        if (r == 0) { if (want) x[best] &= ~CYG_X_BLOCKED; else x[best] |= CYG_X_BLOCKED; return true; }
+        r--;
       }
+      const int cb = range_count(cursor, end - cursor, flipw);
+      if (r < cb) { set_pair_blocked(range_select(cursor, end - cursor, flipw, r), !want); return true; }
+      r -= cb;
     }
-    int pos = select_nth(x, r - extra_before);
-    return direct >= 0 ? direct : pos;
+    return false; /* not reached: r < total */
   }
-  /* the pool of one device: windows over its out-edges and in-edges whose blocked flag == want */
-  struct Pool {
-    int a, c0, lo, li, to, ti;
-    uint32_t dmo, dmi;
-    uint32_t xo[W], xi[W];
-  };
-  CYG_HD bool flip_needs_general(int d) { /* only envs with extra (hub-star) edges need the neighbour-id walk */
-    return n_extra() > 0;
+
+  /* set / clear the units [s, s + m) of the bitset (m <= 4: at most one word boundary) */
+  CYG_HD void set_run(uint32_t* bits, int s, int m, bool b) {
+    const int sh = s & 31;
+    const uint32_t lo = lowmask(m) << sh;
+    uint32_t& w0 = bits[s >> 5];
+    w0 = b ? (w0 | lo) : (w0 & ~lo);
+    if (sh + m > 32) {
+      const uint32_t hi = lowmask(m) >> (32 - sh);
+      uint32_t& w1 = bits[(s >> 5) + 1];
+      w1 = b ? (w1 | hi) : (w1 & ~hi);
+    }
   }
-  /* lists with more than two multi-edges (bit 31 of the packed entry): weights from the edge-order multiplicity
-   * bitsets e_mlo / e_mhi (out-list order) and ei_mlo / ei_mhi (in-list order) instead of the packed entries */
-  CYG_HD int wweight_bits(const uint32_t* x, uint32_t off_lo, uint32_t off_hi, int a, int len) {
-    uint32_t lo[W], hi[W];
-    window(Tp(off_lo), n->EW, a, len, 0u, lo);
-    window(Tp(off_hi), n->EW, a, len, 0u, hi);
-    int c = 0;
-    for (int q = 0; q < W; q++) c += popc(x[q]) + popc(x[q] & lo[q]) + 2 * popc(x[q] & hi[q]);
-    return c;
-  }
-  CYG_HD int wselect_bits(const uint32_t* x, uint32_t off_lo, uint32_t off_hi, int a, int len, int r) {
-    uint32_t lo[W], hi[W];
-    window(Tp(off_lo), n->EW, a, len, 0u, lo);
-    window(Tp(off_hi), n->EW, a, len, 0u, hi);
-    int pos = -1;
-    for (int q = 0; q < W; q++) {
-      uint32_t m = x[q];
-      while (m && pos < 0) {
-        int sb = ctz(m);
-        m &= m - 1;
-        int wt = 1 + (int)((lo[q] >> sb) & 1u) + 2 * (int)((hi[q] >> sb) & 1u);
-        if (r < wt) pos = q * 32 + sb; else r -= wt;
+  /* block / unblock for every device of act[] in ascending id order (the set form of volt:1071-1100), one thread per
+   * env.  The pool of a device with at most 128 units is a 4-word window of the unit bitset, read, weighed and
+   * selected from with no data-dependent branch, so that the 32 envs of a warp walk their lists in lock step (one
+   * iteration per listed device, whatever its degree).  Returns the number of flips. */
+  CYG_HD uint32_t flip_walk(uint32_t* act, bool want, int site) {
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu;
+    Stream st(site);
+    uint32_t cnt = 0;
+    uint32_t* b = inc();
+    const bool has_x = n_extra() > 0;
+    for (;;) {
+      const int d = pop_lowest(act);
+      if (d < 0) break;
+      if (has_x) { cnt += flip_incident_general(d, want, st) ? 1u : 0u; continue; }
+      const uint32_t di = dinfo(d), di1 = dinfo(d + 1);
+      const int a = (int)(di & 0xFFFFu), nt = (int)(di1 & 0xFFFFu) - a;
+      int q;
+      if (nt <= 128) {
+        const int wa = a >> 5, sh = a & 31;
+        uint32_t x[4];
+        uint32_t lo = b[wa];
+        for (int i = 0; i < 4; i++) {
+#ifdef __CUDA_ARCH__
+          const uint32_t hi = SM ? b[wa + i + 1] : (wa + i + 1 <= n->UW ? b[wa + i + 1] : 0u); /* shared memory: whatever follows is readable and masked off */
+#else
+          const uint32_t hi = wa + i + 1 <= n->UW ? b[wa + i + 1] : 0u;
+#endif
+          x[i] = (funnel_r(lo, hi, sh) ^ flipw) & lowmask0(nt - 32 * i);
+          lo = hi;
+        }
+        const int c0 = popc(x[0]), c1 = popc(x[1]), c2 = popc(x[2]), c3 = popc(x[3]);
+        const int total = c0 + c1 + c2 + c3;
+        if (total == 0) continue;
+        const int r = (int)below(st.next(rng), (uint32_t)total);
+        /* word holding unit r, branch-free */
+        const bool g1 = r >= c0, g2 = r >= c0 + c1, g3 = r >= c0 + c1 + c2;
+        const uint32_t xw = g3 ? x[3] : g2 ? x[2] : g1 ? x[1] : x[0];
+        const int base = g3 ? c0 + c1 + c2 : g2 ? c0 + c1 : g1 ? c0 : 0;
+        const int wsel = (g1 ? 1 : 0) + (g2 ? 1 : 0) + (g3 ? 1 : 0);
+        q = a + 32 * wsel + select_in_word(xw, r - base);
+      } else {
+        const int total = range_count(a, nt, flipw);
+        if (total == 0) continue;
+        q = range_select(a, nt, flipw, (int)below(st.next(rng), (uint32_t)total));
       }
+      const uint32_t ui = unit(q);
+      const int m = unit_m(ui);
+      set_run(b, q - unit_off(ui), m, !want);
+      set_run(b, unit_twin(ui), m, !want);
+      cnt++;
     }
-    return pos;
-  }
-  /* the two halves of flip_pool: the windows (state at the time of the call) and their weights (the cooperative
-   * block / unblock of cyg_coop.cuh edits the windows between the two) */
-  CYG_HD void flip_windows(int d, bool want, Pool& P) {
-    P.dmo = T(n->o_dmulti + 2 * d); P.dmi = T(n->o_dmulti + 2 * d + 1);
-    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu; /* pool bits = blocked bits XOR flipw */
-    P.a = row_ptr(d); P.c0 = in_ptr(d);
-    P.lo = row_ptr(d + 1) - P.a; P.li = in_ptr(d + 1) - P.c0;
-    window(blocked(), n->EW, P.a, P.lo, flipw, P.xo);
-    window(blocked_in(), n->EW, P.c0, P.li, flipw, P.xi);
-  }
-  CYG_HD int flip_weigh(Pool& P) {
-    P.to = (P.dmo >> 31) ? wweight_bits(P.xo, n->o_emlo, n->o_emhi, P.a, P.lo) : wweight(P.xo, P.dmo);
-    P.ti = (P.dmi >> 31) ? wweight_bits(P.xi, n->o_eimlo, n->o_eimhi, P.c0, P.li) : wweight(P.xi, P.dmi);
-    return P.to + P.ti;
-  }
-  CYG_HD int flip_pool(int d, bool want, Pool& P) { /* returns the multiplicity-weighted pool size */
-    flip_windows(d, want, P);
-    return flip_weigh(P);
-  }
-  /* drop base edge `eid` (incident to the pool's device) from the pool windows */
-  CYG_HD void pool_remove(Pool& P, int eid) {
-    const int po = eid - P.a;
-    const bool is_out = (unsigned)po < (unsigned)P.lo;
-    const int pp = is_out ? po : out2in(eid) - P.c0;
-    const uint32_t bit = 1u << (pp & 31);
-    for (int q = 0; q < W; q++) {
-      const uint32_t m = bit & eqmask(q, pp >> 5);
-      P.xo[q] &= ~(is_out ? m : 0u);
-      P.xi[q] &= ~(is_out ? 0u : m);
-    }
-  }
-  /* pool element holding weight unit r: returns the base edge id, `other` = the far endpoint of that edge */
-  CYG_HD int flip_pick(const Pool& P, int r, int& other) {
-    const bool from_out = r < P.to;
-    uint32_t xs[W];
-    for (int q = 0; q < W; q++) xs[q] = from_out ? P.xo[q] : P.xi[q];
-    const uint32_t dm = from_out ? P.dmo : P.dmi;
-    const int rr = from_out ? r : r - P.to;
-    int pos;
-    if (dm >> 31)
-      pos = from_out ? wselect_bits(xs, n->o_emlo, n->o_emhi, P.a, P.lo, rr) : wselect_bits(xs, n->o_eimlo, n->o_eimhi, P.c0, P.li, rr);
-    else
-      pos = wselect(xs, dm, rr);
-    int j_in = P.c0 + (from_out ? 0 : pos);
-    int e = from_out ? P.a + pos : in_eid(j_in);
-    other = from_out ? col(e) : in_src(j_in);
-    return e;
-  }
-  CYG_HD bool flip_incident(int d, bool want, Stream& st) {
-    if (flip_needs_general(d)) return flip_incident_general(d, want, st);
-    Pool P;
-    int total = flip_pool(d, want, P);
-    if (total == 0) return false;
-    int other;
-    int e = flip_pick(P, (int)below(st.next(rng), (uint32_t)total), other);
-    set_base_blocked(e, !want);
-    return true;
+    if (!has_x) { if (want) nblk() -= cnt; else nblk() += cnt; }
+    return cnt;
   }
 
   /* devices of act[] with app_index < len(device.apps) (volt:1014-1016): bit-sliced compare over the napps planes */
@@ -994,15 +907,9 @@ struct Env {
         }
         break;
       case 6: case 9: {
-        Stream st(atype == 6 ? SITE_BLOCK : SITE_UNBLOCK);
         cost += -0.5 * ds * na;
         defcost += 0.5 * ds * na;
-        uint32_t cnt = 0;
-        for (;;) {
-          int d = pop_lowest(act);
-          if (d < 0) break;
-          if (flip_incident(d, atype == 9, st)) cnt++;
-        }
+        const uint32_t cnt = flip_walk(act, atype == 9, atype == 6 ? SITE_BLOCK : SITE_UNBLOCK);
         if (cnt) { scal(atype == 6 ? CYG_S_EBLK : CYG_S_EADD) += cnt; dirty = true; }
       } break;
       case 7: /* volt:1082-1089 */
@@ -1123,113 +1030,51 @@ struct Env {
   /* ---- attacker actions (volt:1126-1202) ---- */
   /* unblocked out-neighbours of s (base row minus blocked pairs, plus unblocked extra edges) */
   CYG_HD void live_row(int s, bool has_blk, int nx, uint32_t* row) {
-    for (int w = 0; w < W; w++) row[w] = adj(s, w);
-    if (has_blk) {
-      const uint32_t* b = blocked();
-      int a = row_ptr(s), z = row_ptr(s + 1);
-      if (a < z) {
-        for (int wi = a >> 5; wi <= (z - 1) >> 5; wi++) {
-          uint32_t x = b[wi];
-          if (wi == (a >> 5)) x &= ~lowmask(a & 31);
-          if (wi == ((z - 1) >> 5)) x &= lowmask(((z - 1) & 31) + 1);
-          while (x) {
-            int e = wi * 32 + ctz(x);
-            x &= x - 1;
-            int v = col(e);
-            for (int w = 0; w < W; w++) row[w] &= ~((1u << (v & 31)) & eqmask(w, v >> 5));
-          }
-        }
-      }
-    }
-    if (nx > 0) {
-      const uint32_t* x = extra();
-      for (int j = 0; j < nx; j++) {
-        uint32_t xe = x[j];
-        if ((int)(xe & CYG_X_IDMASK) != s || (xe & CYG_X_BLOCKED)) continue;
-        int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
-        for (int w = 0; w < W; w++) row[w] |= (1u << (v & 31)) & eqmask(w, v >> 5);
-      }
-    }
+    uint32_t bl[W], xo[W];
+    for (int w = 0; w < W; w++) { bl[w] = 0; xo[w] = 0; }
+    if (has_blk) blocked_out_ids(s, bl);
+    if (nx > 0) extra_out_row(s, false, xo);
+    for (int w = 0; w < W; w++) row[w] = (adj(s, w) & ~bl[w]) | xo[w];
   }
   /* One source of the lateral-movement loop (volt:1148-1185): scan the unblocked out-neighbours of s in ascending
    * order; a DomainController source hits the first one, otherwise the first that is reachable_by_attacker or
    * (not compromised, known, vulnerable to the exploit).  comp[] = current isCompromised words, kv[] = known &
-   * vulnerable.  Returns the hit device (-1: none); cnt = hops logged before the hit (log_communication, volt:1161:
-   * every repeat of a multi-edge counts); rule3 = the hit relied on "not yet compromised". */
-  CYG_HD int attack_source(int s, const uint32_t* comp, const uint32_t* kv, bool has_blk, int nx, int& cnt, bool& rule3) {
+   * vulnerable, xrow = unblocked extra out-neighbours of s (nullptr: none).  Returns the hit device (-1: none); cnt =
+   * hops logged before the hit (log_communication, volt:1161: every repeat of a multi-edge counts) = unblocked units in
+   * front of the hit's first unit; rule3 = the hit relied on "not yet compromised". */
+  CYG_HD int attack_source(int s, const uint32_t* comp, const uint32_t* kv, bool has_blk, const uint32_t* xrow, int& cnt, bool& rule3) {
     const bool is_dc = devbit(n->o_dc, s);
-    const uint32_t dmo = T(n->o_dmulti + 2 * s);
-    int vw = -1;
+    const int a = ip(s), no = nout(s);
+    uint32_t row[W], cand[W], xc[W];
+    for (int w = 0; w < W; w++) {
+      const uint32_t ok = is_dc ? 0xFFFFFFFFu : (m_reach(w) | (~comp[w] & kv[w]));
+      row[w] = adj(s, w);
+      xc[w] = xrow ? (xrow[w] & ok) : 0u;
+      cand[w] = (row[w] & ok) | xc[w];
+    }
+    int vw = -1, upos = no; /* units walked in front of the hit (all of them when nothing is hit) */
     uint32_t hitbit = 0;
-    if (nx > 0) {
-      /* general form: materialise the unblocked row (envs with extra edges) */
-      uint32_t row[W];
-      live_row(s, has_blk, nx, row);
-      uint32_t cand_w = 0;
-      for (int w = W - 1; w >= 0; w--) {
-        uint32_t cand = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
-        bool nz = cand != 0;
-        vw = nz ? w : vw;
-        cand_w = nz ? cand : cand_w;
+    for (;;) { /* first candidate whose edge is not blocked (volt:1157-1159) */
+      int w0 = -1;
+      uint32_t cw = 0, xw = 0;
+      for (int w = W - 1; w >= 0; w--) { bool nz = cand[w] != 0; w0 = nz ? w : w0; cw = nz ? cand[w] : cw; xw = nz ? xc[w] : xw; }
+      if (w0 < 0) break;
+      const uint32_t lb = cw & (0u - cw);
+      int rk = 0;
+      for (int w = 0; w < W; w++) rk += popc(row[w] & ((w < w0 ? 0xFFFFFFFFu : 0u) | ((lb - 1u) & eqmask(w, w0))));
+      const int up = rk + multi_before(s, rk);
+      if (!(xw & lb) && has_blk && ubit(a + up)) { /* a blocked base pair: not walked, not logged */
+        for (int w = 0; w < W; w++) cand[w] ^= lb & eqmask(w, w0);
+        continue;
       }
-      hitbit = cand_w & (0u - cand_w);
-      cnt = 0;
-      const bool multi = devbit(n->o_rowmulti, s);
+      vw = w0; hitbit = lb; upos = up;
+      break;
+    }
+    cnt = upos - (has_blk ? range_count(a, upos, 0u) : 0);
+    if (xrow) { /* unblocked extra edges in front of the hit (all of them when nothing is hit) */
       for (int w = 0; w < W; w++) {
-        uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
-        uint32_t m = row[w] & bm;
-        cnt += popc(m);
-        if (multi) cnt += popc(m & tc[n->o_mlo + s * W + w]) + 2 * popc(m & tc[n->o_mhi + s * W + w]);
-      }
-    } else {
-      /* edge-id form: the pair (s, v) is bit row_ptr[s] + rank of v in adj[s] of the blocked bitset */
-      uint32_t row[W], cand[W];
-      const int a = row_ptr(s);
-      int deg = 0;
-      for (int w = 0; w < W; w++) {
-        row[w] = adj(s, w);
-        deg += popc(row[w]);
-        cand[w] = is_dc ? row[w] : (row[w] & (m_reach(w) | (~comp[w] & kv[w])));
-      }
-      int nb = deg; /* pairs walked before the hit (all of them when nothing is hit) */
-      const uint32_t* b = blocked();
-      for (;;) { /* first candidate whose edge is not blocked (volt:1157-1159) */
-        int w0 = -1;
-        uint32_t cw = 0;
-        for (int w = W - 1; w >= 0; w--) { bool nz = cand[w] != 0; w0 = nz ? w : w0; cw = nz ? cand[w] : cw; }
-        if (w0 < 0) break;
-        uint32_t lb = cw & (0u - cw);
-        int rk = 0;
-        for (int w = 0; w < W; w++) rk += popc(row[w] & ((w < w0 ? 0xFFFFFFFFu : 0u) | ((lb - 1u) & eqmask(w, w0))));
-        int e = a + rk;
-        if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) {
-          for (int w = 0; w < W; w++) cand[w] ^= lb & eqmask(w, w0);
-          continue;
-        }
-        vw = w0; hitbit = lb; nb = rk;
-        break;
-      }
-      cnt = nb;
-      if (has_blk && nb > 0) { /* minus the blocked pairs among the first nb of the row */
-        uint32_t xb[W];
-        window(b, n->EW, a, nb, 0u, xb);
-        for (int q = 0; q < W; q++) cnt -= popc(xb[q]);
-      }
-      if (dmo >> 31) { /* more than two multi-edges in the row: repeats from the multiplicity bitsets */
-        uint32_t xu[W], lo[W], hi[W];
-        window(b, n->EW, a, nb, has_blk ? 0xFFFFFFFFu : 0u, xu); /* unblocked pairs among the first nb */
-        if (!has_blk) for (int q = 0; q < W; q++) { int rem = nb - 32 * q; xu[q] = rem <= 0 ? 0u : (rem >= 32 ? 0xFFFFFFFFu : lowmask(rem)); }
-        window(Tp(n->o_emlo), n->EW, a, nb, 0u, lo);
-        window(Tp(n->o_emhi), n->EW, a, nb, 0u, hi);
-        for (int q = 0; q < W; q++) cnt += popc(xu[q] & lo[q]) + 2 * popc(xu[q] & hi[q]);
-      } else {
-        for (int k = 0; k < 2; k++) { /* multi-edges walked: every repeat is logged */
-          int off = (int)((dmo >> (10 * k)) & 0xFFu);
-          if (off == 0xFF || off >= nb) continue;
-          int e = a + off;
-          if (has_blk && ((b[e >> 5] >> (e & 31)) & 1u)) continue;
-          cnt += (int)((dmo >> (8 + 10 * k)) & 3u);
-        }
+        const uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
+        cnt += popc(xrow[w] & bm);
       }
     }
     if (vw < 0) { rule3 = false; return -1; }
@@ -1275,7 +1120,9 @@ struct Env {
           if (s < 0) break;
           int cnt;
           bool rule3;
-          const int v = attack_source(s, comp, kv, has_blk, nx, cnt, rule3);
+          uint32_t xrow[W];
+          if (nx > 0) extra_out_row(s, false, xrow);
+          const int v = attack_source(s, comp, kv, has_blk, nx > 0 ? xrow : (const uint32_t*)0, cnt, rule3);
           logs += (uint32_t)cnt + (v >= 0 ? 1u : 0u);
           if (v >= 0) {
             const bool is_dc = devbit(n->o_dc, s);
@@ -1412,98 +1259,115 @@ struct Env {
     generate_workloads(nS, true, n_active, ssamp, stri);
   }
 
-  /* ---- evolve_network (CyberDefenseEnv.py:583-875) ---- */
+  /* ---- evolve_network (CyberDefenseEnv.py:583-875) ----
+   * Written for a warp of 32 envs in lock step: the Poisson count comes first (half of the envs draw 0 events), the
+   * Philox blocks of the three per-event sites are fetched together before the loop, and an event is ONE code path
+   * for both kinds (activate / deactivate differ only in the masks they apply), entered only by the lanes whose event
+   * acts -- a removal is a no-op while the network sits at its floor size, which is most of them. */
   CYG_HD void evolve_network() {
     const cyg_config& c = n->cfg;
     if (!(scal(CYG_S_FLAGS) & CYG_FL_SETS_INIT)) { /* :654-659 */
       for (int w = 0; w < W; w++) pl(P_ACTSET, w) = m_valid(w) & ~pl(P_NYA, w);
       scal(CYG_S_FLAGS) |= CYG_FL_SETS_INIT;
     }
-    int n_act = count(P_ACTSET);
-    Stream sp(SITE_EV_POISSON), sadd(SITE_EV_ADD), spick(SITE_EV_PICK), satt(SITE_EV_ATT);
-    uint32_t xp = sp.next(rng); /* :668 */
+    Stream sp(SITE_EV_POISSON);
+    const uint32_t xp = sp.next(rng); /* :668 */
     int num_events = 0; /* #{j : xp >= tab[j]}; the table is ascending: count over all 16 entries with fixed indices
                            (a walk with a per-thread index serialises the constant-bank loads of a warp) */
     for (int j = 0; j < 16; j++) num_events += (xp >= c.poisson_tab[j]) ? 1 : 0;
-    int floor_n = c.num_of_device > c.min_network_size ? c.num_of_device : c.min_network_size;
-    for (int ev = 0; ev < num_events; ev++) {
-      uint32_t xa = sadd.next(rng); /* :679 */
-      if ((uint64_t)xa < c.thr_p_add) {
-        int n_inact = n->M - n_act;
-        if (n_inact > 0) {
+    if (num_events > 0) {
+      int n_act = count(P_ACTSET);
+      const int floor_n = c.num_of_device > c.min_network_size ? c.num_of_device : c.min_network_size;
+      Stream sadd(SITE_EV_ADD), spick(SITE_EV_PICK), satt(SITE_EV_ATT);
+      sadd.load(rng); spick.load(rng); satt.load(rng);
+      for (int ev = 0; ev < num_events; ev++) {
+        const bool add = (uint64_t)sadd.next(rng) < c.thr_p_add; /* :679 */
+        const int pool_n = add ? n->M - n_act : n_act;
+        if (add ? (pool_n > 0) : (n_act > floor_n)) { /* :680-712 */
           uint32_t m[W];
-          for (int w = 0; w < W; w++) m[w] = m_valid(w) & ~pl(P_ACTSET, w);
-          int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)n_inact)); /* :675 */
-          clrb(P_NYA, node);
-          setb(P_ACTSET, node);
-          n_act++;
-          uint32_t xt = satt.next(rng); /* :690: the draw is consumed even when p_attacker == 0 */
-          if ((uint64_t)xt < c.thr_p_attacker) { setb(P_COMP, node); setb(P_OWNED, node); setb(P_KNOWN, node); }
-        }
-      } else if (n_act > floor_n) { /* :701-712 */
-        uint32_t m[W];
-        for (int w = 0; w < W; w++) m[w] = pl(P_ACTSET, w);
-        int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)n_act));
-        setb(P_NYA, node);
+          const uint32_t inv = add ? 0xFFFFFFFFu : 0u; /* the inactive set, or the active one */
+          for (int w = 0; w < W; w++) m[w] = m_valid(w) & (pl(P_ACTSET, w) ^ inv);
+          const int node = select_nth(m, (int)below(spick.next(rng), (uint32_t)pool_n)); /* :675 */
+          const int nw = node >> 5;
+          const uint32_t bit = 1u << (node & 31);
+          const uint32_t on = add ? bit : 0u, off = add ? 0u : bit;
+          pl(P_NYA, nw) = (pl(P_NYA, nw) & ~bit) | off;
+          pl(P_ACTSET, nw) = (pl(P_ACTSET, nw) & ~bit) | on;
+          n_act += add ? 1 : -1;
+          if (add) {
+            const uint32_t xt = satt.next(rng); /* :690: the draw is consumed even when p_attacker == 0 */
+            if ((uint64_t)xt < c.thr_p_attacker) { pl(P_COMP, nw) |= bit; pl(P_OWNED, nw) |= bit; pl(P_KNOWN, nw) |= bit; }
+          } else { /* :701-712: workload dropped, busy_time 0, removed_before */
+            pl(P_HASWL, nw) &= ~bit;
+            pl(P_PT0, nw) &= ~bit; pl(P_PT0 + 1, nw) &= ~bit; pl(P_PT0 + 2, nw) &= ~bit;
+            pl(P_BUSY0, nw) &= ~bit; pl(P_BUSY0 + 1, nw) &= ~bit; pl(P_BUSY0 + 2, nw) &= ~bit; pl(P_BUSY0 + 3, nw) &= ~bit;
 #ifdef __CUDA_ARCH__
-        atomicOr(&ckpt[node], CYG_CKI_REMOVED); /* removed_before: a RED, nobody waits for the global-memory round trip */
+            atomicOr(&ckpt[node], CYG_CKI_REMOVED); /* removed_before: a RED, nobody waits for the global-memory round trip */
 #else
-        ckpt[node] |= CYG_CKI_REMOVED; /* removed_before */
+            ckpt[node] |= CYG_CKI_REMOVED;
 #endif
-        drop_wl(node);
-        set_field(P_BUSY0, 4, node, 0);
-        clrb(P_ACTSET, node);
-        n_act--;
+          }
+        }
       }
     }
     /* bidirectional hub-star among active attacker-owned devices, hub = lowest id (:738-774) */
     int hub = -1;
-    bool changed = false;
     uint32_t oa[W];
     for (int w = W - 1; w >= 0; w--) {
       oa[w] = pl(P_OWNED, w) & pl(P_ACTSET, w);
       if (oa[w]) hub = w * 32 + ctz(oa[w]);
     }
-    if (hub >= 0) {
-      /* ONE pass over the extra list (it lives in global memory: the loads are independent and pipeline) instead of
-       * one has_edge() scan per direction and device: the extra out- and in-neighbours of the hub as bit rows */
+    if (hub < 0) return;
+    /* the hub's out- and in-neighbours: base rows plus ONE pass over the extra list (global memory: the loads are
+     * independent and pipeline) instead of one has_edge() scan per direction and device */
+    uint32_t need_out[W], need_in[W];
+    uint32_t any = 0;
+    {
       uint32_t xo[W], xi[W];
       for (int w = 0; w < W; w++) { xo[w] = 0; xi[w] = 0; }
-      {
-        const int nx0 = n_extra();
-        const uint32_t* x = extra();
-        for (int j = 0; j < nx0; j++) {
-          const uint32_t xe = x[j];
-          const int u = (int)(xe & CYG_X_IDMASK), v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
-          for (int w = 0; w < W; w++) {
-            xo[w] |= (u == hub) ? ((1u << (v & 31)) & eqmask(w, v >> 5)) : 0u;
-            xi[w] |= (v == hub) ? ((1u << (u & 31)) & eqmask(w, u >> 5)) : 0u;
-          }
+      const int nx0 = n_extra();
+      const uint32_t* x = extra();
+      for (int j = 0; j < nx0; j++) {
+        const uint32_t xe = x[j];
+        const int u = (int)(xe & CYG_X_IDMASK), v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+        for (int w = 0; w < W; w++) {
+          xo[w] |= (u == hub) ? ((1u << (v & 31)) & eqmask(w, v >> 5)) : 0u;
+          xi[w] |= (v == hub) ? ((1u << (u & 31)) & eqmask(w, u >> 5)) : 0u;
         }
       }
       for (int w = 0; w < W; w++) {
-        uint32_t rest = oa[w] & ~((1u << (hub & 31)) & eqmask(w, hub >> 5));
-        /* devices i of this word that lack hub -> i (base row of the hub or an extra edge) or i -> hub */
-        uint32_t need_out = rest & ~(adj(hub, w) | xo[w]);
-        uint32_t need_in = rest & ~xi[w];
-        while (rest) {
-          const int b = ctz(rest);
-          rest &= rest - 1;
-          const int i = w * 32 + b;
-          for (int dir = 0; dir < 2; dir++) {
-            const int u = dir ? i : hub, v = dir ? hub : i;
-            const bool missing = dir ? (((need_in >> b) & 1u) && !((adj(i, hub >> 5) >> (hub & 31)) & 1u)) : (((need_out >> b) & 1u) != 0);
-            if (!missing) continue;
-            int nx = n_extra();
-            if (nx >= c.xcap) { scal(CYG_S_FLAGS) |= CYG_FL_ERR_XCAP; continue; }
-            extra()[nx] = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
-            scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFFu) | ((uint32_t)(nx + 1) << 16);
-            changed = true;
-          }
+        const uint32_t rest = oa[w] & ~((1u << (hub & 31)) & eqmask(w, hub >> 5));
+        need_out[w] = rest & ~(adj(hub, w) | xo[w]); /* i lacks hub -> i */
+        uint32_t ni = rest & ~xi[w], r = ni;          /* i lacks i -> hub: not an extra edge and not in i's base row */
+        while (r) {
+          const int b = ctz(r);
+          r &= r - 1;
+          if ((adj(w * 32 + b, hub >> 5) >> (hub & 31)) & 1u) ni &= ~(1u << b);
+        }
+        need_in[w] = ni;
+        any |= need_out[w] | ni;
+      }
+    }
+    if (any == 0) return; /* the star is complete: the usual case */
+    bool changed = false;
+    for (int w = 0; w < W; w++) {
+      uint32_t rest = need_out[w] | need_in[w];
+      while (rest) { /* ascending i; per device hub -> i first, then i -> hub (:752-770) */
+        const int b = ctz(rest);
+        rest &= rest - 1;
+        const int i = w * 32 + b;
+        for (int dir = 0; dir < 2; dir++) {
+          if (!(((dir ? need_in[w] : need_out[w]) >> b) & 1u)) continue;
+          const int u = dir ? i : hub, v = dir ? hub : i;
+          int nx = n_extra();
+          if (nx >= c.xcap) { scal(CYG_S_FLAGS) |= CYG_FL_ERR_XCAP; continue; }
+          extra()[nx] = (uint32_t)u | ((uint32_t)v << CYG_X_V_SHIFT);
+          scal(CYG_S_PREV_X) = (scal(CYG_S_PREV_X) & 0xFFFFu) | ((uint32_t)(nx + 1) << 16);
+          changed = true;
         }
       }
     }
-    /* the preferential-attachment repair (:776-843) needs a degree-0 vertex: dead on these graphs */
+    /* the preferential-attachment repair (:776-843) needs a degree-0 vertex: build_tables refuses such networks */
     if (changed) rebuild_cache();
   }
 
@@ -1559,7 +1423,20 @@ struct Env {
   /* the action types the plain-step kernel hands to a whole warp (cyg_coop.cuh) */
   CYG_HD static bool coop_type(int mode, int atype) {
     if (mode == CYG_MODE_ATTACKER) return atype == 1;
-    return atype == 1 || atype == 3 || atype == 4 || atype == 6 || atype == 9;
+    return atype == 1 || atype == 3 || atype == 4;
+  }
+  /* ... plus block / unblock.  (Measured: the owning thread walking the list itself -- flip_walk, ~135 instructions per
+   * listed device, branch-free -- is a ~90k-cycle dependent chain for a 46-device list; the warp-per-env windows of
+   * cyg_coop.cuh take ~11k.  -DCYG_FLIP_THREAD keeps that experiment for envs without extra edges.) */
+  CYG_HD bool deferred_type(int mode, int atype) {
+    if (mode == CYG_MODE_DEFENDER && (atype == 6 || atype == 9)) {
+#ifdef CYG_FLIP_THREAD
+      return n_extra() > 0;
+#else
+      return true;
+#endif
+    }
+    return coop_type(mode, atype);
   }
   /* LIGHT: a plain (ungrouped, set-form) step whose cooperative types are handled elsewhere -- they return at once
    * here (the only one that can arrive is the attacker's type 1 under base_line "No Attack", a no-op), which lets the
@@ -1574,7 +1451,7 @@ struct Env {
     Act a;
     decode(hdr, mask, order, a);
     const int mode = a.mode;
-    if (LIGHT && coop_type(mode, atype)) { store_costs(); return atype; }
+    if (LIGHT && deferred_type(mode, atype)) { store_costs(); return atype; }
     if (!grouped) {
       if (a.atype == -1000) { a.n_dev = 0; a.first = -1; a.n_ex = 1; a.exw = 0; a.app_index = 0; }
       if (mode == CYG_MODE_DEFENDER) {
@@ -1782,6 +1659,21 @@ CYG_HD uint32_t export_device(const Net* n, const uint32_t* rec, int d, uint32_t
   for (int k = 0; k < 4; k++) w |= get(P_BUSY0 + k) << (CYG_DEV_BUSY_SHIFT + k);
   for (int k = 0; k < n->ncby; k++) w |= get(P_CBY0 + k) << (CYG_DEV_CBY_SHIFT + k);
   return w;
+}
+
+/* canonical blocked[] (bit e = base pair e, out-list pair order; include/cygym_b200.h) <-> the unit bitset of a record.
+ * set_units: the word / mask pairs a blocked pair e sets (2 m bits: its run in the source's out list and the twin run in
+ * the target's in list); `put(word_index, mask)` is the caller's store (plain on the host, atomicOr in the import kernel) */
+template <class Put>
+CYG_HD void pair_units(const Net* n, int e, Put put) {
+  const int q = (int)n->blob[n->o_pair2unit + e];
+  const uint32_t ui = n->blob[n->o_unit + q];
+  const int t = unit_twin(ui), m = unit_m(ui);
+  for (int k = 0; k < m; k++) { put((q + k) >> 5, 1u << ((q + k) & 31)); put((t + k) >> 5, 1u << ((t + k) & 31)); }
+}
+CYG_HD bool pair_blocked(const Net* n, const uint32_t* rec, int e) {
+  const int q = (int)n->blob[n->o_pair2unit + e];
+  return (rec[n->off_inc + (q >> 5)] >> (q & 31)) & 1u;
 }
 
 /* one element of an observation row (CyberDefenseEnv.py:146-257); obs_mode as in cyg_step_out */

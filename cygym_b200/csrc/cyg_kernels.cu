@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       mode = (int)((act[0] >> 8) & 1u);
       if (bl_t) e.bl = (int)bl_t[env];
       atype = e.step_pre(act, p.flags);
-      deferred = coop_ok && Coop<W>::is_heavy(mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
+      deferred = coop_ok && Coop<W>::is_heavy(e, mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
     }
     if (coop_ok) {
       /* once every env has its epoch open and its busy tick done (s_cnt[CYG_NKEYS + 6] counts the owning warps that
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (lg == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 1], 1u);
         task = __shfl_sync(gm, task, gbase);
         if (task >= nf) break;
+        if (!((s_def[(lof + task) >> 5] >> ((lof + task) & 31)) & 1u)) continue; /* no extra edges: its own thread did it in phase A */
         const int el_b = s_perm[lof + task];
         const int env_b = env0 + el_b;
         Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
@@ -655,22 +656,26 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
     if (lane == CYG_S_FLAGS) v |= err;
     rec[lane] = v;
   }
+  /* canonical blocked[] (bit e = base pair e) -> the unit bitset: zero it, then every blocked pair sets its 2 m units */
+  for (int i = n.off_inc + lane; i < n.S; i += 32) rec[i] = 0u;
+  __syncwarp();
   uint32_t nblk = 0;
+  const uint32_t* bo = p.blocked + (size_t)warp * n.EW;
   for (int i = lane; i < n.EW; i += 32) {
-    const uint32_t* bo = p.blocked + (size_t)warp * n.EW;
-    rec[n.off_blocked + i] = bo[i];
-    nblk += (uint32_t)__popc(bo[i]);
-    uint32_t bi = 0; /* the same bits in in-list order */
-    for (int j = 0; j < 32 && i * 32 + j < n.E; j++) {
-      int jj = i * 32 + j;
-      int e = (int)((n.blob[n.o_in_eid + (jj >> 1)] >> ((jj & 1) * 16)) & 0xFFFFu);
-      bi |= ((bo[e >> 5] >> (e & 31)) & 1u) << j;
+    uint32_t x = bo[i];
+    if (i == n.EW - 1 && (n.E & 31)) x &= (1u << (n.E & 31)) - 1u;
+    if (n.E == 0) x = 0;
+    nblk += (uint32_t)__popc(x);
+    while (x) {
+      const int e = i * 32 + __ffs((int)x) - 1;
+      x &= x - 1;
+      pair_units(&n, e, [&](int wi, uint32_t m) { atomicOr(&rec[n.off_inc + wi], m); });
     }
-    rec[n.off_blocked_in + i] = bi;
   }
   nblk = __reduce_add_sync(0xFFFFFFFFu, nblk);
   for (int i = lane; i < n.cfg.xcap; i += 32) p.xtra_int[(size_t)warp * n.cfg.xcap + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
-  for (int i = n.off_aux + lane; i < n.S; i += 32) rec[i] = (i == n.off_aux) ? nblk : 0u;
+  __syncwarp();
+  if (lane == 0) rec[n.off_aux] = nblk;
 }
 
 template <int W>
@@ -688,7 +693,11 @@ __global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
     if (p.ckpt) p.ckpt[(size_t)warp * M + d] = ck & ~CYG_CKI_REMOVED;
   }
   if (lane < CYG_NSCAL) p.scal[(size_t)warp * CYG_NSCAL + lane] = rec[lane];
-  for (int i = lane; i < n.EW; i += 32) p.blocked[(size_t)warp * n.EW + i] = rec[n.off_blocked + i];
+  for (int i = lane; i < n.EW; i += 32) {
+    uint32_t x = 0;
+    for (int j = 0; j < 32 && i * 32 + j < n.E; j++) x |= (pair_blocked(&n, rec, i * 32 + j) ? 1u : 0u) << j;
+    p.blocked[(size_t)warp * n.EW + i] = x;
+  }
   for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = p.xtra_int[(size_t)warp * n.cfg.xcap + i];
 }
 

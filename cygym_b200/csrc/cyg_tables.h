@@ -24,8 +24,7 @@ struct TableBlob {
   std::vector<uint32_t> words; /* everything, 16-byte aligned sections */
   Net net;                     /* pointers are OFFSETS (in words) until relocate() */
   size_t hot_words;            /* prefix that the step kernel stages in shared memory */
-  size_t o_adj, o_adjT, o_mlo, o_mhi, o_mloT, o_mhiT, o_row_ptr, o_col, o_in_ptr, o_in_eid, o_static, o_dc, o_server,
-      o_reach, o_valid, o_rowmulti, o_incmulti, o_napps, o_vuln, o_os, o_ver, o_out2in, o_in_src, o_emlo, o_emhi, o_eimlo, o_eimhi, o_dmulti;
+  size_t o_adj, o_dc, o_server, o_reach, o_valid, o_napps, o_vuln, o_dinfo, o_unit, o_omulti, o_static, o_pair2unit, o_os, o_ver;
 };
 
 inline size_t tb_alloc(TableBlob& b, size_t nwords) {
@@ -48,57 +47,8 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   const int W = M <= 32 * CYG_MAX_W ? (M + 31) / 32 : CYG_BIG_W; /* large networks: planes padded to 64 words */
   const int EW = E > 0 ? (E + 31) / 32 : 1;
   if (hn.row_ptr[0] != 0 || hn.row_ptr[M] != E) return "row_ptr must start at 0 and end at E";
-  Net& n = b.net;
-  memset(&n, 0, sizeof(n));
-  n.cfg = cfg;
-  n.M = M; n.W = W; n.E = E; n.EW = EW; n.Wm = (M + 31) / 32;
-  n.ncby = cfg.n_exploits > 0 ? cfg.n_exploits : 1;
-  n.NP = P_CBY0 + n.ncby;
-  n.off_blocked = CYG_REC_PLANES + n.NP * W;
-  n.off_blocked_in = n.off_blocked + EW;
-  n.off_aux = n.off_blocked_in + EW;
-  int S = n.off_aux + 1;
-  if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
-  n.S = S;
-  b.words.clear();
-  /* hot section (staged in shared memory by the step kernel) */
-  b.o_adj = tb_alloc(b, (size_t)M * W);
-  b.o_dc = tb_alloc(b, W);
-  b.o_server = tb_alloc(b, W);
-  b.o_reach = tb_alloc(b, W);
-  b.o_valid = tb_alloc(b, W);
-  b.o_rowmulti = tb_alloc(b, W);
-  b.o_incmulti = tb_alloc(b, W);
-  b.o_napps = tb_alloc(b, (size_t)8 * W);
-  b.o_vuln = tb_alloc(b, (size_t)X * W);
-  b.o_row_ptr = tb_alloc(b, M + 1);
-  b.o_col = tb_alloc(b, (E + 1) / 2 + 1);
-  b.o_in_ptr = tb_alloc(b, M + 1);
-  b.o_in_eid = tb_alloc(b, (E + 1) / 2 + 1);
-  b.o_static = tb_alloc(b, M);
-  b.o_out2in = tb_alloc(b, (E + 1) / 2 + 1);
-  b.o_in_src = tb_alloc(b, (E + 1) / 2 + 1);
-  b.o_emlo = tb_alloc(b, EW);
-  b.o_emhi = tb_alloc(b, EW);
-  b.o_eimlo = tb_alloc(b, EW);
-  b.o_eimhi = tb_alloc(b, EW);
-  b.o_dmulti = tb_alloc(b, (size_t)2 * M);
-  b.hot_words = b.words.size();
-  /* cold section: read through L1/L2 (multi-edge weights, in-rows for envs with extra edges, observation rows) */
-  b.o_mlo = tb_alloc(b, (size_t)M * W);
-  b.o_mhi = tb_alloc(b, (size_t)M * W);
-  b.o_adjT = tb_alloc(b, (size_t)M * W);
-  b.o_mloT = tb_alloc(b, (size_t)M * W);
-  b.o_mhiT = tb_alloc(b, (size_t)M * W);
-  b.o_os = tb_alloc(b, M);
-  b.o_ver = tb_alloc(b, M);
-  uint32_t* w = b.words.data();
-  uint16_t* col16 = (uint16_t*)(w + b.o_col);
-  uint16_t* ineid16 = (uint16_t*)(w + b.o_in_eid);
-  int32_t* rp = (int32_t*)(w + b.o_row_ptr);
-  int32_t* ip = (int32_t*)(w + b.o_in_ptr);
-  for (int i = 0; i <= M; i++) rp[i] = hn.row_ptr[i];
-  std::vector<int> indeg(M + 1, 0);
+  /* first pass: validate, degrees in UNITS (a pair of multiplicity m is m units on either side) */
+  std::vector<int> outu(M, 0), inu(M, 0), indeg(M, 0);
   for (int u = 0; u < M; u++) {
     if (hn.row_ptr[u + 1] < hn.row_ptr[u]) return "row_ptr not monotone";
     int prev = -1;
@@ -109,50 +59,80 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
       prev = v;
       int mu = hn.mult ? hn.mult[e] : 1;
       if (mu < 1 || mu > 4) return "edge multiplicity must be in 1..4";
-      col16[e] = (uint16_t)v;
-      w[b.o_adj + (size_t)u * W + (v >> 5)] |= 1u << (v & 31);
-      w[b.o_adjT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31);
-      if ((mu - 1) & 1) { w[b.o_mlo + (size_t)u * W + (v >> 5)] |= 1u << (v & 31); w[b.o_mloT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31); }
-      if ((mu - 1) & 2) { w[b.o_mhi + (size_t)u * W + (v >> 5)] |= 1u << (v & 31); w[b.o_mhiT + (size_t)v * W + (u >> 5)] |= 1u << (u & 31); }
-      if (mu > 1) {
-        w[b.o_rowmulti + (u >> 5)] |= 1u << (u & 31);
-        w[b.o_incmulti + (u >> 5)] |= 1u << (u & 31);
-        w[b.o_incmulti + (v >> 5)] |= 1u << (v & 31);
-      }
-      indeg[v + 1]++;
+      outu[u] += mu; inu[v] += mu; indeg[v]++;
     }
   }
-  for (int i = 0; i < M; i++) indeg[i + 1] += indeg[i];
-  for (int i = 0; i <= M; i++) ip[i] = indeg[i];
-  std::vector<int> fill(M, 0);
-  for (int u = 0; u < M; u++) /* ascending u => in-lists ascending by source */
-    for (int e = hn.row_ptr[u]; e < hn.row_ptr[u + 1]; e++) {
-      int v = hn.col[e];
-      int j = indeg[v] + fill[v]++;
-      ineid16[j] = (uint16_t)e;
-      ((uint16_t*)(w + b.o_out2in))[e] = (uint16_t)j;
-      ((uint16_t*)(w + b.o_in_src))[j] = (uint16_t)u;
-      int mu = hn.mult ? hn.mult[e] : 1;
-      if ((mu - 1) & 1) { w[b.o_emlo + (e >> 5)] |= 1u << (e & 31); w[b.o_eimlo + (j >> 5)] |= 1u << (j & 31); }
-      if ((mu - 1) & 2) { w[b.o_emhi + (e >> 5)] |= 1u << (e & 31); w[b.o_eimhi + (j >> 5)] |= 1u << (j & 31); }
-    }
-  /* packed multi-edge entries of every device's out list and in list */
-  for (int i = 0; i < M; i++) {
-    for (int side = 0; side < 2; side++) {
-      int lo = side ? ip[i] : rp[i], hi = side ? ip[i + 1] : rp[i + 1];
-      uint32_t dm = 0xFFu | (0xFFu << 10);
-      int cnt = 0;
-      for (int p = lo; p < hi; p++) {
-        int e = side ? ineid16[p] : p;
-        int mu = hn.mult ? hn.mult[e] : 1;
-        if (mu <= 1) continue;
-        if (cnt >= 2 || p - lo >= 0xFF) { dm |= 0x80000000u; continue; }
-        dm &= ~(0x3FFu << (10 * cnt));
-        dm |= ((uint32_t)(p - lo) | ((uint32_t)(mu - 1) << 8)) << (10 * cnt);
-        cnt++;
+  /* evolve_network's preferential-attachment repair (CyberDefenseEnv.py:776-843) fires for a newly activated vertex of
+   * total degree 0 and draws random.uniform; the kernels leave that branch out, so such a network is refused loudly */
+  for (int i = 0; i < M; i++)
+    if (indeg[i] == 0 && hn.row_ptr[i + 1] == hn.row_ptr[i] && M > 1)
+      return "device " + std::to_string(i) + " has no incident edge: the preferential-attachment repair of evolve_network "
+             "(CyberDefenseEnv.py:776-843) is not part of the kernels";
+  std::vector<int> ip(M + 1, 0);
+  for (int i = 0; i < M; i++) ip[i + 1] = ip[i] + outu[i] + inu[i];
+  const int U2 = ip[M];
+  if (U2 > 65535) return "more than 65535 incidence units (2 x sum of edge multiplicities)";
+  for (int i = 0; i < M; i++) if (outu[i] > 65535) return "out-degree out of range";
+  const int UW = U2 > 0 ? (U2 + 31) / 32 : 1;
+  Net& n = b.net;
+  memset(&n, 0, sizeof(n));
+  n.cfg = cfg;
+  n.M = M; n.W = W; n.E = E; n.EW = EW; n.Wm = (M + 31) / 32; n.U2 = U2; n.UW = UW;
+  n.ncby = cfg.n_exploits > 0 ? cfg.n_exploits : 1;
+  n.NP = P_CBY0 + n.ncby;
+  n.off_inc = CYG_REC_PLANES + n.NP * W;
+  n.off_aux = n.off_inc + UW;
+  int S = n.off_aux + 1;
+  if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
+  n.S = S;
+  b.words.clear();
+  /* hot section (staged in shared memory by the step kernel) */
+  b.o_adj = tb_alloc(b, (size_t)M * W);
+  b.o_dc = tb_alloc(b, W);
+  b.o_server = tb_alloc(b, W);
+  b.o_reach = tb_alloc(b, W);
+  b.o_valid = tb_alloc(b, W);
+  b.o_napps = tb_alloc(b, (size_t)8 * W);
+  b.o_vuln = tb_alloc(b, (size_t)X * W);
+  b.o_dinfo = tb_alloc(b, M + 1);
+  b.o_unit = tb_alloc(b, (size_t)U2 + 1);
+  b.o_omulti = tb_alloc(b, M);
+  b.o_static = tb_alloc(b, M);
+  b.hot_words = b.words.size();
+  /* cold section: read through L1/L2 (canonical pair <-> unit map for import / export, observation rows) */
+  b.o_pair2unit = tb_alloc(b, (size_t)E + 1);
+  b.o_os = tb_alloc(b, M);
+  b.o_ver = tb_alloc(b, M);
+  uint32_t* w = b.words.data();
+  for (int i = 0; i <= M; i++) w[b.o_dinfo + i] = (uint32_t)ip[i] | ((uint32_t)(i < M ? outu[i] : 0) << 16);
+  /* incidence units: device d owns [ip[d], ip[d+1]): its out-units (ascending neighbour id, a pair of multiplicity m
+   * as m adjacent units -- the order of _outnbrs, volt:456-473), then its in-units (ascending source id).  Entry of a
+   * unit: twin run start | far endpoint << 16 | (m - 1) << 28 | offset inside its own run << 30. */
+  std::vector<int> ofill(M, 0), ifill(M, 0);
+  for (int u = 0; u < M; u++) { /* ascending u => in-lists ascending by source */
+    int pairs = 0, multi_cnt = 0;
+    uint32_t dm = 0xFFu | (0xFFu << 10);
+    for (int e = hn.row_ptr[u]; e < hn.row_ptr[u + 1]; e++, pairs++) {
+      const int v = hn.col[e];
+      const int mu = hn.mult ? hn.mult[e] : 1;
+      const int so = ip[u] + ofill[u], si = ip[v] + outu[v] + ifill[v];
+      ofill[u] += mu; ifill[v] += mu;
+      for (int k = 0; k < mu; k++) {
+        w[b.o_unit + so + k] = (uint32_t)si | ((uint32_t)v << 16) | ((uint32_t)(mu - 1) << 28) | ((uint32_t)k << 30);
+        w[b.o_unit + si + k] = (uint32_t)so | ((uint32_t)u << 16) | ((uint32_t)(mu - 1) << 28) | ((uint32_t)k << 30);
       }
-      w[b.o_dmulti + 2 * i + side] = dm;
+      w[b.o_pair2unit + e] = (uint32_t)so;
+      w[b.o_adj + (size_t)u * W + (v >> 5)] |= 1u << (v & 31);
+      if (mu > 1) { /* packed multi-edge runs of the out list: pair rank | (m - 1) << 8, two entries; bit 31: more */
+        if (multi_cnt >= 2 || pairs >= 0xFF) dm |= 0x80000000u;
+        else {
+          dm &= ~(0x3FFu << (10 * multi_cnt));
+          dm |= ((uint32_t)pairs | ((uint32_t)(mu - 1) << 8)) << (10 * multi_cnt);
+          multi_cnt++;
+        }
+      }
     }
+    w[b.o_omulti + u] = dm;
   }
   for (int i = 0; i < M; i++) {
     uint32_t st = hn.dev_static[i];
@@ -180,15 +160,11 @@ inline void relocate(const TableBlob& b, const uint32_t* base, Net& n) {
   n.blob = base;
   n.hot_words = (uint32_t)b.hot_words;
   n.inv_M = 1.0 / (double)n.M;
-  n.o_adj = (uint32_t)b.o_adj; n.o_adjT = (uint32_t)b.o_adjT;
-  n.o_mlo = (uint32_t)b.o_mlo; n.o_mhi = (uint32_t)b.o_mhi; n.o_mloT = (uint32_t)b.o_mloT; n.o_mhiT = (uint32_t)b.o_mhiT;
-  n.o_row_ptr = (uint32_t)b.o_row_ptr; n.o_col = (uint32_t)b.o_col; n.o_in_ptr = (uint32_t)b.o_in_ptr;
-  n.o_in_eid = (uint32_t)b.o_in_eid; n.o_out2in = (uint32_t)b.o_out2in; n.o_in_src = (uint32_t)b.o_in_src; n.o_static = (uint32_t)b.o_static;
+  n.o_adj = (uint32_t)b.o_adj;
   n.o_dc = (uint32_t)b.o_dc; n.o_server = (uint32_t)b.o_server; n.o_reach = (uint32_t)b.o_reach; n.o_valid = (uint32_t)b.o_valid;
-  n.o_rowmulti = (uint32_t)b.o_rowmulti; n.o_incmulti = (uint32_t)b.o_incmulti; n.o_napps = (uint32_t)b.o_napps;
-  n.o_vuln = (uint32_t)b.o_vuln;
-  n.o_dmulti = (uint32_t)b.o_dmulti;
-  n.o_emlo = (uint32_t)b.o_emlo; n.o_emhi = (uint32_t)b.o_emhi; n.o_eimlo = (uint32_t)b.o_eimlo; n.o_eimhi = (uint32_t)b.o_eimhi;
+  n.o_napps = (uint32_t)b.o_napps; n.o_vuln = (uint32_t)b.o_vuln;
+  n.o_dinfo = (uint32_t)b.o_dinfo; n.o_unit = (uint32_t)b.o_unit; n.o_omulti = (uint32_t)b.o_omulti; n.o_static = (uint32_t)b.o_static;
+  n.o_pair2unit = (uint32_t)b.o_pair2unit;
   n.o_os = (uint32_t)b.o_os; n.o_ver = (uint32_t)b.o_ver;
 }
 

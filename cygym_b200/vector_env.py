@@ -123,8 +123,16 @@ class VectorCyberDefenseEnv:
     def launch_count(self):
         return int(self.L.cyg_launch_count(self.h)) + self._graph_launches
 
+    def _drop_graphs(self):
+        """A captured step_host() graph holds the kernel parameters BY VALUE (base_line, the per-env base_line
+        pointer and stride, the debug buffer): whatever changes one of them must drop the captures."""
+        if self._graphs:
+            torch.cuda.synchronize(self.device)
+            self._graphs = {}
+
     def set_base_line(self, name):
         self.base_line = name
+        self._drop_graphs()
         K.check(self.L.cyg_set_base_line(self.h, K.BASE_LINES.get(name, 4)))
 
     def set_base_line_per_env(self, codes):
@@ -133,6 +141,7 @@ class VectorCyberDefenseEnv:
         if codes is not None:
             codes = codes.to(self.device, torch.uint8).contiguous()
         self._bl_env = codes
+        self._drop_graphs()
         if codes is not None and codes.dim() == 2:
             assert codes.shape[1] == self.B
             K.check(self.L.cyg_set_base_line_per_env_steps(self.h, _ptr(codes), int(codes.shape[0])))

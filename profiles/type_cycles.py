@@ -31,7 +31,7 @@ for t in range(40):
     if t >= 36:
         cyc = dbg.cpu().numpy()
         at = (ab.hdr[:, 0] & 0xFF).cpu().numpy()
-        nd = ab.hdr[:, 2].cpu().numpy()
+        nd = (ab.hdr[:, 2] & 0xFFFF).cpu().numpy()
         print(f"t={t} mode={'att' if mode else 'def'} launch {e0.elapsed_time(e1) * 1e3:.1f} us; per type: mean / p50 / max cycles (n, mean n_dev)")
         for a in sorted(set(at.tolist())):
             m = at == a

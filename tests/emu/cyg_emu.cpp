@@ -35,10 +35,10 @@ static void import_env(const Net& n, uint32_t* rec, const uint32_t* dev, const u
     import_device<W>(&n, rec, d, dev[d]);
     if (ckpt) ckpt[d] = (ckpt[d] & ~CYG_CKI_REMOVED) | ((dev[d] & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u);
   }
-  for (int i = 0; i < n.EW; i++) { rec[n.off_blocked + i] = blocked[i]; rec[n.off_aux] += (uint32_t)__builtin_popcount(blocked[i]); }
-  for (int j = 0; j < n.E; j++) {
-    int e = (int)((n.blob[n.o_in_eid + (j >> 1)] >> ((j & 1) * 16)) & 0xFFFFu);
-    if ((blocked[e >> 5] >> (e & 31)) & 1u) rec[n.off_blocked_in + (j >> 5)] |= 1u << (j & 31);
+  for (int e = 0; e < n.E; e++) {
+    if (!((blocked[e >> 5] >> (e & 31)) & 1u)) continue;
+    rec[n.off_aux]++;
+    pair_units(&n, e, [&](int wi, uint32_t m) { rec[n.off_inc + wi] |= m; });
   }
 }
 template <int W>
@@ -49,7 +49,8 @@ static void export_env(const Net& n, const uint32_t* rec, uint32_t* dev, uint32_
     dev[d] = export_device<W>(&n, rec, d, ckpt ? ckpt[d] : ((dev[d] & CYG_DEV_REMOVED) ? CYG_CKI_REMOVED : 0u));
     if (ckpt) ckpt[d] &= ~CYG_CKI_REMOVED;
   }
-  for (int i = 0; i < n.EW; i++) blocked[i] = rec[n.off_blocked + i];
+  for (int i = 0; i < n.EW; i++) blocked[i] = 0;
+  for (int e = 0; e < n.E; e++) if (pair_blocked(&n, rec, e)) blocked[e >> 5] |= 1u << (e & 31);
 }
 
 template <int W>

@@ -263,6 +263,48 @@ def test_step_host_matches_device_step():
     assert b.launch_count >= 13
 
 
+def test_step_host_follows_base_line_changes():
+    """A captured step_host() graph holds the kernel parameters by value: set_base_line() / set_base_line_per_env()
+    between two replays must reach the next step (the captures are dropped), as they do for step()."""
+    import torch
+    from cygym_b200 import synthetic_network
+    from cygym_b200.vector_env import VectorCyberDefenseEnv
+    net = synthetic_network(100, n_subnets=8, seed=2)
+    B = 1500
+    a = VectorCyberDefenseEnv(net, B, seed=9)
+    b = VectorCyberDefenseEnv(net, B, seed=9)
+    hdr_h, mask_h, _ = b.host_buffers()
+
+    def both(t):
+        ab = a.sample_actions(t & 1)
+        b.sample_actions(t & 1)
+        torch.cuda.synchronize()
+        r = [x.clone().cpu() for x in a.step(ab)]
+        hdr_h.copy_(ab.hdr.cpu()); mask_h.copy_(ab.mask.cpu())
+        raw, shaped, done = b.step_host()
+        assert torch.equal(raw, r[0]) and torch.equal(shaped, r[1]) and torch.equal(done, r[2]), t
+
+    for t in range(4):
+        both(t)                     # captured at t = 0, replayed afterwards
+    for e in (a, b):
+        e.set_base_line("No Defense")
+    for t in range(4, 8):
+        both(t)
+    codes = (torch.arange(B, device="cuda") % 4).to(torch.uint8)
+    for e in (a, b):
+        e.set_base_line_per_env(codes)
+    for t in range(8, 12):
+        both(t)
+    for e in (a, b):
+        e.set_base_line_per_env(None)
+        e.set_base_line("Nash")
+    for t in range(12, 14):
+        both(t)
+    ca, cb = a.export_state(), b.export_state()
+    for k in ca:
+        assert torch.equal(ca[k], cb[k]), k
+
+
 def test_step_host_two_groups_async():
     """Two env groups on two streams driven through step_host(sync=False) / wait_host() (the double-buffered rollout
     loop of bench.py's e2e leg) give the same rewards and states as the synchronous device steps."""
