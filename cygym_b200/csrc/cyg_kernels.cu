@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hdr_t + ((size_t)p.B + env0 + tid) * 4));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_t + ((size_t)p.B + env0 + tid) * W));
   }
-  if (tid < CYG_NKEYS + 7) s_cnt[tid] = 0;
+  for (int i = tid; i < CYG_NKEYS + 7; i += NT) s_cnt[i] = 0; /* ... + one "past pass 0" flag per owning warp */
   __syncthreads(); /* mbarrier initialised, counters zeroed (t > 0: the previous step is complete) */
   CYG_CTA_MARK(1);
 
@@ -245,260 +245,172 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   __syncthreads();
   CYG_CTA_MARK(2);
 
-  /* ---- phase A, thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or
-   *      -- for the draw-heavy defender actions -- hand the env to phase B ---- */
+  /* ---- the step in two passes over ONE copy of the thread-per-env code (the loop is not unrolled: step_post alone
+   *      is ~10k SASS instructions, and the kernel's instruction footprint is what its warps miss on):
+   *      pass 0  thread per env (env perm[tid]): epoch + busy tick, then either the whole rest of the step, or -- for
+   *              the draw-heavy actions -- the env is handed to phase B;
+   *      pass 1  phase B, warp per env, then the rest of the step (step_post) of those envs by their own threads.
+   *      After either pass a warp sends the records its threads finished home (one warp-wide copy per record), so the
+   *      write-back of the ~2/3 of the block that phase A completes drains under phase B. ---- */
   constexpr bool coop_ok = PLAIN;
   const bool lower = (tid & ~31) < nb; /* warps that own envs in the thread-per-env phases */
   bool deferred = false;
   const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
-  uint32_t dmask = 0;
-  {
-    Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
-                   (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
-    uint32_t act[4 + W]; /* this env's action (group 0), in registers */
-    const uint16_t* ord = (!PLAIN && p.order) ? p.order + (size_t)env * p.order_stride : nullptr;
-    long long t_begin = 0;
+  Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+                 (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
+  long long t_begin = 0;
 #ifdef CYG_PHASE_TIMING
-    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    e.phase_t = ph;
+  long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  e.phase_t = ph;
 #endif
-    int mode = 0, atype = 0;
-    if (tid < nb) {
-      uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env * 4);
-      act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
-#pragma unroll
-      for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env * W + w];
-      t_begin = p.dbg_cycles ? clock64() : 0;
-      mode = (int)((act[0] >> 8) & 1u);
-      if (bl_t) e.bl = (int)bl_t[env];
-      atype = e.step_pre(act, p.flags);
-      deferred = coop_ok && Coop<W>::is_heavy(e, mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
+  int mode = 0;
+  uint32_t home_mask = 0; /* lanes of this warp whose env's record is finished and not yet sent home (uniform) */
+  auto send_some = [&](int k) {
+    while (home_mask && k-- > 0) {
+      const int src = __ffs((int)home_mask) - 1;
+      home_mask &= home_mask - 1u;
+      const int el_s = __shfl_sync(0xFFFFFFFFu, el, src);
+      copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
     }
-    if (coop_ok) {
-      /* once every env has its epoch open and its busy tick done (s_cnt[CYG_NKEYS + 6] counts the owning warps that
-       * got there) phase B may touch any deferred env: the warps that own no env start it right away, the owning
-       * warps join after their thread-per-env work -- and check the same counter, a warp whose envs are all deferred
-       * gets to phase B before the others are through step_pre */
-      dmask = __ballot_sync(0xFFFFFFFFu, deferred);
-      if (lower) {
+  };
+#pragma unroll /* two copies of the thread-per-env code: un-unrolled, ptxas spills inside the warp-per-env routines (measured slower) */
+  for (int pass = 0; pass < (PLAIN ? 2 : 1); pass++) {
+    double cost = 0.0;
+    bool dirty = false, do_post = false;
+    if (pass == 0) {
+      uint32_t act[4 + W]; /* this env's action (group 0), in registers */
+      const uint16_t* ord = (!PLAIN && p.order) ? p.order + (size_t)env * p.order_stride : nullptr;
+      int atype = 0;
+      if (tid < nb) {
+        uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env * 4);
+        act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+        for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env * W + w];
+        t_begin = p.dbg_cycles ? clock64() : 0;
+        mode = (int)((act[0] >> 8) & 1u);
+        if (bl_t) e.bl = (int)bl_t[env];
+        atype = e.step_pre(act, p.flags);
+        deferred = coop_ok && Coop<W>::is_heavy(e, mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
+      }
+      if (coop_ok) {
+        /* once every env has its epoch open and its busy tick done (s_cnt[CYG_NKEYS + 6] counts the owning warps that
+         * got there) phase B may touch any deferred env: the warps that own no env start it right away, the owning
+         * warps join after their thread-per-env work -- and check the same counter, a warp whose envs are all deferred
+         * gets to phase B before the others are through step_pre */
+        const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, deferred);
+        if (lower) {
+          __syncwarp();
+          if (lane == 0) { s_def[tid >> 5] = dmask; __threadfence_block(); atomicAdd(&s_cnt[CYG_NKEYS + 6], 1u); }
+        }
+      }
+      if (tid < nb && !deferred) {
+        if (PLAIN) e.template step_act<true>(act, act + 4, nullptr, 0, 0, 0, 1, p.flags, atype, cost, dirty);
+        else if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
+        else e.step_act(hdr_t + (size_t)env * 4, mask_t + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
+                        (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
+        do_post = true;
+      }
+    } else {
+      if constexpr (PLAIN) {
+  CYG_CTA_MARK(3);
+        if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
         __syncwarp();
-        if (lane == 0) { s_def[tid >> 5] = dmask; __threadfence_block(); atomicAdd(&s_cnt[CYG_NKEYS + 6], 1u); }
+        auto load_action = [&](int env_b, uint32_t* act) {
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4)); /* phase A read these lines: L1 */
+          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
+#pragma unroll
+          for (int w = 0; w < W; w++) act[4 + w] = __ldg(mask_t + (size_t)env_b * W + w);
+        };
+        /* B1: block / unblock (keys 6, 9; the longest lists first), B2: attacker exploit + lateral movement (key 16|1),
+         * B3: clean / revert / upgrade (keys 1, 3, 4).  One env per warp; perm[] holds each kind as a contiguous run. */
+#pragma unroll
+        for (int kind = 0; kind < 3; kind++) {
+          int lo0, n0, lo1 = 0, n1 = 0, lo2 = 0, n2 = 0;
+          if (kind == 0) { lo0 = (int)s_cnt[CYG_KEY_FLIP0]; n0 = (int)s_cnt[CYG_NKEYS] - lo0; }
+          else if (kind == 1) { lo0 = (int)s_cnt[17]; n0 = (int)s_cnt[18] - lo0; }
+          else {
+            lo0 = (int)s_cnt[1]; n0 = (int)s_cnt[2] - lo0; lo1 = (int)s_cnt[3]; n1 = (int)s_cnt[4] - lo1;
+            lo2 = (int)s_cnt[4]; n2 = (int)s_cnt[5] - lo2;
+          }
+          const int ntasks = n0 + n1 + n2;
+          for (;;) {
+            int task = 0;
+            if (lane == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 1 + kind], 1u);
+            task = __shfl_sync(0xFFFFFFFFu, task, 0);
+            if (task >= ntasks) break;
+            const int ppos = task < n0 ? lo0 + task : (task < n0 + n1 ? lo1 + task - n0 : lo2 + task - n0 - n1);
+            if (!((s_def[ppos >> 5] >> (ppos & 31)) & 1u)) continue; /* its own thread did it in phase A */
+            const int el_b = s_perm[ppos];
+            const int env_b = env0 + el_b;
+            Env<W, true> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
+                            (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+            eb.resume_epoch();
+            uint32_t act[4 + W];
+            load_action(env_b, act);
+            typename Env<W, true>::Act a;
+            Env<W, true>::decode(act, act + 4, nullptr, a);
+            double tcost = 0.0;
+            bool tdirty = false;
+            long long tb0 = p.dbg_cycles ? clock64() : 0;
+            if (lane == 0) eb.load_costs();
+            if (kind == 0) {
+              Coop<W>::template flip<32>(eb, a, (int)(act[0] & 0xFFu), tcost, tdirty); /* flip keys only hold executed types 6 / 9 == the header's */
+            } else if (kind == 1) {
+              Coop<W>::attack(eb, a);
+            } else {
+              const int atype_b = Env<W, true>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
+              Coop<W>::defender(eb, a, atype_b, tcost, tdirty);
+            }
+            if (lane == 0) {
+#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
+              if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0); /* heavy envs: phase-B cycles */
+#endif
+#ifdef CYG_COUNT_ROUNDS
+              if (p.dbg_cycles && kind == 0) p.dbg_cycles[env_b] = (unsigned long long)eb.dbg_rounds;
+#endif
+              eb.store_costs();
+              s_out[el_b] = (float)tcost;
+              s_out[NB + el_b] = __int_as_float(tdirty ? 1 : 0);
+            }
+            __syncwarp();
+          }
+          CYG_WARP_MARK(kind);
+        }
+        __syncthreads();
+  CYG_CTA_MARK(4);
+        /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
+        if (deferred) {
+          e = Env<W, true>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
+                           (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4)); /* nothing of it stays live across phase B */
+          if (bl_t) e.bl = (int)bl_t[env];
+          e.resume_epoch();
+          cost = (double)s_out[el];
+          dirty = __float_as_int(s_out[NB + el]) != 0;
+          do_post = true;
+        }
       }
     }
-    if (tid < nb && !deferred) {
-      double cost = 0.0;
-      bool dirty = false;
-      if (PLAIN) e.template step_act<true>(act, act + 4, nullptr, 0, 0, 0, 1, p.flags, atype, cost, dirty);
-      else if (!grouped) e.step_act(act, act + 4, ord, 0, 0, 0, 1, p.flags, atype, cost, dirty);
-      else e.step_act(hdr_t + (size_t)env * 4, mask_t + (size_t)env * W, ord, (size_t)p.B * 4, (size_t)p.B * W,
-                      (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
+    if (do_post) {
       float raw, shaped;
       int32_t done;
       e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
       raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done;
     }
-    if (tid < nb) {
+    if (pass == 0 && tid < nb) {
 #ifdef CYG_PHASE_TIMING
       if (p.dbg_cycles) for (int i = 0; i < 8; i++) p.dbg_cycles[(size_t)env * 8 + i] = (unsigned long long)(ph[i] - t_begin);
 #elif !defined(CYG_CTA_TIMING)
-      if (p.dbg_cycles) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
+      if (p.dbg_cycles && !deferred) p.dbg_cycles[env] = (unsigned long long)(clock64() - t_begin);
 #endif
     }
-  }
-
-  /* ---- phase B, warp per env: clean / revert / upgrade / block / unblock with 32 lanes on the listed devices.
-   *      The sort put those envs in contiguous runs of perm[]; warps pull them from a shared counter. ---- */
-  if constexpr (PLAIN) {
-  CYG_CTA_MARK(3);
-    if (lower) { /* this warp's thread-per-env work is done and visible */
-      __syncwarp();
-      if (lane == 0) { __threadfence_block(); atomicAdd(&s_cnt[CYG_NKEYS + 5], 1u); }
-    }
-    if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
-    __syncwarp();
-    /* The records phase A finished go home while phase B runs (coalesced 4-byte stores, one warp per record): every
-     * warp sends up to `k` of them after each of its tasks, so the write-back is spread over the phase instead of
-     * hitting the memory system from all SMs at once; the end of the kernel only has the deferred records left.
-     * s_cnt[CYG_NKEYS + 5] = owning warps past phase A (nothing is sent before all of them are),
-     * s_cnt[CYG_NKEYS + 4] = next position of perm[] to look at. */
-    bool home_ready = false; /* this warp has seen every owning warp past phase A */
-    auto copy_home = [&](int pos) { /* one finished record */
-      const int el_s = s_perm[pos];
-      copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
-    };
-    auto send_home = [&](bool all) { /* claim 4 positions of perm[] at a time (all: until none is left) */
-      if (!last) return; /* fused steps: the records only go home after the last one */
-      if (!home_ready) {
-        int ready = 0;
-        if (lane == 0) {
-          if (all) while (atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(64);
-          ready = atomicAdd(&s_cnt[CYG_NKEYS + 5], 0u) >= (uint32_t)((nb + 31) >> 5);
-        }
-        home_ready = __shfl_sync(0xFFFFFFFFu, ready, 0) != 0;
-        if (!home_ready) return;
-      }
-      do {
-        int pos = 0;
-        if (lane == 0) pos = (int)atomicAdd(&s_cnt[CYG_NKEYS + 4], 4u);
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (pos >= nb) return;
-        const uint32_t dw = s_def[pos >> 5] >> (pos & 31); /* pos is a multiple of 4: the 4 bits sit in one word */
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (pos + j < nb && !((dw >> j) & 1u)) copy_home(pos + j);
-      } while (all);
-    };
-    /* B1: block / unblock (keys 6, 9; the longest tasks first), one env per group of G lanes.  G = 32: narrower
-     * groups were measured slower (the groups of a warp diverge and no longer issue together). */
-    {
-      constexpr int G = 32;
-      const int lg = lane % G, gbase = lane - lg;
-      const uint32_t gm = (G == 32) ? 0xFFFFFFFFu : (((1u << (G & 31)) - 1u) << gbase);
-      const int lof = (int)s_cnt[CYG_KEY_FLIP0], nf = (int)s_cnt[CYG_NKEYS] - lof; /* keys 32..47 are one run of perm[] */
-      for (;;) {
-        int task = 0;
-        if (lg == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 1], 1u);
-        task = __shfl_sync(gm, task, gbase);
-        if (task >= nf) break;
-        if (!((s_def[(lof + task) >> 5] >> ((lof + task) & 31)) & 1u)) continue; /* no extra edges: its own thread did it in phase A */
-        const int el_b = s_perm[lof + task];
-        const int env_b = env0 + el_b;
-        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
-                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
-        e.resume_epoch();
-        uint32_t act[4 + W];
-        {
-          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
-          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
-#pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
-        }
-        typename Env<W, true>::Act a;
-        Env<W, true>::decode(act, act + 4, nullptr, a);
-        double cost = 0.0;
-        bool dirty = false;
-        long long tb0 = p.dbg_cycles ? clock64() : 0;
-        if (lg == 0) e.load_costs();
-        Coop<W>::template flip<G>(e, a, (int)(act[0] & 0xFFu), cost, dirty); /* flip keys only hold executed types 6 / 9 == the header's */
-        if (lg == 0) {
-#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
-          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
-#endif
-#ifdef CYG_COUNT_ROUNDS
-          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)e.dbg_rounds;
-#endif
-          e.store_costs();
-          s_out[el_b] = (float)cost;
-          s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
-        }
-        __syncwarp(gm);
-        send_home(false);
-      }
-    }
-    __syncwarp();
-    CYG_WARP_MARK(0);
-    /* B2: clean / revert / upgrade (keys 1, 3, 4), one env per warp: 32 lanes = the 32 devices of a plane word */
-    {
-      const int heavy_keys[3] = {1, 3, 4};
-      int ntasks = 0;
-#pragma unroll
-      for (int i = 0; i < 3; i++) ntasks += (int)(s_cnt[heavy_keys[i] + 1] - s_cnt[heavy_keys[i]]);
-      for (;;) {
-        int task = 0;
-        if (lane == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 2], 1u);
-        task = __shfl_sync(0xFFFFFFFFu, task, 0);
-        if (task >= ntasks) break;
-        int ppos = -1, rem = task;
-#pragma unroll
-        for (int i = 0; i < 3; i++) { /* s_cnt[k] .. s_cnt[k+1] = run of key k in perm[] (k >= 1) */
-          const int lo = (int)s_cnt[heavy_keys[i]], n_k = (int)s_cnt[heavy_keys[i] + 1] - lo;
-          const bool here = ppos < 0 && rem < n_k;
-          ppos = here ? lo + rem : ppos;
-          rem -= (ppos < 0) ? n_k : 0;
-        }
-        const int el_b = s_perm[ppos];
-        const int env_b = env0 + el_b;
-        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
-                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
-        e.resume_epoch();
-        uint32_t act[4 + W];
-        {
-          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
-          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
-#pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
-        }
-        typename Env<W, true>::Act a;
-        Env<W, true>::decode(act, act + 4, nullptr, a);
-        const int atype = Env<W, true>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
-        double cost = 0.0;
-        bool dirty = false;
-        long long tb0 = p.dbg_cycles ? clock64() : 0;
-        if (lane == 0) e.load_costs();
-        Coop<W>::defender(e, a, atype, cost, dirty);
-        if (lane == 0) {
-#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
-          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0); /* heavy envs: phase-B cycles */
-#endif
-          e.store_costs();
-          s_out[el_b] = (float)cost;
-          s_out[NB + el_b] = __int_as_float(dirty ? 1 : 0);
-        }
-        __syncwarp();
-        send_home(false);
-      }
-    }
-    CYG_WARP_MARK(1);
-    /* B3: attacker exploit + lateral movement (key 16|1), one env per warp */
-    {
-      const int lo = (int)s_cnt[17], ntasks = (int)s_cnt[18] - lo;
-      for (;;) {
-        int task = 0;
-        if (lane == 0) task = (int)atomicAdd(&s_cnt[CYG_NKEYS + 3], 1u);
-        task = __shfl_sync(0xFFFFFFFFu, task, 0);
-        if (task >= ntasks) break;
-        const int el_b = s_perm[lo + task];
-        const int env_b = env0 + el_b;
-        if ((bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line) == CYG_BL_NO_ATTACK) continue; /* phase A did it */
-        Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
-                       (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
-        e.resume_epoch();
-        uint32_t act[4 + W];
-        {
-          uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4);
-          act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
-#pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env_b * W + w];
-        }
-        typename Env<W, true>::Act a;
-        Env<W, true>::decode(act, act + 4, nullptr, a);
-        long long tb0 = p.dbg_cycles ? clock64() : 0;
-        Coop<W>::attack(e, a);
-        if (lane == 0) {
-#if !defined(CYG_PHASE_TIMING) && !defined(CYG_CTA_TIMING)
-          if (p.dbg_cycles) p.dbg_cycles[env_b] = (unsigned long long)(clock64() - tb0);
-#endif
-          s_out[el_b] = 0.f;
-          s_out[NB + el_b] = __int_as_float(0);
-        }
-        __syncwarp();
-        send_home(false);
-      }
-    }
-    CYG_WARP_MARK(2);
-    send_home(true); /* B4: whatever is left of the finished records */
-    __syncthreads();
-  CYG_CTA_MARK(4);
-    /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
-    if (deferred) {
-      Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
-                     (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
-      e.resume_epoch();
-      float raw, shaped;
-      int32_t done;
-      e.step_post((int)((hdr_t[(size_t)env * 4] >> 8) & 1u), (double)s_out[el], __float_as_int(s_out[NB + el]) != 0, p.flags, &raw, &shaped, &done,
-                  p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-      raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done;
+    if (PLAIN && last && lower) {
+      /* The records this warp's threads just finished go home by warp-wide copies, right away.  Measured alternatives:
+       * 4 records after each phase-B task of the warp (38.3 / 50.5 us fused / single against 37.8 / 48.1), a shared
+       * claim counter with 4 records per claim (37.8 / 49.5), ONE warp copying for the whole block (45.1 / 67.5: a
+       * single warp cannot keep enough stores in flight), per-warp step_post batches right after the warp's phase-B
+       * tasks instead of the barrier + phase C (42.3 / 49.1: the ~10k-cycle chain runs with a handful of lanes). */
+      home_mask = __ballot_sync(0xFFFFFFFFu, do_post);
+      send_some(32);
     }
   }
   __syncthreads();
@@ -516,12 +428,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   }
 
   /* ---- write the block's records back ---- */
-  if constexpr (PLAIN) { /* the records of phase A are on their way already: one warp per deferred record */
-    for (int pos = tid >> 5; pos < nb; pos += NT >> 5) {
-      if (!((s_def[pos >> 5] >> (pos & 31)) & 1u)) continue;
-      const int el_s = s_perm[pos];
-      copy_record(g_rec + (size_t)el_s * S, s_rec + el_s * S, S, lane);
-    }
+  if constexpr (PLAIN) { /* every warp sent its records home already */
     CYG_CTA_MARK(6);
   } else
 #ifdef CYG_TMA_STORE
