@@ -7,12 +7,20 @@
 Workload (config.workload "C3"): 65 536 envs x 100 device slots / 8 subnets per GPU, synthetic network
 (cygym_b200.network.synthetic_network), uniformly random sample_action()-style defender / attacker
 actions on alternating turns, detector untrained (defender action 10 rewritten to the no-op 8).
-A "step" is ONE launch of cyg_step over one batch of B envs.  Envs shard across GPUs with no
+A "step" is ONE pass of cyg_step over one batch of B envs.  Envs shard across GPUs with no
 data-path collective (weak scaling: B envs per GPU); NCCL only carries the timing reduction.
 
-L2 policy: the bench rotates over `--sets` independent env sets (default 3 x 57 MB of state
+L2 policy: the C3 legs rotate over `--sets` independent env sets (default 3 x 59 MB of state
 > 126 MB L2) and a ring of pre-generated action batches, so a launch never finds its records
-in L2 from the previous launch.
+in L2 from the previous launch.  The small-state legs (C2, C4) write a 256 MB buffer between
+launches and are timed per launch with CUDA events.
+
+One JSON line.  Besides the contract keys it carries `single_step_launch` (the same workload at
+one launch per step) and `legs`: the same kernel on the other shapes callers use --
+`randomized` (after randomize_compromise_and_ownership: every Double-Oracle rollout), `obs_on`
+(observation rows materialised every step), `grouped` (13-group step_grouped: the IPPO / MAPPO
+rollout shape), `c2` (4096 x 50) and `c4` (1024 x 2000) -- each with its own roofline fraction
+(at N = 1 only: they are diagnostics of the kernel, not scaling points).
 """
 import argparse
 import json
@@ -28,6 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec at 64K envs x 100 devices"
 UNIT = "env-steps/s"
+PREHEAT = 8  # untimed launches before every timed region, whatever --warmup says
 
 
 def parse():
@@ -42,18 +51,26 @@ def parse():
     ap.add_argument("--sets", type=int, default=3, help="independent env sets rotated to defeat L2 residency")
     ap.add_argument("--ring", type=int, default=8, help="pre-generated action batches per mode")
     ap.add_argument("--fuse", type=int, default=4, help="plain steps fused per launch (VectorCyberDefenseEnv.step_many / cyg_step_multi); 1 = one launch per step")
-    ap.add_argument("--randomize", action="store_true", help="randomize_compromise_and_ownership() on every env set first (diagnostic: "
-                    "the owned set moves, evolve_network adds extra hub-star edges, and the steps take the kernels' extra-edge forms)")
+    ap.add_argument("--randomize", action="store_true", help="headline on envs after randomize_compromise_and_ownership() (the `randomized` leg as the main line)")
     ap.add_argument("--obs", type=int, default=0, help="fused observation mode inside the step (0 none, 1 defender, 2 attacker)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=240, help="host-buffer steps of the e2e leg (fixed: the leg is host / PCIe paced and noisy when short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
 
 
 def workload_name(a):
     return f"C3: {a.envs} envs x {a.devices} device slots / {a.subnets} subnets per GPU, random sample_action defender/attacker turns"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 class ClockSampler(threading.Thread):
@@ -119,14 +136,13 @@ class ClockSampler(threading.Thread):
 
 def cpu_arm(a, seconds, threads=None):
     """The oracle port (oracle/cyg_oracle.c, OpenMP over envs) timed on the host cores on a bounded
-    sample of the same workload.  Returns (env-steps/s, cores, description)."""
+    sample of the same workload.  The thread count is passed explicitly (the `num_threads` clause of cyo_step), so
+    torchrun's OMP_NUM_THREADS=1 does not collapse the arm.  Returns (env-steps/s, cores, description)."""
     import numpy as np
     from cygym_b200 import synthetic_network
-    from oracle import cyg_oracle as O
     from tests.common import oracle_for, oracle_state_from_template, sanitize_actions
     net = synthetic_network(a.devices, n_subnets=a.subnets, seed=a.seed)
-    cores = threads or os.cpu_count() or 1
-    cores = min(cores, O.lib().cyo_max_threads()) if O.lib().cyo_max_threads() > 0 else 1
+    cores = max(1, int(threads or host_cores()))
     Bc = max(cores * 256, 1024)
     orc, _ = oracle_for(net, seed=a.seed, xcap=16)
     st = oracle_state_from_template(orc, net, Bc)
@@ -144,7 +160,19 @@ def cpu_arm(a, seconds, threads=None):
         el = time.perf_counter() - t0
         if el >= seconds or n >= 100000:
             break
-    return Bc * n / el, cores, f"{Bc} envs x {n} steps of the same workload, {cores} OpenMP threads, {el:.1f}s"
+    return Bc * n / el, cores, f"{Bc} envs x {n} steps of the same workload, {cores} OpenMP threads (explicit), {el:.1f}s", net
+
+
+def reference_python_record():
+    """The unmodified reference's own Python step() timed in the BUILD container (oracle/time_reference.py): the
+    reference cannot travel to the GPU box, so this is a committed record with its host stated, not a live number."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "reference_python_steps.json")) as f:
+            r = json.load(f)
+        r["note"] = "measured in the build container by oracle/time_reference.py, not on this box"
+        return r
+    except Exception:
+        return None
 
 
 def run_reference(a):
@@ -155,7 +183,7 @@ def run_reference(a):
     # each "step" of this arm is one bounded CPU sample
     vals = []
     for i in range(a.warmup + a.steps):
-        v, cores, sample = cpu_arm(a, per_step)
+        v, cores, sample, net = cpu_arm(a, per_step)
         if i >= a.warmup:
             vals.append(v)
     val = sum(vals) / len(vals)
@@ -163,13 +191,22 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "l2_policy": "n/a (CPU arm)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" per step, {a.steps} steps"},
+        "config": {"workload": workload_name(a), "envs_per_gpu": a.envs, "device_slots": a.devices, "edges": int(net.E),
+                   "l2_policy": "n/a (CPU arm)", "sampled_envs": int(sample.split()[0])},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + f" per step, {a.steps} steps",
+                         "reference_python": reference_python_record()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def latest_profile(pattern):
+    """Newest committed profiles/rNN_<pattern> (the ncu-derived per-launch DRAM traffic of the current kernels)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_" + pattern)))
+    return files[-1] if files else None
 
 
 def main():
@@ -179,7 +216,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from cygym_b200 import synthetic_network
+    from cygym_b200 import marl, synthetic_network
     from cygym_b200.vector_env import ActionBatch, VectorCyberDefenseEnv
 
     rank = int(os.environ.get("RANK", "0"))
@@ -191,91 +228,163 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, K, Wm = a.envs, a.steps, max(3, a.warmup)
 
-    net = synthetic_network(a.devices, n_subnets=a.subnets, seed=a.seed)
-    # one env set per rotation slot; env ids are globally unique across ranks and sets
-    sets = [VectorCyberDefenseEnv(net, B, device=dev, seed=a.seed, env_id0=(rank * a.sets + s) * B, xcap=16)
-            for s in range(a.sets)]
-    if a.randomize:
-        for s_ in sets:
-            s_.randomize_compromise_and_ownership()
-    # ring of pre-generated action batches (inputs resident in HBM before the timed region)
-    ring = {0: [], 1: []}
-    for mode in (0, 1):
-        for r in range(a.ring):
-            ab = sets[r % a.sets].sample_actions(mode)
-            if mode == 0:  # detector untrained: defender 10 -> no-op 8
-                ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == 10, (ab.hdr[:, 0] & ~0xFF) | 8, ab.hdr[:, 0])
-            for spec in filter(None, os.environ.get('CYG_BENCH_EXCLUDE', '').split(',')):  # diagnostics only
-                m_, t_ = spec.split(':')
-                if int(m_) == mode:
-                    ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == int(t_), (ab.hdr[:, 0] & ~0xFF) | (8 if mode == 0 else 3), ab.hdr[:, 0])
-            ring[mode].append(ActionBatch(ab.hdr.clone(), ab.mask.clone()))
-    torch.cuda.synchronize()
-
-    def one_step(i):
-        env = sets[i % a.sets]
-        turn = (i // a.sets) & 1  # every set alternates defender / attacker turns
-        env.step(ring[turn][(i // (2 * a.sets)) % a.ring], obs_mode=a.obs)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n, warm):
-        for i in range(warm):
+    def timed(fn, n, warm, counters=()):
+        """W warm-up calls (+ the fixed pre-heat), then n calls between two CUDA events on the current stream."""
+        for i in range(max(warm, PREHEAT)):
             fn(i)
         barrier()
-        l0 = sum(s.launch_count for s in sets)
+        l0 = sum(s.launch_count for s in counters)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
         for i in range(n):
-            fn(warm + i)
+            fn(max(warm, PREHEAT) + i)
         ev1.record()
         barrier()
-        return ev0.elapsed_time(ev1), sum(s.launch_count for s in sets) - l0
+        return ev0.elapsed_time(ev1), sum(s.launch_count for s in counters) - l0
 
+    flush_buf = None
+
+    def timed_flushed(fn, n, warm):
+        """Small-state legs: a 256 MB write between launches evicts the state from L2; every launch has its own pair of
+        CUDA events (the flush is outside them).  Returns the summed launch time in ms."""
+        nonlocal flush_buf
+        if flush_buf is None:
+            flush_buf = torch.empty(64 * 1024 * 1024, dtype=torch.int32, device=dev)
+        for i in range(max(warm, PREHEAT)):
+            fn(i)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        torch.cuda.synchronize()
+        for i in range(n):
+            flush_buf.fill_(i)
+            evs[i][0].record()
+            fn(max(warm, PREHEAT) + i)
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
+    def make_sets(net, nB, n_sets, randomize, id_base=0):
+        sets = [VectorCyberDefenseEnv(net, nB, device=dev, seed=a.seed, env_id0=id_base + (rank * n_sets + s) * nB, xcap=16)
+                for s in range(n_sets)]
+        if randomize:
+            for s_ in sets:
+                s_.randomize_compromise_and_ownership()
+        return sets
+
+    def make_ring(sets, n_ring):
+        """Pre-generated sample_action batches (inputs resident in HBM before any timed region)."""
+        ring = {0: [], 1: []}
+        for mode in (0, 1):
+            for r in range(n_ring):
+                ab = sets[r % len(sets)].sample_actions(mode)
+                if mode == 0:  # detector untrained: defender 10 -> no-op 8
+                    ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == 10, (ab.hdr[:, 0] & ~0xFF) | 8, ab.hdr[:, 0])
+                for spec in filter(None, os.environ.get('CYG_BENCH_EXCLUDE', '').split(',')):  # diagnostics only
+                    m_, t_ = spec.split(':')
+                    if int(m_) == mode:
+                        ab.hdr[:, 0] = torch.where((ab.hdr[:, 0] & 0xFF) == int(t_), (ab.hdr[:, 0] & ~0xFF) | (8 if mode == 0 else 3), ab.hdr[:, 0])
+                ring[mode].append(ActionBatch(ab.hdr.clone(), ab.mask.clone()))
+        torch.cuda.synchronize()
+        return ring
+
+    def plain_legs(net, sets, ring, n_steps, fuse, obs=0, flushed=False):
+        """Fused (`fuse` plain steps per launch) and one-launch-per-step timings of alternating defender / attacker turns
+        over the rotating env sets.  Returns dict(ms_fused, steps_fused, launches, ms_single, steps_single)."""
+        nB, n_sets, n_ring = sets[0].B, len(sets), len(ring[0])
+
+        def one_step(i):
+            env = sets[i % n_sets]
+            turn = (i // n_sets) & 1  # every set alternates defender / attacker turns
+            om = 0 if not obs else (1 + turn)  # the view the turn's player reads (defender 6M / attacker 4M+X)
+            env.step(ring[turn][(i // (2 * n_sets)) % n_ring], obs_mode=om)
+
+        out = {}
+        F = max(1, fuse) if not obs else 1
+        if F > 1:
+            Kf = ((n_steps + F - 1) // F) * F
+            fused = []
+            for s_i in range(n_sets):
+                per_set = []
+                for v in range(2):  # two variants per set so that consecutive launches of a set read different batches
+                    hs = [ring[t & 1][(s_i + v * 3 + t // 2) % n_ring].hdr for t in range(F)]
+                    mk = [ring[t & 1][(s_i + v * 3 + t // 2) % n_ring].mask for t in range(F)]
+                    per_set.append((torch.stack(hs).contiguous(), torch.stack(mk).contiguous()))
+                fused.append(per_set)
+            outs = [(torch.empty(F, nB, dtype=torch.float32, device=dev), torch.empty(F, nB, dtype=torch.float32, device=dev),
+                     torch.empty(F, nB, dtype=torch.int32, device=dev)) for _ in range(n_sets)]
+            torch.cuda.synchronize()
+
+            def one_launch(j):
+                s_i = j % n_sets
+                h_, m_ = fused[s_i][(j // n_sets) & 1]
+                sets[s_i].step_many(h_, m_, out=outs[s_i])
+
+            if flushed:
+                out["ms_fused"], out["launches"] = timed_flushed(one_launch, Kf // F, (Wm + F - 1) // F), Kf // F
+            else:
+                out["ms_fused"], out["launches"] = timed(one_launch, Kf // F, (Wm + F - 1) // F, sets)
+            out["steps_fused"] = Kf
+        K1 = min(n_steps, 600)
+        if flushed:
+            out["ms_single"] = timed_flushed(one_step, K1, Wm)
+        else:
+            out["ms_single"], l1 = timed(one_step, K1, Wm, sets)
+            if F == 1:
+                out["launches"] = l1
+        out["steps_single"] = K1
+        return out
+
+    def leg_record(net, nB, r, fuse, obs=False, extra=None):
+        alg = net.algorithmic_bytes_per_step(obs=obs)
+        d = {"envs": nB, "device_slots": net.M, "edges": int(net.E), "algorithmic_bytes_per_env_step": alg}
+        if "ms_fused" in r:
+            us = r["ms_fused"] * 1e3 / r["steps_fused"]
+            d["fused"] = {"steps_per_launch": fuse, "us_per_step": us, "value": world * nB / (us * 1e-6), "unit": UNIT,
+                          "roofline": {"bound": "hbm", "achieved": alg * nB / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg * nB / (us * 1e-6) / 1e9 / peak}}
+        us1 = r["ms_single"] * 1e3 / r["steps_single"]
+        d["single"] = {"launch_us": us1, "value": world * nB / (us1 * 1e-6), "unit": UNIT,
+                       "roofline": {"bound": "hbm", "achieved": alg * nB / (us1 * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": alg * nB / (us1 * 1e-6) / 1e9 / peak}}
+        if extra:
+            d.update(extra)
+        return d
+
+    # ================= the headline: C3 =================
+    net = synthetic_network(a.devices, n_subnets=a.subnets, seed=a.seed)
+    sets = make_sets(net, B, a.sets, a.randomize)
+    ring = make_ring(sets, a.ring)
     F = max(1, a.fuse) if not a.obs else 1
     sampler = ClockSampler(local)
+    sampler.start()
+    head = plain_legs(net, sets, ring, K, F, obs=a.obs)
+    clocks = sampler.stop()
     if F > 1:
-        # the headline leg: F plain steps per launch (alternating defender / attacker turns), the records of a CTA's envs
-        # stay in shared memory between them; every env set gets its own [F, B, ..] action tensors out of the ring
-        K = ((K + F - 1) // F) * F
-        fused = []
-        for s_i in range(a.sets):
-            per_set = []
-            for v in range(2):  # two variants per set so that consecutive launches of a set read different batches
-                hs = [ring[t & 1][(s_i + v * 3 + t // 2) % a.ring].hdr for t in range(F)]
-                mk = [ring[t & 1][(s_i + v * 3 + t // 2) % a.ring].mask for t in range(F)]
-                per_set.append((torch.stack(hs).contiguous(), torch.stack(mk).contiguous()))
-            fused.append(per_set)
-        outs = [(torch.empty(F, B, dtype=torch.float32, device=dev), torch.empty(F, B, dtype=torch.float32, device=dev),
-                 torch.empty(F, B, dtype=torch.int32, device=dev)) for _ in range(a.sets)]
-        torch.cuda.synchronize()
-
-        def one_launch(j):
-            s_i = j % a.sets
-            h_, m_ = fused[s_i][(j // a.sets) & 1]
-            sets[s_i].step_many(h_, m_, out=outs[s_i])
-
-        sampler.start()
-        ms, launches = timed(one_launch, K // F, max(1, (Wm + F - 1) // F))
-        clocks = sampler.stop()
-        K1 = min(K, 600)
-        ms1, _ = timed(one_step, K1, Wm)  # the same workload, one launch per step
+        ms, Kh, launches = head["ms_fused"], head["steps_fused"], head["launches"]
     else:
-        sampler.start()
-        ms, launches = timed(one_step, K, Wm)
-        clocks = sampler.stop()
-        ms1, K1 = ms, K
+        ms, Kh, launches = head["ms_single"], head["steps_single"], head["launches"]
+    ms1, K1 = head["ms_single"], head["steps_single"]
     errs = int(max(int(s.error_flags().max().item()) for s in sets))
 
     # ---- e2e: the public host-buffer call VectorCyberDefenseEnv.step_host(): every step copies that step's actions
     #      from pinned host memory, launches the kernel, reads (raw, shaped, done) back and synchronises ----
     e2e = None
     if not a.no_e2e:
-        Ke = max(10, min(K, 200))
+        Ke = max(200, a.e2e_steps)
         groups = sets[:3]  # every env set of the rotation is one group with its own stream
         host_actions = {}
         for gi, env in enumerate(groups):
@@ -310,11 +419,78 @@ def main():
             barrier()
             return t0.elapsed_time(t1)
 
-        run_e2e(len(groups), 6)
+        run_e2e(len(groups), 3 * PREHEAT)
         ems = run_e2e(len(groups), Ke)
-        run_e2e(1, 4)
-        ems1 = run_e2e(1, max(10, Ke // 2))
-        e2e = (ems, Ke, host_actions[0, 0].numel() * 4, out_host.numel() * 4, ems1, max(10, Ke // 2), len(groups))
+        run_e2e(1, PREHEAT)
+        ems1 = run_e2e(1, Ke // 2)
+        e2e = (ems, Ke, host_actions[0, 0].numel() * 4, out_host.numel() * 4, ems1, Ke // 2, len(groups))
+        for env in groups:
+            env._stream = None
+        torch.cuda.synchronize()
+
+    # ================= the other shapes (N = 1: kernel diagnostics, not scaling points) =================
+    legs = {}
+    if world == 1 and not a.no_legs and not a.obs:
+        Kl = min(K, 240)
+        # (1) randomized ownership: what every Double-Oracle rollout steps (do_agent.py:2032: randomize first)
+        if not a.randomize:
+            rsets = make_sets(net, B, a.sets, True, id_base=10 * B * a.sets)
+            rring = make_ring(rsets, a.ring)
+            legs["randomized"] = leg_record(net, B, plain_legs(net, rsets, rring, Kl, F), F, extra={
+                "what": "the headline workload after randomize_compromise_and_ownership() on every env (the owned set moves, "
+                        "evolve_network adds extra hub-star edges): the state every Double-Oracle rollout steps"})
+            del rsets, rring
+        # (2) observations materialised every step (the view the turn's player reads)
+        legs["obs_on"] = leg_record(net, B, plain_legs(net, sets, ring, Kl, 1, obs=1), 1, obs=True, extra={
+            "what": "one launch per step with the fused observation epilogue: _get_defender_state (6M fp32) on defender turns, "
+                    "_get_attacker_state (4M+X) on attacker turns; algorithmic bytes = SURVEY 8(d) with OBS"})
+        # (3) the IPPO / MAPPO rollout shape: per-device action types -> 13 groups -> step_grouped (IPPO.py:559-573)
+        genv = sets[0]
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + a.seed)
+        types = [torch.randint(0, 14, (B, net.M), device=dev, generator=gen, dtype=torch.int32) for _ in range(4)]
+        exp_idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        app_idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        for t_ in types:  # sklearn's branch stays out: per-device type 10 (train detector) -> 8
+            t_[t_ == 10] = 8
+        pre = [marl.grouped_actions_from_types(genv, t_, marl.visibility_mask(genv, "defender"), exp_idx, app_idx, "defender", 14, 8)
+               for t_ in types]
+        ms_g = timed(lambda i: sets[i % a.sets].step_grouped(pre[i % 4]), Kl, Wm, sets)[0]
+
+        def glue_and_step(i):
+            env = sets[i % a.sets]
+            vis = marl.visibility_mask(env, "defender")
+            env.step_grouped(marl.grouped_actions_from_types(env, types[i % 4], vis, exp_idx, app_idx, "defender", 14, 8))
+
+        ms_gg = timed(glue_and_step, Kl, Wm, sets)[0]
+        alg_g = net.algorithmic_bytes_per_step() + 12 * (4 + (net.M + 7) // 8)  # 13 action groups instead of one
+        us_g, us_gg = ms_g * 1e3 / Kl, ms_gg * 1e3 / Kl
+        legs["grouped"] = {
+            "what": "step_grouped with the 13 per-type groups of IPPO.py:559-570 (every device draws a type, the VISIBLE devices -- build_visibility_mask, "
+                    "IPPO.py:74-96 -- are grouped by type), "
+                    "defender turns; `single` = the grouped step alone on pre-built groups, `with_glue` = + visibility mask and "
+                    "group encoding (cygym_b200.marl) as torch ops per step",
+            "envs": B, "device_slots": net.M, "groups": 13, "algorithmic_bytes_per_env_step": alg_g,
+            "single": {"launch_us": us_g, "value": B / (us_g * 1e-6), "unit": UNIT,
+                       "roofline": {"bound": "hbm", "achieved": alg_g * B / (us_g * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": alg_g * B / (us_g * 1e-6) / 1e9 / peak}},
+            "with_glue": {"us_per_step": us_gg, "value": B / (us_gg * 1e-6), "unit": UNIT}}
+        del pre, types
+        # (4) C2: 4096 envs x 50 device slots / 3 subnets (BASELINE.json configs[1])
+        net2 = synthetic_network(50, n_subnets=3, seed=a.seed)
+        s2 = make_sets(net2, 4096, 2, False, id_base=20 * B * a.sets)
+        legs["c2"] = leg_record(net2, 4096, plain_legs(net2, s2, make_ring(s2, 4), Kl, F, flushed=True), F, extra={
+            "what": "C2: 4096 envs x 50 device slots / 3 subnets; 2 MB of state: a 256 MB write between launches evicts it from L2, "
+                    "per-launch CUDA events; 4096 envs fill 128 of the 148 SMs with one 32-env CTA each"})
+        del s2
+        # (5) C4: 1024 envs x 2000 device slots / 64 subnets (BASELINE.json configs[3])
+        net4 = synthetic_network(2000, n_subnets=64, seed=a.seed)
+        s4 = make_sets(net4, 1024, 1, False, id_base=30 * B * a.sets)
+        legs["c4"] = leg_record(net4, 1024, plain_legs(net4, s4, make_ring(s4, 2), min(Kl, 60), 1, flushed=True), 1, extra={
+            "what": "C4: 1024 envs x 2000 device slots / 64 subnets (the adjacency matrix exceeds shared memory); 256 MB write "
+                    "between launches, per-launch CUDA events"})
+        errs = max(errs, int(s4[0].error_flags().max().item()))
+        del s4
 
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0, e2e[4] if e2e else 0.0, ms1], dtype=torch.float64, device=dev)
@@ -322,67 +498,60 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ems, ems1, ms1 = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         alg = net.algorithmic_bytes_per_step(obs=bool(a.obs))
-        traffic = None  # dram read+write bytes per launch of the step kernel from the committed `ncu --set full` capture
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_step_kernel_traffic.json")) as f:
-                tj = json.load(f)
-            if tj.get("envs_per_launch") == B and tj.get("device_slots") == a.devices and not a.obs:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        traffic_f = None  # the same for a fused launch (its own capture)
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_step_kernel_fused_traffic.json")) as f:
-                tj = json.load(f)
-            if tj.get("envs_per_launch") == B and tj.get("device_slots") == a.devices and tj.get("steps_per_launch") == F:
-                traffic_f = tj["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        launch_s = ms * 1e-3 / (K // F)      # average duration of one launch (F steps)
+
+        def traffic_of(pattern, **match):
+            p_ = latest_profile(pattern)
+            try:
+                with open(p_) as f:
+                    tj = json.load(f)
+                if all(tj.get(k) == v for k, v in match.items()) and not a.obs and not a.randomize:
+                    return tj["dram_bytes_per_launch"], os.path.basename(p_)
+            except Exception:
+                pass
+            return None, None
+        traffic, traffic_src = traffic_of("step_kernel_traffic.json", envs_per_launch=B, device_slots=a.devices)
+        traffic_f, traffic_f_src = traffic_of("step_kernel_fused_traffic.json", envs_per_launch=B, device_slots=a.devices, steps_per_launch=F)
+        launch_s = ms * 1e-3 / (Kh // F)      # average duration of one launch (F steps)
         achieved = alg * B * F / launch_s / 1e9
-        value = world * B * K / (ms * 1e-3)
+        value = world * B * Kh / (ms * 1e-3)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Kh, "warmup": Wm,
+            "ms_per_step": ms / Kh, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
                        "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
-                       "randomized_ownership": bool(a.randomize), "steps_per_launch": F,
+                       "randomized_ownership": bool(a.randomize), "steps_per_launch": F, "preheat_launches": max(PREHEAT, (Wm + F - 1) // F),
                        "fusion": (f"{F} plain steps per launch (step_many / cyg_step_multi): open-loop action batches resident in HBM, records stay in "
                                   "shared memory between the steps of a launch, so per-step HBM traffic is actions in + rewards out; "
                                   "single_step_launch below is the same workload at one launch per step") if F > 1 else "one launch per step",
                        "l2_policy": f"rotating {a.sets} env sets ({a.sets * B * (sets[0].S + net.M) * 4 / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
                        "parallelism": f"env-sharded x{world}, no per-step collective", "error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic if F == 1 else traffic_f, "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
+                         "traffic": traffic if F == 1 else traffic_f, "traffic_source": traffic_src if F == 1 else traffic_f_src,
+                         "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
                          "env_steps_per_launch": B * F, "launch_us": launch_s * 1e6, "peak_source": peak_src,
                          "actual_bytes_per_env_step": (2 * sets[0].S * 4) / F + 4 * (4 + net.W) + 12,
                          "note": ("algorithmic bytes are SURVEY 8(d)'s per-step figure x env-steps per launch; a fused launch moves less than that "
                                   "(state in/out once per launch), which 8(d) allows for") if F > 1 else None},
             "single_step_launch": {"value": world * B * K1 / (ms1 * 1e-3), "unit": UNIT, "launch_us": ms1 * 1e3 / K1, "steps": K1,
-                                   "roofline_frac": alg * B / (ms1 * 1e-3 / K1) / 1e9 / peak, "traffic": traffic},
+                                   "roofline_frac": alg * B / (ms1 * 1e-3 / K1) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src},
             "clocks": clocks, "gpu_launches": int(launches),
         }
+        if legs:
+            line["legs"] = legs
         if e2e:
             line["e2e"] = {"value": world * B * e2e[1] / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[2],
-                           "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1],
+                           "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1], "preheat_steps": 3 * PREHEAT,
                            "how": f"VectorCyberDefenseEnv.step_host(act=pinned rows, sync=False) / wait_host() over {e2e[6]} env groups of "
                                   f"{B} envs on {e2e[6]} streams: each group waits for its own previous (raw, shaped, done) before its next "
                                   "step; the copies of one group overlap the kernel of the other",
                            "one_group_synchronous": {"value": world * B * e2e[5] / (ems1 * 1e-3), "unit": UNIT,
                                                      "ms_per_step": ems1 / e2e[5], "steps": e2e[5]}}
         if not a.no_cpu_baseline and world == 1:
-            v, cores, sample = cpu_arm(a, a.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            v, cores, sample, _ = cpu_arm(a, a.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "reference_python": reference_python_record()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -1070,7 +1070,26 @@ struct Env {
       vw = w0; hitbit = lb; upos = up;
       break;
     }
-    cnt = upos - (has_blk ? range_count(a, upos, 0u) : 0);
+    cnt = upos;
+    if (has_blk) { /* minus the blocked units in front of the hit */
+#ifdef __CUDA_ARCH__
+      if (SM && W <= CYG_MAX_W) { /* shared memory, out lists of at most 128 units: a 4-word window, no data-dependent loop */
+        const uint32_t* b = inc();
+        const int wa = a >> 5, sh = a & 31;
+        uint32_t lo = b[wa];
+        int blk_n = 0;
+        bool fits = upos <= 128;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t hi = b[wa + i + 1];
+          blk_n += popc(funnel_r(lo, hi, sh) & lowmask0(upos - 32 * i));
+          lo = hi;
+        }
+        cnt -= fits ? blk_n : range_count(a, upos, 0u);
+      } else
+#endif
+      cnt -= range_count(a, upos, 0u);
+    }
     if (xrow) { /* unblocked extra edges in front of the hit (all of them when nothing is hit) */
       for (int w = 0; w < W; w++) {
         const uint32_t bm = vw < 0 ? 0xFFFFFFFFu : ((w < vw ? 0xFFFFFFFFu : 0u) | ((hitbit - 1u) & eqmask(w, vw)));
