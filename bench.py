@@ -457,10 +457,12 @@ def main():
                for t_ in types]
         ms_g = timed(lambda i: sets[i % a.sets].step_grouped(pre[i % 4]), Kl, Wm, sets)[0]
 
+        gouts = [None] * a.sets
+
         def glue_and_step(i):
             env = sets[i % a.sets]
-            vis = marl.visibility_mask(env, "defender")
-            env.step_grouped(marl.grouped_actions_from_types(env, types[i % 4], vis, exp_idx, app_idx, "defender", 14, 8))
+            gouts[i % a.sets] = marl.grouped_actions(env, types[i % 4], "defender", exp_idx, app_idx, "defender", 14, 8, out=gouts[i % a.sets])
+            env.step_grouped(gouts[i % a.sets])
 
         ms_gg = timed(glue_and_step, Kl, Wm, sets)[0]
         alg_g = net.algorithmic_bytes_per_step() + 12 * (4 + (net.M + 7) // 8)  # 13 action groups instead of one

@@ -76,7 +76,7 @@ class CygStepOut(C.Structure):
 
 EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_set_base_line_per_env_steps", "cyg_internal_words",
            "cyg_bind", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_randomize", "cyg_sample_actions", "cyg_sample_actions_ordered",
-           "cyg_observe", "cyg_launch_count", "cyg_set_debug_cycles"]
+           "cyg_observe", "cyg_group_actions", "cyg_launch_count", "cyg_set_debug_cycles"]
 
 
 class CygError(RuntimeError):
@@ -179,6 +179,8 @@ def lib():
         L.cyg_sample_actions.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_sample_actions_ordered.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.cyg_observe.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.cyg_group_actions.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_launch_count.argtypes = [C.c_void_p]
         L.cyg_launch_count.restype = C.c_int64
         L.cyg_set_debug_cycles.argtypes = [C.c_void_p, C.c_void_p]

@@ -119,6 +119,45 @@ __device__ __forceinline__ void copy_record(uint32_t* dst, const uint32_t* src, 
   }
 }
 
+/* Observation rows (CyberDefenseEnv.py:146-257; obs_mode as in cyg_step_out) of n_envs consecutive records: one warp per
+ * (env, plane word) = 32 devices, the lanes on consecutive OUTPUT floats (coalesced stores): an element is a static
+ * table value (OS id, version) or one bit of the four plane words the whole warp shares. */
+template <int W, int F>
+__device__ __forceinline__ void observe_rows_f(const Net& n, const uint32_t* recs, int S, int n_envs, int obs_mode, float* out, int warp,
+                                               int nwarps, int lane) {
+  const int M = n.M, Wm = n.Wm, dim = F == 4 ? 4 * M + n.cfg.X : 6 * M;
+  const float* osv = (const float*)(n.blob + n.o_os);
+  const float* verv = (const float*)(n.blob + n.o_ver);
+  for (int chunk = warp; chunk < n_envs * Wm; chunk += nwarps) {
+    const int el = chunk / Wm, w = chunk - el * Wm;
+    const uint32_t* pl = recs + (size_t)el * S + CYG_REC_PLANES;
+    const uint32_t c = pl[P_COMP * W + w], k = pl[P_KNOWN * W + w], y = pl[P_NYA * W + w], o = pl[P_OWNED * W + w];
+    const uint32_t vis = F == 4 ? (k & ~y & o) : (obs_mode == 1 ? (~y & o) : 0xFFFFFFFFu); /* rows outside are -1 */
+    const int nelem = min(32, M - 32 * w) * F;
+    float* row = out + (size_t)el * dim + 32 * w * F;
+#pragma unroll
+    for (int t = 0; t < F; t++) {
+      const int e = t * 32 + lane;
+      if (e >= nelem) continue;
+      const int sd = e / F, f = e - sd * F, d = 32 * w + sd;
+      float v;
+      if (!((vis >> sd) & 1u)) v = -1.f;
+      else if (f == 0) v = osv[d];
+      else if (f == 1) v = verv[d];
+      else if (F == 4) v = f == 2 ? (float)((c >> sd) & 1u) : 1.f;
+      else v = f == 2 ? (obs_mode == 1 ? -1.f : (float)((c >> sd) & 1u)) : f == 3 ? 0.f : f == 4 ? (float)((k >> sd) & 1u) : (float)((y >> sd) & 1u);
+      row[e] = v;
+    }
+    if (F == 4 && w == 0 && lane < n.cfg.X) out[(size_t)el * dim + 4 * M + lane] = lane < n.cfg.n_exploits ? 1.f : 0.f;
+  }
+}
+template <int W>
+__device__ __forceinline__ void observe_rows(const Net& n, const uint32_t* recs, int S, int n_envs, int obs_mode, float* out, int warp,
+                                             int nwarps, int lane) {
+  if (obs_mode == 2) observe_rows_f<W, 4>(n, recs, S, n_envs, obs_mode, out, warp, nwarps, lane);
+  else observe_rows_f<W, 6>(n, recs, S, n_envs, obs_mode, out, warp, nwarps, lane);
+}
+
 /* shared-memory carve-up for a CTA of NB envs (all offsets 16-byte aligned; tables first, at word 0) */
 struct SmemPlan {
   size_t off_tables, off_recs, off_out, off_perm, off_cnt, off_def, off_bar, total;
@@ -420,11 +459,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   /* ---- optional fused observation rows (post-evolve view, CyberDefenseEnv.py:146-257) ---- */
   if (p.obs && p.obs_mode) {
     const int dim = p.obs_mode == 2 ? 4 * M + p.net.cfg.X : 6 * M;
-    float* o = p.obs + (size_t)env0 * dim;
-    for (int i = tid; i < nb * dim; i += NT) {
-      int el = i / dim;
-      o[i] = observe_elem<W>(&p.net, s_rec + el * S, p.obs_mode, i - el * dim);
-    }
+    observe_rows<W>(p.net, s_rec, S, nb, p.obs_mode, p.obs + (size_t)env0 * dim, tid >> 5, NT >> 5, lane);
   }
 
   /* ---- write the block's records back ---- */
@@ -608,6 +643,70 @@ __global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
   for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = p.xtra_int[(size_t)warp * n.cfg.xcap + i];
 }
 
+/* ---- IPPO / MAPPO glue: per-device action types -> the per-type action groups of one grouped step (IPPO.py:559-570),
+ *      with the role's visibility mask (build_visibility_mask, IPPO.py:74-96) read straight from the bit-planes.
+ *      One warp per env, lanes on 32 devices; group g = the g-th action type other than the no-op. ---- */
+struct GroupParams {
+  Net net;
+  const uint32_t* recs;
+  const int32_t* types;   /* [B][M] action type each device drew */
+  const int32_t* exp_idx; /* [B] */
+  const int32_t* app_idx; /* [B] */
+  const uint8_t* visible; /* optional [B][M]: the policy's own mask (> 0 = the device counts), ANDed with the role's */
+  const int32_t* single;  /* optional [B][2]: device kept for the single-device types 11 / 12 (random.choice, IPPO.py:567) */
+  uint32_t* hdr;          /* [n_types - 1][B][4] */
+  uint32_t* mask;         /* [n_types - 1][B][Wm] */
+  int B, mode, role, n_types, noop;
+};
+#if defined(CYG_TU_W) && CYG_TU_W == 4 /* one copy: the kernel is not templated on the plane width */
+__global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
+  const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+  if (b >= p.B) return;
+  const Net& n = p.net;
+  const int M = n.M, Wm = n.Wm, Wp = n.W;
+  const uint32_t* pl = p.recs + (size_t)b * n.S + CYG_REC_PLANES;
+  const int G = p.n_types - 1;
+  int ndev = 0;            /* lane g: devices of group g */
+  int first = -1;          /* lane g: lowest device of group g */
+  const int t_mine = lane < G ? (lane < p.noop ? lane : lane + 1) : -1; /* the type of group `lane` */
+  for (int w = 0; w < Wm; w++) {
+    const int d = 32 * w + lane;
+    uint32_t vis = 0xFFFFFFFFu;
+    if (p.role == 1) vis = ~pl[P_NYA * Wp + w] & pl[P_OWNED * Wp + w];
+    else if (p.role == 2) vis = ~pl[P_NYA * Wp + w] & pl[P_OWNED * Wp + w] & pl[P_KNOWN * Wp + w];
+    const int ty = d < M ? p.types[(size_t)b * M + d] : -1;
+    const bool on = d < M && ((vis >> lane) & 1u) && (!p.visible || p.visible[(size_t)b * M + d] != 0);
+    uint32_t mine = 0;
+    for (int g = 0; g < G; g++) { /* uniform */
+      const int t = g < p.noop ? g : g + 1;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, on && ty == t);
+      if (lane == g) mine = m;
+    }
+    if (lane < G) {
+      if (t_mine == 11 || t_mine == 12) { /* single-device types: the chosen device if it is in the set, else (no choice given) the lowest */
+        if (p.single) {
+          const int c = p.single[(size_t)b * 2 + (t_mine - 11)];
+          mine &= (c >= 32 * w && c < 32 * w + 32) ? (1u << (c & 31)) : 0u;
+        } else {
+          mine = first < 0 ? (mine & (0u - mine)) : 0u;
+        }
+      }
+      if (mine && first < 0) first = 32 * w + __ffs((int)mine) - 1;
+      ndev += __popc(mine);
+      p.mask[((size_t)lane * p.B + b) * Wm + w] = mine;
+    }
+  }
+  if (lane < G) {
+    uint32_t* h = p.hdr + ((size_t)lane * p.B + b) * 4;
+    const int at = ndev > 0 ? t_mine : p.noop;
+    h[0] = (uint32_t)(at & 0xFF) | ((uint32_t)p.mode << 8) | (1u << 16);
+    h[1] = (uint32_t)(p.exp_idx ? p.exp_idx[b] : 0) & 0xFFu;
+    h[2] = (uint32_t)ndev;
+    h[3] = (uint32_t)(p.app_idx ? p.app_idx[b] : 0);
+  }
+}
+#endif
+
 struct ObsParams {
   Net net;
   const uint32_t* recs;
@@ -616,12 +715,8 @@ struct ObsParams {
 };
 template <int W>
 __global__ void cyg_observe_kernel(const __grid_constant__ ObsParams p) {
-  const int dim = p.obs_mode == 2 ? 4 * p.net.M + p.net.cfg.X : 6 * p.net.M;
-  const size_t total = (size_t)p.B * dim;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    size_t env = i / dim;
-    p.obs[i] = observe_elem<W>(&p.net, p.recs + env * p.net.S, p.obs_mode, (int)(i - env * dim));
-  }
+  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5), warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  observe_rows<W>(p.net, p.recs, p.net.S, p.B, p.obs_mode, p.obs, warp, nwarps, (int)(threadIdx.x & 31));
 }
 
 /* ===========================================================================
@@ -643,6 +738,9 @@ struct WOps {
 #define CYG_WOPS_NAME(w) CYG_WOPS_NAME2(w)
 
 #ifdef CYG_TU_W
+#if CYG_TU_W == 4
+extern "C" void cyg_group_launch(int blocks, int threads, cudaStream_t st, const GroupParams& p) { cyg_group_kernel<<<blocks, threads, 0, st>>>(p); }
+#endif
 template <int KW>
 struct WImpl {
   static cudaError_t set_smem_optin(int max_optin) {
@@ -675,6 +773,7 @@ extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
 }
 #else /* ---- the C-ABI translation unit ---- */
 extern "C" {
+void cyg_group_launch(int blocks, int threads, cudaStream_t st, const GroupParams& p);
 const WOps* cyg_wops_4(void);
 #ifndef CYG_FAST_BUILD /* profiling builds link the W = 4 unit only (config C3) */
 const WOps* cyg_wops_1(void);
@@ -971,6 +1070,21 @@ int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream) {
   int blocks = (int)((total + threads - 1) / threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
   wops(h->W)->observe(blocks, threads, (cudaStream_t)stream, p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_group_actions(cyg_handle h, int32_t mode, int32_t role, const int32_t* per_dev_types, const uint8_t* visible, const int32_t* exp_idx,
+                      const int32_t* app_idx, const int32_t* single_choice, int32_t n_types, int32_t noop, uint32_t* hdr, uint32_t* mask, void* stream) {
+  if (!h || !per_dev_types || !hdr || !mask) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  if (n_types < 2 || n_types > 33 || noop < 0 || noop >= n_types) return fail(CYG_E_INVAL, "n_types must be 2..33 and noop one of them");
+  if (role < 0 || role > 2 || (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER)) return fail(CYG_E_INVAL, "bad role / mode");
+  DeviceGuard g(h->device);
+  GroupParams p = {h->net, h->state, per_dev_types, exp_idx, app_idx, visible, single_choice, hdr, mask, h->B, mode, role, n_types, noop};
+  const int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
+  cyg_group_launch(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

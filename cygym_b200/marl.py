@@ -29,6 +29,50 @@ def visibility_mask(env: VectorCyberDefenseEnv, role):
     return v.float()
 
 
+class GroupedBatch:
+    """The action groups of one grouped step, stacked: hdr [G, B, 4], mask [G, B, W] int32 device tensors (what
+    cyg_step(CYG_STEP_GROUPED) reads); iterating yields the per-group ActionBatch views."""
+
+    def __init__(self, hdr, mask):
+        self.hdr, self.mask, self.order = hdr, mask, None
+
+    def __len__(self):
+        return int(self.hdr.shape[0])
+
+    def __getitem__(self, g):
+        return ActionBatch(self.hdr[g], self.mask[g])
+
+    def __iter__(self):
+        return (self[g] for g in range(len(self)))
+
+
+_ROLES = {None: 0, "all": 0, "defender": 1, "attacker": 2}
+
+
+def grouped_actions(env: VectorCyberDefenseEnv, per_dev_types, role, exp_idx, app_idx, mode, n_types, noop, visible=None,
+                    single_choice=None, out: GroupedBatch = None):
+    """The grouped action of IPPO.py:559-570 for B envs in ONE kernel (cyg_group_actions): every device drew a type
+    (per_dev_types int [B, M]); the devices the role sees (build_visibility_mask, IPPO.py:74-96, read from the env's
+    bit-planes; role None = all) and, when given, the caller's own `visible` [B, M] mask are grouped by type into the
+    n_types - 1 groups of one step_grouped() call.  Returns a GroupedBatch (pass it to env.step_grouped)."""
+    import ctypes as C
+    from . import _capi as K
+    m = 1 if mode in (1, "attacker") else 0
+    G = n_types - 1
+    dev = env.device
+    if out is None:
+        out = GroupedBatch(torch.empty(G, env.B, 4, dtype=torch.int32, device=dev), torch.empty(G, env.B, env.W, dtype=torch.int32, device=dev))
+    t = per_dev_types.to(dev, torch.int32).contiguous()
+    e = exp_idx.to(dev, torch.int32).contiguous()
+    a = app_idx.to(dev, torch.int32).contiguous()
+    v = None if visible is None else (visible > 0.5 if visible.dtype.is_floating_point else visible != 0).to(dev, torch.uint8).contiguous()
+    sc = None if single_choice is None else single_choice.to(dev, torch.int32).contiguous()
+    p = lambda x: None if x is None else C.c_void_p(x.data_ptr())
+    K.check(env.L.cyg_group_actions(env.h, m, _ROLES[role], p(t), p(v), p(e), p(a), p(sc), int(n_types), int(noop), p(out.hdr), p(out.mask), env._s()))
+    out._hold = (t, e, a, v, sc)
+    return out
+
+
 def _pack_mask(m, W):
     """bool [B, M] -> int32 [B, W] device masks."""
     B, M = m.shape

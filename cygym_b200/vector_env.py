@@ -200,11 +200,13 @@ class VectorCyberDefenseEnv:
 
     def step_grouped(self, groups, obs_mode=0, want_pre=False):
         """step_grouped() of every env (volt_typhoon_env.py:694): groups = list of ActionBatch."""
-        return self._step(list(groups), K.STEP_GROUPED, obs_mode, want_pre)
+        return self._step(groups if hasattr(groups, "hdr") else list(groups), K.STEP_GROUPED, obs_mode, want_pre)
 
     def _step(self, groups, flags, obs_mode, want_pre):
         G = len(groups)
-        if G == 1:
+        if hasattr(groups, "hdr"):  # already stacked [G, B, ..] (marl.GroupedBatch): no per-step torch.stack
+            hdr, mask, order = groups.hdr, groups.mask, None
+        elif G == 1:
             hdr, mask, order = groups[0].hdr, groups[0].mask, groups[0].order
         else:
             hdr = torch.stack([g.hdr for g in groups]).contiguous()

@@ -263,6 +263,17 @@ int cyg_sample_actions_ordered(cyg_handle h, int32_t mode, uint32_t* hdr, uint32
 /* Replaces _get_defender_state / _get_attacker_state / _get_state (CyberDefenseEnv.py:241/194/146). */
 int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream);
 
+/* IPPO / MAPPO glue (IPPO.py:559-570, MAPPO.py same lines): every device of every env drew an action type
+ * (per_dev_types[B][M]); the devices the role sees (build_visibility_mask, IPPO.py:74-96: role 1 defender = not
+ * Not_yet_added and attacker_owned, role 2 attacker = that and Known_to_attacker, role 0 = all; `visible`[B][M], when
+ * given, is the caller's own 0 / 1 mask, ANDed with the role's) are grouped by type into
+ * the n_types - 1 action groups of one cyg_step(CYG_STEP_GROUPED) call, ascending type order without `noop`; a type
+ * with no device becomes a no-op group (the reference skips it).  Types 11 / 12 keep ONE device: single_choice[B][2]
+ * (the reference's random.choice) or, when NULL, the lowest.  Writes hdr[n_types-1][B][4], mask[n_types-1][B][W]. */
+int cyg_group_actions(cyg_handle h, int32_t mode, int32_t role, const int32_t* per_dev_types, const uint8_t* visible,
+                      const int32_t* exp_idx, const int32_t* app_idx, const int32_t* single_choice, int32_t n_types, int32_t noop, uint32_t* hdr,
+                      uint32_t* mask, void* stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t cyg_launch_count(cyg_handle h);
 

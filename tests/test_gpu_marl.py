@@ -60,6 +60,18 @@ def test_grouped_rollout_glue_matches_reference_construction():
         for g in range(G):
             assert np.array_equal(groups[g].hdr.cpu().numpy().view(np.uint32), hdr[g]), (t, g)
             assert np.array_equal(groups[g].mask.cpu().numpy().view(np.uint32), mask[g]), (t, g)
+        # the same groups from ONE kernel (cyg_group_actions), stacked
+        gb = marl.grouped_actions(env, torch.from_numpy(types), None, torch.from_numpy(exp_idx), torch.from_numpy(app_idx), "defender",
+                                  n_types, noop, visible=torch.from_numpy(full_vis))
+        torch.cuda.synchronize()
+        assert np.array_equal(gb.hdr.cpu().numpy().view(np.uint32), hdr) and np.array_equal(gb.mask.cpu().numpy().view(np.uint32), mask), t
+        # ... and with the role's own visibility mask read from the bit-planes (IPPO.py:74-96)
+        gr = marl.grouped_actions(env, torch.from_numpy(types), "defender", torch.from_numpy(exp_idx), torch.from_numpy(app_idx), "defender", n_types, noop)
+        gt = marl.grouped_actions_from_types(env, torch.from_numpy(types).to(env.device), vis, torch.from_numpy(exp_idx).to(env.device),
+                                             torch.from_numpy(app_idx).to(env.device), "defender", n_types, noop)
+        torch.cuda.synchronize()
+        for g in range(G):
+            assert torch.equal(gr[g].hdr, gt[g].hdr) and torch.equal(gr[g].mask, gt[g].mask), (t, g)
         # type 10 with a non-empty log is the sklearn branch: the glue's caller filters it; do the same on both sides
         for g in range(G):
             bad = ((hdr[g, :, 0] & 0xFF) == 10) & (so.scal[:, 6] > 0)
