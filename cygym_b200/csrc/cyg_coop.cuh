@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t draw_at(const Rng& r, int site, uint32_t k) 
 
 template <int W>
 struct Coop {
-  typedef Env<W, true> E;
+  typedef Env<W, 1> E;
 
   /* busy_time = low + below(draw, range) for the devices of A[] (lane-uniform), draws k_base, k_base+1, ... in
    * ascending device order (the set form of _stall, volt:135-138) */
@@ -496,6 +496,251 @@ struct Coop {
       }
     }
     __syncwarp();
+  }
+};
+
+/* ---- large networks (128 < M <= 2048, planes of CYG_BIG_W = 64 words; BASELINE.json config C4): warp-per-env forms
+ *      of the two actions whose thread-per-env cost grows with devices x words -- block / unblock (one pick per listed
+ *      device) and the lateral-movement scan (one scan per source).  The record sits in shared memory (Env<W, 2>), a
+ *      64-word device mask is two words per lane, and the adjacency is walked as CSR rows: a device's out-units
+ *      [ip[d], ip[d] + nout[d]) of the unit table (L2-resident), 32 units per warp step.  Both walks are sequential over
+ *      devices, as in the reference; the lanes share the work inside one device.  Envs with extra (hub-star) edges take
+ *      the one-lane forms of cyg_core.cuh. ---- */
+template <int W>
+struct BigCoop {
+  typedef Env<W, 2> E;
+  static_assert(W == 64, "two plane words per lane");
+
+  /* lowest set bit over a lane-distributed 64-word mask (lane l holds words l and l + 32); clears it; -1 when empty */
+  static __device__ __forceinline__ int pop_lowest(uint32_t& m0, uint32_t& m1, int lane) {
+    const int c0 = m0 ? 32 * lane + __ffs((int)m0) - 1 : 0x7FFFFFFF;
+    const int c1 = m1 ? 32 * (lane + 32) + __ffs((int)m1) - 1 : 0x7FFFFFFF;
+    const int d = (int)__reduce_min_sync(CYG_FULL, (unsigned)min(c0, c1));
+    if (d == 0x7FFFFFFF) return -1;
+    if ((d >> 5) == lane) m0 &= m0 - 1u;
+    if ((d >> 5) == lane + 32) m1 &= m1 - 1u;
+    return d;
+  }
+
+  /* block (6) / unblock (9): volt:1071-1100 -> :485-511, set form.  Returns false when the env must take the one-lane
+   * path instead (extra edges, inconsistent header). */
+  /* lane-distributed mask of the devices that are an endpoint of an extra (hub-star) edge: src = sources only */
+  static __device__ __forceinline__ void extra_endpoints(E& e, bool src_only, uint32_t& x0, uint32_t& x1, int lane) {
+    x0 = 0; x1 = 0;
+    const int nx = e.n_extra();
+    const uint32_t* x = e.extra();
+    for (int base = 0; base < nx; base += 32) { /* uniform */
+      const uint32_t xe = base + lane < nx ? x[base + lane] : 0xFFFFFFFFu;
+      const int cnt = min(32, nx - base);
+      for (int t = 0; t < cnt; t++) {
+        const uint32_t w = __shfl_sync(CYG_FULL, xe, t);
+        const int u = (int)(w & CYG_X_IDMASK), v = (int)((w >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+        if ((u >> 5) == lane) x0 |= 1u << (u & 31);
+        if ((u >> 5) == lane + 32) x1 |= 1u << (u & 31);
+        if (!src_only) {
+          if ((v >> 5) == lane) x0 |= 1u << (v & 31);
+          if ((v >> 5) == lane + 32) x1 |= 1u << (v & 31);
+        }
+      }
+    }
+  }
+  static __device__ __forceinline__ bool test_bit(uint32_t x0, uint32_t x1, int d) {
+    const uint32_t w = __shfl_sync(CYG_FULL, (d >> 5) < 32 ? x0 : x1, (d >> 5) & 31);
+    return (w >> (d & 31)) & 1u;
+  }
+
+  static __device__ __forceinline__ bool flip(E& e, const typename E::Act& a, int atype, double& cost, bool& dirty) {
+    const int lane = lane_id();
+    const bool has_x = e.n_extra() > 0;
+    uint32_t xi0 = 0, xi1 = 0; /* devices with an incident extra edge: their pool is a merged list, walked by lane 0 alone */
+    if (has_x) extra_endpoints(e, false, xi0, xi1, lane);
+    const bool want = atype == 9;
+    const int site = want ? SITE_UNBLOCK : SITE_BLOCK;
+    const uint32_t flipw = want ? 0u : 0xFFFFFFFFu;
+    const int Wm = e.n->Wm;
+    uint32_t m0 = (lane < Wm ? a.mask[lane] : 0u) & e.m_valid(lane);
+    uint32_t m1 = (lane + 32 < Wm ? a.mask[lane + 32] : 0u) & e.m_valid(lane + 32);
+    const int nl = (int)__reduce_add_sync(CYG_FULL, (unsigned)(popc(m0) + popc(m1)));
+    if (a.n_dev < nl) return false;
+    m0 &= ~e.pl(P_NYA, lane); m1 &= ~e.pl(P_NYA, lane + 32);
+    const int na = (int)__reduce_add_sync(CYG_FULL, (unsigned)(popc(m0) + popc(m1)));
+    if (na == 0) return true;
+    const double ds = (double)e.n->cfg.def_scale;
+    if (lane == 0) { cost += -0.5 * ds * na; e.defcost += 0.5 * ds * na; }
+    uint32_t* const bits = e.inc();
+    uint32_t blk[4]; /* lane l: Philox block (kblk + l) of the site = draws 4 (kblk + l) .. + 3 */
+    uint32_t kdraw = 0, kblk = 0xFFFFFFFFu, cnt = 0;
+    for (;;) { /* uniform */
+      const int d = pop_lowest(m0, m1, lane);
+      if (d < 0) break;
+      if (has_x && test_bit(xi0, xi1, d)) { /* uniform */
+        uint32_t kn = kdraw, ok = 0;
+        if (lane == 0) {
+          Stream st(site);
+          st.k = kdraw;
+          ok = e.flip_incident_general(d, want, st) ? 1u : 0u;
+          kn = st.k;
+        }
+        kdraw = __shfl_sync(CYG_FULL, kn, 0);
+        cnt += __shfl_sync(CYG_FULL, ok, 0);
+        __syncwarp();
+        continue;
+      }
+      const uint32_t di = e.dinfo(d), di1 = e.dinfo(d + 1);
+      const int a0 = (int)(di & 0xFFFFu), nt = (int)(di1 & 0xFFFFu) - a0;
+      /* the pool: units [a0, a0 + nt) with the wanted flag.  At most 32 units (all but the hubs): one window word, every
+       * lane computes the same weight and pick, no reduction; else 32 words (1024 units) per round across the lanes */
+      const bool small = nt <= 32;
+      uint32_t xs = 0;
+      int total = 0;
+      if (small) {
+        xs = (funnel_r(bits[a0 >> 5], bits[(a0 >> 5) + 1], a0 & 31) ^ flipw) & lowmask(nt);
+        total = popc(xs);
+      } else {
+        for (int base = 0; base < nt; base += 1024) {
+          const int q0 = a0 + base + 32 * lane;
+          uint32_t x = 0;
+          if (base + 32 * lane < nt) x = (funnel_r(bits[q0 >> 5], bits[(q0 >> 5) + 1], q0 & 31) ^ flipw) & lowmask0(nt - base - 32 * lane);
+          total += (int)__reduce_add_sync(CYG_FULL, (unsigned)popc(x));
+        }
+      }
+      if (total == 0) continue;
+      if ((kdraw >> 7) != kblk) { /* refill: 128 draws */
+        kblk = kdraw >> 7;
+        philox4x32_10(e.rng.env, e.rng.epoch, (uint32_t)site, (kblk << 5) + (uint32_t)lane, e.rng.k0, e.rng.k1, blk);
+      }
+      const int from = (int)((kdraw >> 2) & 31u);
+      const uint32_t x0 = __shfl_sync(CYG_FULL, blk[0], from), x1 = __shfl_sync(CYG_FULL, blk[1], from);
+      const uint32_t x2 = __shfl_sync(CYG_FULL, blk[2], from), x3 = __shfl_sync(CYG_FULL, blk[3], from);
+      const uint32_t j = kdraw & 3u;
+      kdraw++;
+      int r = (int)below(j == 0 ? x0 : j == 1 ? x1 : j == 2 ? x2 : x3, (uint32_t)total);
+      int q = -1;
+      if (small) {
+        q = a0 + select_in_word(xs, r);
+      } else {
+        for (int base = 0; base < nt && q < 0; base += 1024) { /* uniform: q is */
+          const int q0 = a0 + base + 32 * lane;
+          uint32_t x = 0;
+          if (base + 32 * lane < nt) x = (funnel_r(bits[q0 >> 5], bits[(q0 >> 5) + 1], q0 & 31) ^ flipw) & lowmask0(nt - base - 32 * lane);
+          const int pc = popc(x);
+          int incl = pc;
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const int y = __shfl_up_sync(CYG_FULL, incl, dd);
+            if (lane >= dd) incl += y;
+          }
+          const int tot_r = __shfl_sync(CYG_FULL, incl, 31), excl = incl - pc;
+          const bool mine = r >= excl && r < incl;
+          const uint32_t mm = __ballot_sync(CYG_FULL, mine);
+          if (mm) {
+            const int qq = mine ? q0 + select_in_word(x, r - excl) : 0;
+            q = __shfl_sync(CYG_FULL, qq, __ffs((int)mm) - 1);
+          } else {
+            r -= tot_r;
+          }
+        }
+      }
+      if (lane == 0) e.set_pair_blocked(q, !want);
+      cnt++;
+      __syncwarp();
+    }
+    if (lane == 0 && cnt) { e.scal(want ? CYG_S_EADD : CYG_S_EBLK) += cnt; dirty = true; }
+    __syncwarp();
+    return true;
+  }
+
+  /* attacker action 1, exploit + lateral movement (volt:1126-1185): sources in ascending id order, each source's
+   * out-units scanned 32 at a time (lane = unit): blocked units are skipped unlogged, the first unit whose far endpoint
+   * qualifies is the hit, the unblocked units in front of it are the hops logged.  Returns false when the env must take
+   * the one-lane path (extra edges). */
+  static __device__ __forceinline__ bool attack(E& e, const typename E::Act& a) {
+    const int lane = lane_id();
+    const int nx = e.n_extra();
+    uint32_t xs0 = 0, xs1 = 0; /* sources with extra out-edges */
+    if (nx > 0) extra_endpoints(e, true, xs0, xs1, lane);
+    const uint32_t* const xl = e.extra();
+    uint32_t s0 = e.pl(P_COMP, lane) | e.pl(P_OWNED, lane), s1 = e.pl(P_COMP, lane + 32) | e.pl(P_OWNED, lane + 32);
+    const bool has_blk = e.any_blocked();
+    __syncwarp();
+    const uint32_t* const bits = e.inc();
+    uint32_t logs_add = 0, zk = 0;
+    for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
+      int raw = a.ex(xi);
+      uint32_t zx = 0;
+      if (e.needs_zday_draw(raw)) zx = draw_at(e.rng, SITE_ZDAY, zk++);
+      raw = e.resolve_exploit(raw, zx);
+      if (raw < 0) continue;
+      uint32_t t0 = s0, t1 = s1;
+      for (;;) {
+        const int s = pop_lowest(t0, t1, lane);
+        if (s < 0) break;
+        const bool is_dc = e.devbit(e.n->o_dc, s);
+        const uint32_t di = e.dinfo(s);
+        const int a0 = (int)(di & 0xFFFFu), no = (int)(di >> 16);
+        int hit = -1, walked = 0;
+        /* extra out-edges of s (unblocked ones): the lowest qualifying target competes with the base scan, the unblocked
+         * ones in front of the hit are logged like base hops */
+        int ve = 0x7FFFFFFF;
+        const bool sx = nx > 0 && test_bit(xs0, xs1, s);
+        if (sx) {
+          for (int base = 0; base < nx; base += 32) {
+            const uint32_t xe = base + lane < nx ? xl[base + lane] : 0xFFFFFFFFu;
+            int cand = 0x7FFFFFFF;
+            if ((int)(xe & CYG_X_IDMASK) == s && !(xe & CYG_X_BLOCKED) && xe != 0xFFFFFFFFu) {
+              const int v = (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK);
+              const uint32_t vb = 1u << (v & 31);
+              const int vw = v >> 5;
+              if (is_dc || (e.m_reach(vw) & vb) || (!(e.pl(P_COMP, vw) & vb) && (e.pl(P_KNOWN, vw) & vb) && (e.m_vuln(raw, vw) & vb))) cand = v;
+            }
+            ve = min(ve, (int)__reduce_min_sync(CYG_FULL, (unsigned)cand));
+          }
+        }
+        bool stopped = false;
+        for (int base = 0; base < no && !stopped; base += 32) { /* uniform */
+          const int q = a0 + base + lane;
+          const bool in = base + lane < no;
+          int v = 0;
+          bool open = false, ok = false;
+          if (in) {
+            v = unit_other(e.unit(q));
+            open = !(has_blk && ((bits[q >> 5] >> (q & 31)) & 1u));
+            const uint32_t vb = 1u << (v & 31);
+            const int vw = v >> 5;
+            ok = open && (is_dc || (e.m_reach(vw) & vb) || (!(e.pl(P_COMP, vw) & vb) && (e.pl(P_KNOWN, vw) & vb) && (e.m_vuln(raw, vw) & vb)));
+          }
+          const uint32_t openm = __ballot_sync(CYG_FULL, open), okm = __ballot_sync(CYG_FULL, ok);
+          const uint32_t stopm = okm | __ballot_sync(CYG_FULL, in && v > ve); /* ascending ids: past ve the extra edge comes first */
+          if (stopm) {
+            const int hl = __ffs((int)stopm) - 1;
+            const int vh = __shfl_sync(CYG_FULL, v, hl);
+            if (((okm >> hl) & 1u) && vh < ve) hit = vh;
+            walked += popc(openm & lanes_below(hl));
+            stopped = true;
+          } else {
+            walked += popc(openm);
+          }
+        }
+        if (hit < 0 && ve != 0x7FFFFFFF) hit = ve;
+        if (sx) { /* unblocked extra edges of s in front of the hit (all of them when nothing is hit) */
+          for (int base = 0; base < nx; base += 32) {
+            const uint32_t xe = base + lane < nx ? xl[base + lane] : 0xFFFFFFFFu;
+            const bool mine = xe != 0xFFFFFFFFu && (int)(xe & CYG_X_IDMASK) == s && !(xe & CYG_X_BLOCKED) &&
+                              (hit < 0 || (int)((xe >> CYG_X_V_SHIFT) & CYG_X_IDMASK) < hit);
+            walked += popc(__ballot_sync(CYG_FULL, mine));
+          }
+        }
+        logs_add += (uint32_t)walked + (hit >= 0 ? 1u : 0u);
+        if (hit >= 0 && lane == 0) {
+          e.pl(P_COMP, hit >> 5) |= 1u << (hit & 31);
+          if (is_dc) e.pl(P_CBY0 + raw, hit >> 5) |= 1u << (hit & 31);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) e.scal(CYG_S_LOGS) += logs_add;
+    __syncwarp();
+    return true;
   }
 };
 

@@ -219,13 +219,15 @@ struct Stream {
 };
 
 /* ---- per-env view over an internal record ---------------------------------
- * SM = true : the record and the hot tables are addressed as offsets into the kernel's dynamic shared memory
+ * SM = 1    : the record and the hot tables are addressed as offsets into the kernel's dynamic shared memory
+ * SM = 2    : the record and the hot PREFIX of the tables in shared memory, the rest of the tables (large networks: the
+ *             adjacency bit rows) through pointers
  *             (every access is an LDS with a constant-bank offset);
- * SM = false: plain pointers (host build, and the small kernels that work on records in global memory). */
+ * SM = 0    : plain pointers (host build, and the small kernels that work on records in global memory). */
 #ifdef __CUDACC__
 extern __shared__ __align__(128) uint32_t cyg_smem[];
 #endif
-template <int W, bool SM = false>
+template <int W, int SM = 0>
 struct Env {
   const Net* n;
   uint32_t* rec;   /* the record (SM: unused) */
@@ -259,13 +261,14 @@ struct Env {
   }
   CYG_HD uint32_t T(uint32_t i) const {
 #ifdef __CUDA_ARCH__
-    if (SM) return cyg_smem[to + i];
+    if (SM == 1) return cyg_smem[to + i];
+    if (SM == 2 && i < n->hot_words) return cyg_smem[to + i];
 #endif
     return th[i];
   }
   CYG_HD const uint32_t* Tp(uint32_t i) const {
 #ifdef __CUDA_ARCH__
-    if (SM) return cyg_smem + to + i;
+    if (SM == 1) return cyg_smem + to + i;
 #endif
     return th + i;
   }

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)(env0 + tid) * 4);
       const uint32_t h0 = hv.x;
       const int blk = bl_t ? (int)bl_t[env0 + tid] : p.net.cfg.base_line;
-      const int xt = Env<W, true>::exec_type(p.net.cfg, h0, blk) & 15;
+      const int xt = Env<W, 1>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
         int nd = (int)(hv.z & 0xFFFFu);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   const bool lower = (tid & ~31) < nb; /* warps that own envs in the thread-per-env phases */
   bool deferred = false;
   const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
-  Env<W, true> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
+  Env<W, 1> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
                  (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
   long long t_begin = 0;
 #ifdef CYG_PHASE_TIMING
@@ -381,13 +381,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             if (!((s_def[ppos >> 5] >> (ppos & 31)) & 1u)) continue; /* its own thread did it in phase A */
             const int el_b = s_perm[ppos];
             const int env_b = env0 + el_b;
-            Env<W, true> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
+            Env<W, 1> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                             (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
             eb.resume_epoch();
             uint32_t act[4 + W];
             load_action(env_b, act);
-            typename Env<W, true>::Act a;
-            Env<W, true>::decode(act, act + 4, nullptr, a);
+            typename Env<W, 1>::Act a;
+            Env<W, 1>::decode(act, act + 4, nullptr, a);
             double tcost = 0.0;
             bool tdirty = false;
             long long tb0 = p.dbg_cycles ? clock64() : 0;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             } else if (kind == 1) {
               Coop<W>::attack(eb, a);
             } else {
-              const int atype_b = Env<W, true>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
+              const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
               Coop<W>::defender(eb, a, atype_b, tcost, tdirty);
             }
             if (lane == 0) {
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   CYG_CTA_MARK(4);
         /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
         if (deferred) {
-          e = Env<W, true>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
+          e = Env<W, 1>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
                            (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4)); /* nothing of it stays live across phase B */
           if (bl_t) e.bl = (int)bl_t[env];
           e.resume_epoch();
@@ -495,20 +495,78 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
  *      shared memory, so this first correct path steps one env per thread straight on the records in global
  *      memory with the tables read through L2.  Same transition code (cyg_core.cuh), no staging, no sort. ---- */
 template <int W>
-__global__ void __launch_bounds__(64) cyg_step_generic_kernel(const __grid_constant__ StepParams p) {
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= p.B) return;
-  const int M = p.net.M;
-  Env<W, false> e(&p.net, p.recs + (size_t)env * p.net.S, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
-                  (uint32_t)(p.env_id0 + env));
-  if (p.bl_env) e.bl = (int)p.bl_env[env];
-  const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
-  float raw, shaped;
-  int32_t done;
-  const int Wm = p.net.Wm;
-  e.step(p.hdr + (size_t)env * 4, p.mask + (size_t)env * Wm, ord, (size_t)p.B * 4, (size_t)p.B * Wm, (size_t)p.B * p.order_stride,
-         p.G, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * Wm : nullptr);
-  p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+__global__ void __launch_bounds__(256) cyg_step_generic_kernel(const __grid_constant__ StepParams p) {
+  /* block_envs envs per CTA, spread over all SMs (B = 1024 -> 7 per CTA); their records (~6.4 KB each at M = 2000) are
+   * staged in shared memory by coalesced copies.  Phase A, thread per env: epoch, busy tick and the actions whose cost
+   * is a few passes over the 64-word planes.  Phase B, warp per env: block / unblock and the lateral-movement scan
+   * (BigCoop, cyg_coop.cuh) -- one thread walking ~1000 listed devices or ~800 sources over 64-word rows took 6-9 ms
+   * per launch.  Phase C, thread per env: the rest of the step. */
+  const int NB = p.block_envs, S = p.net.S, M = p.net.M, tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+  const int env0 = blockIdx.x * NB, nb = min(NB, p.B - env0), Wm = p.net.Wm;
+  uint32_t* g_rec = p.recs + (size_t)env0 * S;
+  uint32_t* s_misc = cyg_smem + (size_t)NB * S + 4; /* per env: heavy kind, cost (float bits), dirty, atype */
+  const uint32_t tab_off = (uint32_t)(NB * S + 4 + 4 * NB); /* the hot tables (masks, device ranges, unit table = CSR) behind them */
+  for (int i = tid; i < nb * S; i += NT) cyg_smem[i] = g_rec[i];
+  for (int i = tid; i < (int)p.net.hot_words; i += NT) cyg_smem[tab_off + i] = p.net.blob[i];
+  __syncthreads();
+  const bool plain = !(p.flags & CYG_STEP_GROUPED) && p.order == nullptr;
+  const int env = env0 + tid;
+  int mode = 0;
+  if (tid < nb) {
+    Env<W, 2> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env), (uint32_t)(tid * S), tab_off);
+    if (p.bl_env) e.bl = (int)p.bl_env[env];
+    const uint32_t* hdr = p.hdr + (size_t)env * 4;
+    const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
+    mode = (int)((hdr[0] >> 8) & 1u);
+    int atype = e.step_pre(hdr, p.flags);
+    int heavy = 0;
+    if (plain) {
+      if (mode == CYG_MODE_DEFENDER && (atype == 6 || atype == 9)) heavy = 1;
+      if (mode == CYG_MODE_ATTACKER && atype == 1 && e.bl != CYG_BL_NO_ATTACK) heavy = 2;
+    }
+    double cost = 0.0;
+    bool dirty = false;
+    if (!heavy) atype = e.step_act(hdr, p.mask + (size_t)env * Wm, ord, (size_t)p.B * 4, (size_t)p.B * Wm, (size_t)p.B * p.order_stride, p.G, p.flags, atype, cost, dirty);
+    s_misc[4 * tid] = (uint32_t)heavy; s_misc[4 * tid + 1] = __float_as_uint((float)cost); s_misc[4 * tid + 2] = dirty ? 1u : 0u; s_misc[4 * tid + 3] = (uint32_t)atype;
+  }
+  __syncthreads();
+  for (int el = tid >> 5; el < nb; el += NT >> 5) { /* phase B: one warp per heavy env */
+    const int heavy = (int)s_misc[4 * el];
+    if (!heavy) continue;
+    const int env_b = env0 + el;
+    Env<W, 2> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env_b), (uint32_t)(el * S), tab_off);
+    if (p.bl_env) e.bl = (int)p.bl_env[env_b];
+    e.resume_epoch();
+    typename Env<W, 2>::Act a;
+    Env<W, 2>::decode(p.hdr + (size_t)env_b * 4, p.mask + (size_t)env_b * Wm, nullptr, a);
+    double cost = 0.0;
+    bool dirty = false;
+    if (lane == 0) e.load_costs();
+    const bool done = heavy == 1 ? BigCoop<W>::flip(e, a, (int)s_misc[4 * el + 3], cost, dirty) : BigCoop<W>::attack(e, a);
+    if (lane == 0) {
+      if (!done) { /* extra edges / inconsistent header: the one-lane form */
+        int at = (int)s_misc[4 * el + 3];
+        e.step_act(p.hdr + (size_t)env_b * 4, p.mask + (size_t)env_b * Wm, nullptr, 0, 0, 0, 1, p.flags, at, cost, dirty);
+      } else {
+        e.store_costs();
+      }
+      s_misc[4 * el + 1] = __float_as_uint((float)cost); s_misc[4 * el + 2] = dirty ? 1u : 0u;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (tid < nb) {
+    Env<W, 2> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env), (uint32_t)(tid * S), tab_off);
+    if (p.bl_env) e.bl = (int)p.bl_env[env];
+    e.resume_epoch();
+    float raw, shaped;
+    int32_t done;
+    e.step_post(mode, (double)__uint_as_float(s_misc[4 * tid + 1]), s_misc[4 * tid + 2] != 0, p.flags, &raw, &shaped, &done,
+                p.pre_masks ? p.pre_masks + (size_t)env * 3 * Wm : nullptr);
+    p.raw[env] = raw; p.shaped[env] = shaped; p.done[env] = done;
+  }
+  __syncthreads();
+  for (int i = tid; i < nb * S; i += NT) g_rec[i] = cyg_smem[i];
 }
 
 /* ---- randomize_compromise_and_ownership: thread per env on the global record ---- */
@@ -749,7 +807,7 @@ struct WImpl {
       if (e != cudaSuccess) return e;
       return cudaFuncSetAttribute(cyg_step_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     } else {
-      return cudaSuccess;
+      return cudaFuncSetAttribute(cyg_step_generic_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     }
   }
   static void step(bool plain, int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p) {
@@ -757,7 +815,7 @@ struct WImpl {
       if (plain) cyg_step_kernel<KW, true><<<blocks, threads, smem, st>>>(p);
       else cyg_step_kernel<KW, false><<<blocks, threads, smem, st>>>(p);
     } else {
-      cyg_step_generic_kernel<KW><<<blocks, threads, 0, st>>>(p);
+      cyg_step_generic_kernel<KW><<<blocks, threads, smem, st>>>(p);
     }
   }
   static void import_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_import_kernel<KW><<<blocks, threads, 0, st>>>(p); }
@@ -848,8 +906,19 @@ static int pick_block_envs(const cyg_env_s* h, int requested) {
 
 static int configure_step(cyg_env_s* h) {
   if (!wops(h->W)) return fail(CYG_E_INVAL, "this build has no kernels for the network's plane width");
-  if (h->W > CYG_MAX_W) { /* generic global-memory kernel: no staging */
-    h->smem_bytes = 0;
+  if (h->W > CYG_MAX_W) { /* large networks: a few envs per CTA so that every SM gets some, records staged in shared memory */
+    int per_sm = (h->B + h->n_sms - 1) / h->n_sms;
+    const size_t rec_bytes = (size_t)h->net.S * 4;
+    const size_t tab_bytes = (size_t)h->net.hot_words * 4;
+    if (tab_bytes + rec_bytes + 64 > 220 * 1024) return fail(CYG_E_INVAL, "network tables do not fit in shared memory");
+    int cap = (int)((220 * 1024 - tab_bytes - 64) / (rec_bytes + 16));
+    if (cap < 1) return fail(CYG_E_INVAL, "a record does not fit in shared memory");
+    h->NB = per_sm < 1 ? 1 : (per_sm > cap ? cap : per_sm);
+    if (h->NB > 128) h->NB = 128;
+    h->smem_bytes = (size_t)h->NB * rec_bytes + 16 + (size_t)h->NB * 16 + tab_bytes; /* records, pad, 4 words of phase hand-over per env, hot tables */
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CU(wops(h->W)->set_smem_optin(max_optin));
     return CYG_OK;
   }
   SmemPlan sp = smem_plan(h->net.hot_words, h->net.S, h->NB);
@@ -1014,7 +1083,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
   if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
   if (h->W > CYG_MAX_W) {
-    wops(h->W)->step(false, (h->B + 63) / 64, 64, 0, (cudaStream_t)stream, p);
+    wops(h->W)->step(false, (h->B + h->NB - 1) / h->NB, 256, h->smem_bytes, (cudaStream_t)stream, p);
     if (out->obs) { /* post-evolve observation rows: a second launch on the generic path */
       h->launches++;
       CU(cudaGetLastError());

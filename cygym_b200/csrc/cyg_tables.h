@@ -86,8 +86,9 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   if ((S & 1) == 0) S++; /* odd stride: thread-per-env accesses to shared memory are bank-conflict free */
   n.S = S;
   b.words.clear();
-  /* hot section (staged in shared memory by the step kernel) */
-  b.o_adj = tb_alloc(b, (size_t)M * W);
+  /* hot section (staged in shared memory by the step kernels).  The adjacency bit rows come last: for the large
+   * networks (W = 64: 8 KB per device row set, 512 KB at M = 2000) they stay in global memory and the hot prefix ends
+   * in front of them -- the large-network kernel walks the unit table (CSR) instead. */
   b.o_dc = tb_alloc(b, W);
   b.o_server = tb_alloc(b, W);
   b.o_reach = tb_alloc(b, W);
@@ -98,7 +99,9 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   b.o_unit = tb_alloc(b, (size_t)U2 + 1);
   b.o_omulti = tb_alloc(b, M);
   b.o_static = tb_alloc(b, M);
-  b.hot_words = b.words.size();
+  if (W > CYG_MAX_W) b.hot_words = b.words.size();
+  b.o_adj = tb_alloc(b, (size_t)M * W);
+  if (W <= CYG_MAX_W) b.hot_words = b.words.size();
   /* cold section: read through L1/L2 (canonical pair <-> unit map for import / export, observation rows) */
   b.o_pair2unit = tb_alloc(b, (size_t)E + 1);
   b.o_os = tb_alloc(b, M);

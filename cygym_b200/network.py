@@ -155,6 +155,16 @@ def synthetic_network(M=100, num_of_device=None, n_subnets=8, seed=0, n_cve_rows
                 add_edge(o, v)
             for v in rng.choice(M, size=k_extra, replace=False):
                 add_edge(o, int(v))
+        # ... and the bidirectional hub-star among the active owned devices (hub = lowest id) that the reference's FIRST
+        # evolve_network() adds to the graph (CyberDefenseEnv.py:738-774): generated as base edges, i.e. the network as it
+        # stands after that first call and the cache rebuild that follows it (volt:1329 -> :456).  Without it every env
+        # would carry 2 (n_owned - 1) extra edges in its per-env list from the second step on.
+        oa = sorted(o for o in owned if o in active)
+        for i in oa[1:]:
+            if (oa[0], i) not in pair:
+                add_edge(oa[0], i)
+            if (i, oa[0]) not in pair:
+                add_edge(i, oa[0])
     for (u, v) in list(pair):
         pair[(u, v)] = min(pair[(u, v)], 4)
 
