@@ -495,6 +495,40 @@ def main():
         errs = max(errs, legs["c4"]["error_flags"])
         del s4
 
+    if world == 1 and not a.no_legs and not a.obs:
+        # (6) C1: ONE env behind the reference's Gym surface (init_experiments.py defaults: numOfDevice 10, Max_network_size 20),
+        #     sample_action() + step() on alternating turns: host-side latency per step, wall clock
+        from cygym_b200.volt_typhoon_env import Volt_Typhoon_CyberDefenseEnv
+        genv1 = Volt_Typhoon_CyberDefenseEnv(device=dev, seed=a.seed)
+        genv1.numOfDevice, genv1.Max_network_size = 10, 20
+        genv1.initialize_environment()
+
+        def gym_steps(n, policy):
+            for t in range(n):
+                genv1.mode = "defender" if t % 2 == 0 else "attacker"
+                if policy == "sample":
+                    act = genv1.sample_action()
+                    act = (8 if genv1.mode == "defender" and act[0] == 10 else act[0], act[1], act[2], act[3])
+                else:
+                    act = None
+                genv1.step(act)
+
+        res = {}
+        for policy in ("sample", "none"):
+            gym_steps(30, policy)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            gym_steps(300, policy)
+            torch.cuda.synchronize()
+            res[policy] = 300 / (time.perf_counter() - t0)
+        refpy = (reference_python_record() or {}).get("sizes", {}).get("20", {})
+        legs["c1"] = {"what": "C1: one env through the drop-in Volt_Typhoon_CyberDefenseEnv (batch of 1; every step = action packing, "
+                              "H2D, one kernel, one D2H of rewards + pre-evolve masks + the 6-tuple), wall clock on the host",
+                      "steps_per_s_sample_action_plus_step": res["sample"], "steps_per_s_step_only_none_action": res["none"],
+                      "reference_python_steps_per_s_1_core": refpy.get("steps_per_s_1_core"),
+                      "note": "a single 20-device env is launch- and PCIe-latency bound on a GPU; the reference's pure-Python step is "
+                              "the faster one at this size -- the batched VectorCyberDefenseEnv is the product"}
+
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0, e2e[4] if e2e else 0.0, ms1], dtype=torch.float64, device=dev)
     if world > 1:

@@ -86,6 +86,11 @@ struct StepParams {
   int bl_stride;                  /* fused steps: bl_env row of step t starts at t * bl_stride (0: one row for all) */
   int B, env_id0, G, order_stride, obs_mode, block_envs;
   uint32_t flags;
+  /* rollouts (cyg_rollout): action rows are shared by runs of envs -- env b reads row (row_base + b) / envs_per_row of
+   * the n_rows rows of a step (envs_per_row == 0: one row per env, n_rows == B) -- and the raw rewards are summed per env */
+  long long row_base;
+  int envs_per_row, n_rows;
+  double* ret_acc;      /* optional [2][B]: += raw reward, row 0 defender turns, row 1 attacker turns */
   int T;                /* plain steps fused into this launch (cyg_step_multi): hdr / mask hold T consecutive batches,
                            raw / shaped / done T consecutive [B] rows; the records stay in shared memory in between */
 };
@@ -223,13 +228,15 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   const int lane = tid & 31;
   for (int t = 0; t < T; t++) { /* the steps fused into this launch; the records stay in shared memory */
   const bool last = t == T - 1;
-  const uint32_t* hdr_t = p.hdr + (size_t)t * p.B * 4 * (PLAIN ? 1 : 0);
-  const uint32_t* mask_t = p.mask + (size_t)t * p.B * W * (PLAIN ? 1 : 0);
-  float* raw_t = p.raw + (size_t)t * p.B;
-  float* shaped_t = p.shaped + (size_t)t * p.B;
-  int32_t* done_t = p.done + (size_t)t * p.B;
+  const uint32_t* hdr_t = p.hdr + (size_t)t * p.n_rows * 4 * (PLAIN ? 1 : 0);
+  const uint32_t* mask_t = p.mask + (size_t)t * p.n_rows * W * (PLAIN ? 1 : 0);
+  float* raw_t = p.raw ? p.raw + (size_t)t * p.B : nullptr;
+  float* shaped_t = p.shaped ? p.shaped + (size_t)t * p.B : nullptr;
+  int32_t* done_t = p.done ? p.done + (size_t)t * p.B : nullptr;
   const uint8_t* bl_t = p.bl_env ? p.bl_env + (size_t)t * p.bl_stride : nullptr; /* base_line rows may change per step */
-  if (PLAIN && !last && tid < nb) { /* the next step's action rows of this block: into L2 while this step runs */
+  /* the action row of env (index into this step's n_rows rows) */
+  auto arow = [&](int env_i) -> size_t { return p.envs_per_row ? (size_t)((p.row_base + env_i) / p.envs_per_row) : (size_t)env_i; };
+  if (PLAIN && !last && tid < nb && !p.envs_per_row) { /* the next step's action rows of this block: into L2 while this step runs */
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hdr_t + ((size_t)p.B + env0 + tid) * 4));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_t + ((size_t)p.B + env0 + tid) * W));
   }
@@ -242,9 +249,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   int key = 0;
   if (tid < nb) {
     if (!grouped) {
-      const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)(env0 + tid) * 4);
+      const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + arow(env0 + tid) * 4);
       const uint32_t h0 = hv.x;
-      const int blk = bl_t ? (int)bl_t[env0 + tid] : p.net.cfg.base_line;
+      const int blk = bl_t ? (int)bl_t[arow(env0 + tid)] : p.net.cfg.base_line;
       const int xt = Env<W, 1>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
@@ -321,13 +328,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       const uint16_t* ord = (!PLAIN && p.order) ? p.order + (size_t)env * p.order_stride : nullptr;
       int atype = 0;
       if (tid < nb) {
-        uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + (size_t)env * 4);
+        uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + arow(env) * 4);
         act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-        for (int w = 0; w < W; w++) act[4 + w] = mask_t[(size_t)env * W + w];
+        for (int w = 0; w < W; w++) act[4 + w] = mask_t[arow(env) * W + w];
         t_begin = p.dbg_cycles ? clock64() : 0;
         mode = (int)((act[0] >> 8) & 1u);
-        if (bl_t) e.bl = (int)bl_t[env];
+        if (bl_t) e.bl = (int)bl_t[arow(env)];
         atype = e.step_pre(act, p.flags);
         deferred = coop_ok && Coop<W>::is_heavy(e, mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
       }
@@ -355,10 +362,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
         __syncwarp();
         auto load_action = [&](int env_b, uint32_t* act) {
-          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hdr_t + (size_t)env_b * 4)); /* phase A read these lines: L1 */
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hdr_t + arow(env_b) * 4)); /* phase A read these lines: L1 */
           act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = __ldg(mask_t + (size_t)env_b * W + w);
+          for (int w = 0; w < W; w++) act[4 + w] = __ldg(mask_t + arow(env_b) * W + w);
         };
         /* B1: block / unblock (keys 6, 9; the longest lists first), B2: attacker exploit + lateral movement (key 16|1),
          * B3: clean / revert / upgrade (keys 1, 3, 4).  One env per warp; perm[] holds each kind as a contiguous run. */
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             } else if (kind == 1) {
               Coop<W>::attack(eb, a);
             } else {
-              const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[env_b] : p.net.cfg.base_line);
+              const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[arow(env_b)] : p.net.cfg.base_line);
               Coop<W>::defender(eb, a, atype_b, tcost, tdirty);
             }
             if (lane == 0) {
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
         if (deferred) {
           e = Env<W, 1>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
                            (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4)); /* nothing of it stays live across phase B */
-          if (bl_t) e.bl = (int)bl_t[env];
+          if (bl_t) e.bl = (int)bl_t[arow(env)];
           e.resume_epoch();
           cost = (double)s_out[el];
           dirty = __float_as_int(s_out[NB + el]) != 0;
@@ -433,7 +440,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       float raw, shaped;
       int32_t done;
       e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-      raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done;
+      if (raw_t) { raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done; }
+      if (p.ret_acc) p.ret_acc[(size_t)mode * p.B + env] += (double)raw;
     }
     if (pass == 0 && tid < nb) {
 #ifdef CYG_PHASE_TIMING
@@ -589,6 +597,17 @@ __global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
   if (p.env_mask && !p.env_mask[env]) return;
   Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
   e.randomize();
+}
+
+/* _rebuild_graph_cache() called from outside a step (DoubleOracle.restore, do_agent.py:891-895; reset(from_init),
+ * volt:1933-1936): the rebuilt cache forgets every block (volt:476).  New edges are visible to the kernels at once. */
+template <int W>
+__global__ void cyg_rebuild_kernel(const __grid_constant__ SimpleParams p) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  if (p.env_mask && !p.env_mask[env]) return;
+  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
+  e.rebuild_cache();
 }
 
 template <int W>
@@ -789,6 +808,7 @@ struct WOps {
   void (*import_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
   void (*export_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
   void (*randomize)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
+  void (*rebuild)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
   void (*sample)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
   void (*observe)(int blocks, int threads, cudaStream_t st, const ObsParams& p);
 };
@@ -821,12 +841,13 @@ struct WImpl {
   static void import_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_import_kernel<KW><<<blocks, threads, 0, st>>>(p); }
   static void export_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_export_kernel<KW><<<blocks, threads, 0, st>>>(p); }
   static void randomize(int blocks, int threads, cudaStream_t st, const SimpleParams& p) { cyg_randomize_kernel<KW><<<blocks, threads, 0, st>>>(p); }
+  static void rebuild(int blocks, int threads, cudaStream_t st, const SimpleParams& p) { cyg_rebuild_kernel<KW><<<blocks, threads, 0, st>>>(p); }
   static void sample(int blocks, int threads, cudaStream_t st, const SimpleParams& p) { cyg_sample_kernel<KW><<<blocks, threads, 0, st>>>(p); }
   static void observe(int blocks, int threads, cudaStream_t st, const ObsParams& p) { cyg_observe_kernel<KW><<<blocks, threads, 0, st>>>(p); }
 };
 extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
   typedef WImpl<CYG_TU_W> I;
-  static const WOps ops = {I::set_smem_optin, I::step, I::import_state, I::export_state, I::randomize, I::sample, I::observe};
+  static const WOps ops = {I::set_smem_optin, I::step, I::import_state, I::export_state, I::randomize, I::rebuild, I::sample, I::observe};
   return &ops;
 }
 #else /* ---- the C-ABI translation unit ---- */
@@ -1076,6 +1097,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
   p.T = n_steps;
+  p.row_base = 0; p.envs_per_row = 0; p.n_rows = h->B; p.ret_acc = nullptr;
   p.block_envs = h->NB;
   const bool plain = !(step_flags & CYG_STEP_GROUPED) && a->order == nullptr; /* the hot form: see cyg_step_kernel */
   int blocks = (h->B + h->NB - 1) / h->NB;
@@ -1097,6 +1119,34 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   return CYG_OK;
 }
 
+int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, void* stream) {
+  if (!h || !a || !a->hdr || !a->mask || !a->returns) return fail(CYG_E_INVAL, "null argument");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  if (h->W > CYG_MAX_W) return fail(CYG_E_INVAL, "cyg_rollout: networks of at most 128 device slots");
+  if (a->n_steps < 1 || a->n_rows < 1 || a->envs_per_row < 1 || a->row_base < 0) return fail(CYG_E_INVAL, "cyg_rollout: bad sizes");
+  if ((a->row_base + h->B - 1) / a->envs_per_row >= a->n_rows) return fail(CYG_E_INVAL, "cyg_rollout: an env's action row is beyond n_rows");
+  if (step_flags & CYG_STEP_GROUPED) return fail(CYG_E_INVAL, "cyg_rollout: plain steps only");
+  if (((uintptr_t)a->hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
+  DeviceGuard g(h->device);
+  StepParams p;
+  p.net = h->net;
+  p.recs = h->state; p.ckpt = ckpt_of(h); p.xtra = xtra_of(h);
+  p.hdr = a->hdr; p.mask = a->mask; p.order = nullptr;
+  p.raw = nullptr; p.shaped = nullptr; p.done = nullptr; p.pre_masks = nullptr; p.obs = nullptr; p.dbg_cycles = nullptr;
+  p.bl_env = a->base_line; p.bl_stride = a->base_line ? a->n_rows : 0;
+  p.B = h->B; p.env_id0 = h->env_id0; p.G = 1; p.order_stride = 0; p.obs_mode = 0; p.flags = step_flags; p.T = a->n_steps;
+  p.row_base = a->row_base; p.envs_per_row = a->envs_per_row; p.n_rows = a->n_rows; p.ret_acc = a->returns;
+  p.block_envs = h->NB;
+  int blocks = (h->B + h->NB - 1) / h->NB;
+  int threads = ((2 * h->NB + 31) / 32) * 32;
+  if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
+  if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
+  wops(h->W)->step(true, blocks, threads, h->smem_bytes, (cudaStream_t)stream, p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
@@ -1104,6 +1154,18 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->randomize(blocks, threads, (cudaStream_t)stream, p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_rebuild_graph_cache(cyg_handle h, const uint8_t* env_mask, void* stream) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  DeviceGuard g(h->device);
+  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0};
+  int threads = 128, blocks = (h->B + threads - 1) / threads;
+  wops(h->W)->rebuild(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

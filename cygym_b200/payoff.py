@@ -16,14 +16,19 @@ COLUMNS = ("defender_return", "attacker_return", "compromised_fraction", "jobs_c
 
 
 class Strategy:
-    """The non-neural flavours of strategy.Strategy: baseline_name | actions (fixed sequence) | neither (no-op)."""
+    """The flavours of strategy.Strategy the evaluators serve: baseline_name | actions (fixed sequence) | actor (a torch
+    module: the parametric DDPG best responses, Actor of do_agent.py:357-371; evaluate_payoff_matrix_batched only) |
+    none of them (no-op)."""
 
-    def __init__(self, baseline_name=None, actions=None):
+    def __init__(self, baseline_name=None, actions=None, actor=None):
         self.baseline_name = baseline_name
         self.actions = list(actions) if actions is not None else None
+        self.actor = actor
 
     def decide(self, t_step):
         """(action, base_line to set or None) -- _strategy_decide_action (do_agent.py:707-764)."""
+        if self.actor is not None:
+            raise NotImplementedError("parametric strategies act on observations: evaluate_payoff_matrix_batched()")
         if self.baseline_name is not None:
             return None, self.baseline_name
         if self.actions:
@@ -100,67 +105,116 @@ def evaluate_payoff_matrix(network, def_strategies, att_strategies, n_rollouts, 
     return reduce_payoff(sums, n_rollouts, steps_per_episode, group=group)
 
 
+def decode_actions(raw, mode, n_types, M, X, n_app, W):
+    """DoubleOracle.decode_action (do_agent.py:935-998, the epsilon-free branch: evaluation) for a batch of actor outputs
+    raw [N, n_types + M + X + n_app] on the device -> (hdr [N, 4], mask [N, W]) int32.  action_type = argmax of the type
+    slice, device_indices = where(slice > 0) (ascending: the set form), exploit and app index = argmax of their slices."""
+    import torch
+    from .marl import _pack_mask
+    m = 1 if mode in (1, "attacker") else 0
+    at = raw[:, :n_types].argmax(1).to(torch.int32)
+    dev = raw[:, n_types:n_types + M] > 0
+    ex = raw[:, n_types + M:n_types + M + X].argmax(1).to(torch.int32)
+    app = raw[:, n_types + M + X:n_types + M + X + n_app].argmax(1).to(torch.int32) if n_app > 0 else torch.zeros_like(at)
+    hdr = torch.stack([(at & 0xFF) | (m << 8) | (1 << 16), ex & 0xFF, dev.sum(1).to(torch.int32), app], dim=1)
+    return hdr.contiguous(), _pack_mask(dev, W).contiguous()
+
+
+def _strategy_tables(def_strategies, att_strategies, T, M):
+    """Per-STRATEGY action rows of every turn (host, tiny): hdr [T, S, 4], mask [T, S, W], base_line code [T, S] (255 =
+    the strategy does not touch env.base_line on that turn), S = the side that moves on turn t."""
+    from .vector_env import ActionBatch
+    from . import _capi as K
+    hdr_s, mask_s, bl_s = [], [], []
+    for t in range(T):
+        mode = t & 1
+        decided = [(None, None) if st.actor is not None else st.decide(t) for st in (def_strategies if mode == 0 else att_strategies)]
+        for a, _ in decided:
+            if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
+                raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
+        h, m, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
+        hdr_s.append(h.view(np.int32)); mask_s.append(m.view(np.int32))
+        bl_s.append(np.array([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], np.uint8))
+    return hdr_s, mask_s, bl_s
+
+
 def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_rollouts, steps_per_episode=100, seed=0,
-                                   device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True, steps_per_launch=10):
+                                   device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True, steps_per_launch=None):
     """Same result as evaluate_payoff_matrix(), with ALL (pair, rollout) combinations in one batch: the flattened
-    index g = pair * n_rollouts + rollout is split contiguously over the ranks (env id == g, so the draw streams
-    do not depend on the number of ranks), `steps_per_launch` turns are ONE kernel launch (cyg_step_multi: the records
-    stay in shared memory between the turns), baselines act through per-env base_line rows (one per turn of the
-    launch, cyg_set_base_line_per_env_steps) and fixed-sequence strategies through per-pair action rows gathered to
-    the envs on the device.  Strategies with unsorted / repeated device lists are not handled here (use the
-    per-pair evaluator)."""
+    index g = pair * n_rollouts + rollout is split contiguously over the ranks (env id == g, so the draw streams do not
+    depend on the number of ranks).
+
+    Strategies that need no observation (baseline names, fixed sequences, the no-op) become per-PAIR tables of action
+    rows and base_line codes for all turns, uploaded ONCE and gathered inside the kernel (cyg_rollout): the whole
+    100-turn evaluation is `ceil(T / steps_per_launch)` launches (default: one) with no host work in between, the
+    records staying in shared memory between the turns of a launch and the returns summed per env on the device.
+
+    With a parametric strategy (Strategy(actor=...): the DDPG best responses) on either side the rollout is closed
+    loop: per turn one observation launch, one batched actor forward per parametric strategy on the rows of its envs,
+    decode_actions() on the device, one step launch.  Strategies with unsorted / repeated device lists are not handled
+    here (use the per-pair evaluator)."""
     import torch
     from .vector_env import ActionBatch, VectorCyberDefenseEnv
     from . import _capi as K
     nd, na = len(def_strategies), len(att_strategies)
-    P = nd * na
+    P, T = nd * na, int(steps_per_episode)
     lo, hi = shard_range(P * n_rollouts, rank, world)
     nloc = hi - lo
     sums = torch.zeros(P, len(COLUMNS), dtype=torch.float64, device=device)
     if nloc > 0:
-        M = network.M
+        M, W = network.M, network.W
         env = VectorCyberDefenseEnv(network, nloc, device=device, seed=seed, env_id0=lo, xcap=xcap)
         pair_of_env = (torch.arange(lo, hi, device=device) // n_rollouts)
-        i_of_pair = torch.arange(P, device=device) // na
-        j_of_pair = torch.arange(P, device=device) % na
+        i_of_pair = np.arange(P) // na
+        j_of_pair = np.arange(P) % na
         env.randomize_compromise_and_ownership()
         s = env.scalars
         for slot in (K.S_STEP, K.S_DEF_STEP, K.S_ATT_STEP, K.S_WORK, K.S_CKPT, K.S_DEFCOST, K.S_CLEANCOST, K.S_REVERT, K.S_SCAN):
             s[:, slot] = 0
-        bl_pair = torch.full((P,), K.BASE_LINES["Nash"], dtype=torch.uint8, device=device)
+        hdr_s, mask_s, bl_s = _strategy_tables(def_strategies, att_strategies, T, M)
+        # per-pair tables: the moving side's row of every turn, and the base_line each pair's env carries on that turn
+        # (a strategy that sets no base_line leaves it as the other player's last baseline left it, do_agent.py:716-719)
+        hdr_p = np.stack([hdr_s[t][i_of_pair if t % 2 == 0 else j_of_pair] for t in range(T)])
+        mask_p = np.stack([mask_s[t][i_of_pair if t % 2 == 0 else j_of_pair] for t in range(T)])
+        bl_p = np.zeros((T, P), np.uint8)
+        cur = np.full(P, K.BASE_LINES["Nash"], np.uint8)
+        for t in range(T):
+            nb = bl_s[t][i_of_pair if t % 2 == 0 else j_of_pair]
+            cur = np.where(nb == 255, cur, nb)
+            bl_p[t] = cur
+        hdr_d = torch.from_numpy(hdr_p).to(device).contiguous()
+        mask_d = torch.from_numpy(mask_p).to(device).contiguous()
+        bl_d = torch.from_numpy(bl_p).to(device).contiguous()
         ret = torch.zeros(2, nloc, dtype=torch.float64, device=device)
-        fuse = max(1, int(steps_per_launch)) if network.W <= 4 else 1
-        t0 = 0
-        while t0 < steps_per_episode:
-            # one chunk of turns = ONE launch (cyg_step_multi): per-pair action rows and base_line codes of every turn
-            # of the chunk are packed on the host ([Tc, P, ..], tiny) and gathered to the envs on the device
-            Tc = min(fuse, steps_per_episode - t0)
-            hdr_p, mask_p, bl_p = [], [], []
-            for t in range(t0, t0 + Tc):
+        any_nn = any(st.actor is not None for st in list(def_strategies) + list(att_strategies))
+        if not any_nn and W <= 4:
+            spl = T if not steps_per_launch else max(1, int(steps_per_launch))
+            for t0 in range(0, T, spl):
+                t1 = min(T, t0 + spl)
+                env.rollout(hdr_d[t0:t1], mask_d[t0:t1], bl_d[t0:t1], n_rollouts, lo, returns=ret)  # the mode of a turn is in its headers
+        else:
+            X, n_app = network.X, int(network.cfg.get("n_app_ids", 0))
+            side_of_env = [torch.from_numpy(i_of_pair).to(device)[pair_of_env], torch.from_numpy(j_of_pair).to(device)[pair_of_env]]
+            nn_rows = [[(k, st, (side_of_env[m_] == k).nonzero(as_tuple=True)[0]) for k, st in enumerate(sts) if st.actor is not None]
+                       for m_, sts in enumerate((def_strategies, att_strategies))]
+            for t in range(T):
                 mode = t & 1
-                strategies = def_strategies if mode == 0 else att_strategies
-                decided = [st.decide(t) for st in strategies]
-                for a, _ in decided:
-                    if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
-                        raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
-                hdr, mask, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
-                which = i_of_pair if mode == 0 else j_of_pair
-                new_bl = torch.tensor([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], dtype=torch.uint8, device=device)[which]
-                bl_pair = torch.where(new_bl == 255, bl_pair, new_bl)   # a strategy that sets no base_line leaves it as it was
-                hdr_p.append(torch.from_numpy(hdr.view(np.int32)).to(device)[which])
-                mask_p.append(torch.from_numpy(mask.view(np.int32)).to(device)[which])
-                bl_p.append(bl_pair)
-            if Tc == 1:
-                env.set_base_line_per_env(bl_p[0][pair_of_env])
-                raw, _, _ = env.step(ActionBatch(hdr_p[0][pair_of_env].contiguous(), mask_p[0][pair_of_env].contiguous()))
-                ret[t0 & 1] += raw.double()
-            else:
-                env.set_base_line_per_env(torch.stack(bl_p)[:, pair_of_env])
-                raw, _, _ = env.step_many(torch.stack(hdr_p)[:, pair_of_env].contiguous(), torch.stack(mask_p)[:, pair_of_env].contiguous())
-                r64 = raw.double()
-                ret[t0 & 1] += r64[0::2].sum(0)
-                ret[(t0 + 1) & 1] += r64[1::2].sum(0)
-            t0 += Tc
+                hdr_e = hdr_d[t][pair_of_env].contiguous()
+                mask_e = mask_d[t][pair_of_env].contiguous()
+                if nn_rows[mode]:
+                    obs = env.observe(1 + mode)  # _get_defender_state / _get_attacker_state of every env (do_agent.py:748)
+                    n_types = 14 if mode == 0 else 3  # get_num_action_types (volt:514-520): the actors' type slice
+                    for k, st, idx in nn_rows[mode]:
+                        if idx.numel() == 0:
+                            continue
+                        with torch.no_grad():
+                            raw_a = st.actor(obs[idx])
+                        h_k, m_k = decode_actions(raw_a, mode, n_types, M, X, n_app, W)
+                        hdr_e[idx] = h_k
+                        mask_e[idx] = m_k
+                env.set_base_line_per_env(bl_d[t][pair_of_env])
+                raw, _, _ = env.step(ActionBatch(hdr_e, mask_e))
+                ret[mode] += raw.double()
         info = env.info()
         cols = torch.stack([ret[0], ret[1], info["Compromised_devices"].double(), info["work_done"].double(),
                             info["Scan_count"].double(), info["defensive_cost"].double(), info["checkpoint_count"].double(),

@@ -161,3 +161,120 @@ def from_reference_env(env):
         turbo_ramp_steps=int(env.turbo_ramp_steps))
     template = dict(dev=dev, ckpt=ckpt, blocked=blocked, extra=np.zeros(0, np.uint32), scal=scal)
     return Network(row_ptr, col, mult, dev_static, os_val, ver_val, cfg, template)
+
+
+# ---- the reference's own on-disk format: a pickled env object (init_experiments.py:53-62, volt_typhoon_env.py:1904-1925) ----
+def load_reference_pickle(path):
+    """`initial_net_DO_its<N>.pkl` -> Network (template = the pickled env's state).  Unpickling needs the reference's
+    classes importable in this process (the file stores objects of volt_typhoon_env / CDSimulatorComponents); this
+    module itself never imports them.  Returns (network, env_object)."""
+    import pickle
+    with open(path, "rb") as f:
+        env = pickle.load(f)
+    if isinstance(env, dict):
+        raise ValueError("old dict snapshot {'simulator', 'state'} (volt:1884-1888): load it through a reference env's reset()")
+    env._rebuild_graph_cache()  # what reset(from_init=True) does right after loading (volt:1933-1936)
+    return from_reference_env(env), env
+
+
+def apply_state_to_reference_env(env, net, state):
+    """The inverse of from_reference_env for the DYNAMIC state: write a canonical state (dict of numpy arrays dev / ckpt
+    / blocked / extra / scal for ONE env, layout of include/cygym_b200.h) stepped on `net` into the live reference env
+    object it was flattened from, so that the reference can go on from where the kernels stopped -- or be pickled back
+    to disk.  Duck-typed: classes (Workload) are taken from the objects already in the graph."""
+    import sys
+    sim = env.simulator
+    devs = sim.subnet.net
+    M = net.M
+    dev = np.asarray(state["dev"], np.uint32)
+    ck = np.asarray(state["ckpt"], np.uint32)
+    sc = np.asarray(state["scal"], np.uint32)
+    exploits = list(sim.exploits)
+    Workload = getattr(sys.modules[type(devs[0]).__module__], "Workload")
+    for i in range(M):
+        d, w = devs[i], int(dev[i])
+        d.isCompromised = bool(w & DEV_COMP)
+        d.Known_to_attacker = bool(w & DEV_KNOWN)
+        d.Not_yet_added = bool(w & DEV_NYA)
+        d.attacker_owned = bool(w & DEV_OWNED)
+        d.removed_before = 1 if w & DEV_REMOVED else 0
+        d.busy_time = float((w >> DEV_BUSY_SHIFT) & 0xFF)
+        if w & DEV_HASWL:
+            wl = Workload()
+            wl.processing_time = (w >> DEV_PT_SHIFT) & 7
+            wl.adversarial, wl.assigned, wl.wtype = False, True, d.wtype
+            d.workload = wl
+        else:
+            d.workload = None
+        cb = (w >> DEV_CBY_SHIFT) & 0x3F
+        d.compromised_by = type(d.compromised_by)(exploits[e].id for e in range(len(exploits)) if (cb >> e) & 1)
+    env._device_ckpts = {}
+    for i in range(M):
+        k = int(ck[i])
+        if k & CK_VALID:
+            cb = (k >> DEV_CBY_SHIFT) & 0x3F
+            env._device_ckpts[i] = dict(
+                isCompromised=bool(k & CK_COMP), Known_to_attacker=bool(k & CK_KNOWN), Not_yet_added=bool(k & CK_NYA),
+                reachable_by_attacker=bool(k & CK_REACH),
+                workload=({"processing_time": (k >> DEV_PT_SHIFT) & 7, "adversarial": False} if k & CK_HASWL else None),
+                busy_time=float((k >> DEV_BUSY_SHIFT) & 0xFF),
+                compromised_by=[exploits[e].id for e in range(len(exploits)) if (cb >> e) & 1])
+    # extra (hub-star) edges go into the graph; the cache rebuild makes them visible and forgets the blocks (volt:476) ...
+    g = sim.subnet.graph
+    n_extra = int(sc[3]) >> 16
+    have = set(g.get_edgelist())
+    new_edges = [(int(x & 0xFFF), int((x >> 12) & 0xFFF)) for x in np.asarray(state["extra"], np.uint32)[:n_extra]]
+    add = [e for e in new_edges if e not in have]
+    if add:
+        g.add_edges(add)
+    env._rebuild_graph_cache()
+    # ... so the blocked set is put back after it
+    blocked = set()
+    bl = np.asarray(state["blocked"], np.uint32)
+    for u in range(M):
+        for e in range(int(net.row_ptr[u]), int(net.row_ptr[u + 1])):
+            if (int(bl[e >> 5]) >> (e & 31)) & 1:
+                blocked.add((u, int(net.col[e])))
+    for x in np.asarray(state["extra"], np.uint32)[:n_extra]:
+        if int(x) & (1 << 24):
+            blocked.add((int(x & 0xFFF), int((x >> 12) & 0xFFF)))
+    env._blocked = blocked
+    env._busy_devices = {devs[i] for i in range(M) if int(dev[i]) & DEV_BUSYSET}
+    if int(sc[2]) & 2:  # CYG_FL_SETS_INIT
+        env._active_ids = {i for i in range(M) if int(dev[i]) & DEV_ACTSET}
+        env._inactive_ids = {i for i in range(M) if not int(dev[i]) & DEV_ACTSET}
+    else:
+        for a in ("_active_ids", "_inactive_ids"):
+            if hasattr(env, a):
+                delattr(env, a)
+    env.checkpoint = {"simulator": sim, "state": env.state} if int(sc[2]) & 1 else None  # an alias, as checkpoint_variables stores it
+    for e, exp in enumerate(exploits):
+        exp.discovered = bool((int(sc[2]) >> (8 + e)) & 1)
+    pn = int(sc[3]) & 0xFFFF
+    env._prev_att_potential = None if pn == 0xFFFF else env.γ * (pn / M)
+    env.step_num, env.defender_step, env.attacker_step = int(sc[0]), int(sc[4]), int(sc[5])
+    env.compromised_devices_cnt, env.work_done = int(sc[7]), int(sc[8])
+    env.defensive_cost = float(sc[9:10].view(np.float32)[0])
+    env.clearning_cost = float(sc[10:11].view(np.float32)[0])
+    env.scan_cnt, env.revert_count, env.checkpoint_count = int(sc[11]), int(sc[12]), int(sc[13])
+    env.edges_blocked, env.edges_added = int(sc[14]), int(sc[15])
+    # the hop log: the kernels keep its length; records beyond what is known are neutral placeholders
+    logs = sim.logger.logs
+    n = int(sc[6])
+    if len(logs) > n:
+        del logs[n:]
+    while len(logs) < n:
+        logs.append({"time_step": 0, "from_device": 0, "to_device": 0, "kind": "D"})
+    env.state = env._get_state()
+    return env
+
+
+def write_reference_pickle(path, env, net=None, state=None):
+    """Write a reference-format snapshot (init_experiments.py:60-61: pickle.dump(env)) -- of `env` as it is, or, with
+    (net, state), after the kernels' canonical state has been written into it."""
+    import pickle
+    if state is not None:
+        apply_state_to_reference_env(env, net, state)
+    with open(path, "wb") as f:
+        pickle.dump(env, f)
+    return path

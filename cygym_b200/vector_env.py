@@ -245,6 +245,24 @@ class VectorCyberDefenseEnv:
         self._hold = (hdr, mask, out)
         return out
 
+    def rollout(self, hdr, mask, base_line, envs_per_row, row_base, returns=None, flags=0):
+        """n_steps plain steps of every env in ONE launch from per-ROW action tables (cyg_rollout): hdr [T, R, 4],
+        mask [T, R, W] int32, base_line [T, R] uint8 or None; env b reads row (row_base + b) // envs_per_row.
+        `returns` [2, B] float64 accumulates the raw rewards of defender / attacker turns.  The loop body of
+        DoubleOracle.simulate_game (do_agent.py:1875-2089) for the strategies that need no observation."""
+        T, R = int(hdr.shape[0]), int(hdr.shape[1])
+        assert hdr.shape == (T, R, 4) and mask.shape == (T, R, self.W) and hdr.is_contiguous() and mask.is_contiguous()
+        if returns is None:
+            returns = torch.zeros(2, self.B, dtype=torch.float64, device=self.device)
+        if base_line is not None:
+            base_line = base_line.to(self.device, torch.uint8).contiguous()
+            assert base_line.shape == (T, R)
+        a = K.CygRolloutArgs(hdr.data_ptr(), mask.data_ptr(), None if base_line is None else base_line.data_ptr(), T, R,
+                             int(row_base), int(envs_per_row), 0, returns.data_ptr())
+        K.check(self.L.cyg_rollout(self.h, C.byref(a), flags, self._s()))
+        self._hold = (hdr, mask, base_line, returns)
+        return returns
+
     # ---- host-buffer front end: what a CPU-side caller (the reference's rollout loops) uses ----
     def host_buffers(self):
         """Pinned host staging, allocated once: action headers [B, 4] and device masks [B, W] (int32) in, results
@@ -354,6 +372,13 @@ class VectorCyberDefenseEnv:
             env_mask = env_mask.to(self.device, torch.uint8).contiguous()
             self._hold_mask = env_mask
         K.check(self.L.cyg_randomize(self.h, _ptr(env_mask), self._s()))
+
+    def rebuild_graph_cache(self, env_mask=None):
+        """_rebuild_graph_cache() from outside a step (volt_typhoon_env.py:456-483): every blocked edge is forgotten (:476)."""
+        if env_mask is not None:
+            env_mask = env_mask.to(self.device, torch.uint8).contiguous()
+            self._hold_mask = env_mask
+        K.check(self.L.cyg_rebuild_graph_cache(self.h, _ptr(env_mask), self._s()))
 
     def sample_actions(self, mode, out: ActionBatch = None, want_order=False):
         """sample_action() of every env (CyberDefenseEnv.py:555-578) as an ActionBatch on the device.  The set form

@@ -249,8 +249,34 @@ int cyg_step(cyg_handle h, const cyg_actions* actions, uint32_t step_flags, cons
 int cyg_step_multi(cyg_handle h, const cyg_actions* actions, int32_t n_steps, uint32_t step_flags,
                    const cyg_step_out* out, void* stream);
 
+/* Whole rollouts of the payoff-matrix evaluation (DoubleOracle.simulate_game, do_agent.py:1875-2089, under
+ * build_payoff_matrices, :1666-1870) in ONE launch: n_steps consecutive plain steps of every env, the records staying
+ * in shared memory between them.  The strategies that need no observation (baseline names, fixed action sequences,
+ * the no-op; strategy.py:25-60) are TABLES shared by runs of envs: env b reads action row (row_base + b) / envs_per_row
+ * of the n_rows rows of a step -- with rows = (defender, attacker) strategy pairs and envs_per_row = rollouts per pair,
+ * the per-pair tables are uploaded once per evaluation and gathered inside the kernel.  base_line (optional) has the
+ * same row layout: what the two players' baselines set env.base_line to on their turns (do_agent.py:716-719).
+ * returns[2][B] (float64) receives += the raw reward of every step, row 0 on defender turns, row 1 on attacker turns
+ * (def_r / att_r of do_agent.py:2060-2062); the counters of the info dict are read from the scalars afterwards. */
+typedef struct cyg_rollout_args {
+  const uint32_t* hdr;      /* [n_steps][n_rows][4] */
+  const uint32_t* mask;     /* [n_steps][n_rows][W] */
+  const uint8_t* base_line; /* optional [n_steps][n_rows] CYG_BL_* */
+  int32_t n_steps, n_rows;
+  int64_t row_base;
+  int32_t envs_per_row;
+  int32_t reserved;
+  double* returns;          /* [2][B] */
+} cyg_rollout_args;
+int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, void* stream);
+
 /* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
+
+/* Replaces a _rebuild_graph_cache() call made from OUTSIDE a step (volt_typhoon_env.py:456-483; DoubleOracle.restore,
+ * do_agent.py:891-895; reset(from_init), volt:1933-1936): the rebuilt cache forgets every blocked edge (volt:476).
+ * env_mask may be NULL. */
+int cyg_rebuild_graph_cache(cyg_handle h, const uint8_t* env_mask, void* stream);
 
 /* Replaces sample_action() (CyberDefenseEnv.py:555-578) for every env; writes hdr[B][4], mask[B][W]. */
 int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream);

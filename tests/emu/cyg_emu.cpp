@@ -91,6 +91,19 @@ static void randomize_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* bl
 }
 
 template <int W>
+static void rebuild_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* blocked, uint32_t* extra, uint32_t* scal) {
+  const Net& n = em->net;
+  std::vector<uint32_t> rec(n.S);
+  for (int b = 0; b < B; b++) {
+    uint32_t* dv = dev + (size_t)b * n.M;
+    import_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL, nullptr);
+    Env<W> e(&n, rec.data(), nullptr, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
+    e.rebuild_cache();
+    export_env<W>(n, rec.data(), dv, blocked + (size_t)b * n.EW, extra + (size_t)b * n.cfg.xcap, scal + (size_t)b * CYG_NSCAL, nullptr);
+  }
+}
+
+template <int W>
 static void sample_w(Emu* em, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask, uint16_t* order, int order_stride) {
   const Net& n = em->net;
   std::vector<uint32_t> rec(n.S);
@@ -149,6 +162,11 @@ int emu_randomize(void* h, int B, int env_id0, uint32_t* dev, uint32_t* blocked,
                   const uint8_t* env_mask) {
   Emu* em = (Emu*)h;
   DISPATCH_W(randomize_w, em, B, env_id0, dev, blocked, extra, scal, env_mask);
+  return 0;
+}
+int emu_rebuild(void* h, int B, int env_id0, uint32_t* dev, uint32_t* blocked, uint32_t* extra, uint32_t* scal) {
+  Emu* em = (Emu*)h;
+  DISPATCH_W(rebuild_w, em, B, env_id0, dev, blocked, extra, scal);
   return 0;
 }
 int emu_sample_actions(void* h, int B, int env_id0, uint32_t* scal, int mode, uint32_t* hdr, uint32_t* mask, uint16_t* order, int order_stride) {

@@ -41,6 +41,7 @@ def lib():
         L.emu_record_words.argtypes = [C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint32] + [C.c_void_p] * 5
         L.emu_randomize.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.emu_rebuild.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.emu_sample_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_observe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
@@ -105,6 +106,9 @@ class Emu:
         if env_mask is not None:
             env_mask = np.ascontiguousarray(env_mask, np.uint8)
         self.L.emu_randomize(self.h, st.B, self.env_id0, _p(st.dev), _p(st.blocked), _p(st.extra), _p(st.scal), _p(env_mask))
+
+    def rebuild_graph_cache(self, st):
+        self.L.emu_rebuild(self.h, st.B, self.env_id0, _p(st.dev), _p(st.blocked), _p(st.extra), _p(st.scal))
 
     def sample_actions(self, st, mode, want_order=False):
         hdr = np.zeros((st.B, 4), np.uint32)

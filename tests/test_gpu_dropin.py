@@ -17,7 +17,7 @@ def _decode(hdr, mask, order, M, order_form):
         return None
     n_ex = (int(hdr[0]) >> 16) & 0xFF
     ex = [int(np.int8((int(hdr[1]) >> (8 * i)) & 0xFF)) for i in range(n_ex)]
-    n = int(hdr[2])
+    n = int(hdr[2]) & 0xFFFF
     devs = [int(x) for x in order[:n]] if order_form else [d for d in range(M) if (int(mask[d >> 5]) >> (d & 31)) & 1]
     return (at, ex, devs, int(np.int32(hdr[3])))
 
@@ -45,6 +45,7 @@ def test_gym_surface_replays_golden(name):
         acts = [_decode(g["hdr"][t][k], g["mask"][t][k], g["order"][t][k], M, meta["order_form"]) for k in range(G)]
         # the reference drew every non-None action with sample_action(): one draw epoch each
         env._venv.scalars[:, 1] += sum(1 for a in acts if a is not None)
+        env._host = None
         out = env.step(acts if kind == TR.OP_GROUPED else acts[0])
         assert len(out) == 6
         state, raw, shaped, done, info, logs = out
@@ -63,6 +64,11 @@ def test_gym_surface_replays_golden(name):
         assert env.step_num == int(sc[0]) and env.work_done == int(sc[8]) and env.scan_cnt == int(sc[11])
         assert env.compromised_devices_cnt == int(sc[7]) and env.edges_blocked == int(sc[14])
         assert info["Compromised_devices"] == int(sc[7]) and info["mode"] == env.mode
+        # info is built before step_num moves in step(), after it in step_grouped() (volt:1272-1285 / :746-755)
+        assert info["step_count"] == (int(sc[0]) if kind == TR.OP_GROUPED else int(sc[0]) - 1), f"op {t}"
+        assert len(logs) == int(sc[6])
+        nya = np.array([(int(g["dev"][t][d]) >> 2) & 1 for d in range(M)])
+        assert [int(d.Not_yet_added) for d in env._get_ordered_devices()] == nya.tolist()
 
 
 def test_gym_surface_errors_and_counters():
@@ -87,3 +93,31 @@ def test_gym_surface_errors_and_counters():
     assert env.step_num == 0 and env.defensive_cost == 0.0
     s1 = env.reset(from_init=True)
     assert np.array_equal(s0, s1)
+
+
+def test_gym_surface_pickle_rebuild_and_views():
+    """Pickled copies step like the original (workers: do_agent.py:642-705); _rebuild_graph_cache() from outside a step
+    forgets the blocked edges (volt:476); the simulator views read the live state."""
+    import pickle
+    from cygym_b200.volt_typhoon_env import Volt_Typhoon_CyberDefenseEnv
+    env = Volt_Typhoon_CyberDefenseEnv(seed=5)
+    env.step_num = 3          # set before the env exists: replayed into the scalars by initialize_environment()
+    env.numOfDevice, env.Max_network_size = 30, 40
+    env.initialize_environment()
+    assert env.step_num == 3
+    env.mode = "defender"
+    env.step((6, [0], list(range(0, 40, 2)), 0))  # block one edge per listed active device
+    assert env.edges_blocked > 0
+    blocked = int(np.unpackbits(env._snap()["blocked"].view(np.uint8)).sum())
+    assert blocked == env.edges_blocked
+    clone = pickle.loads(pickle.dumps(env))
+    for e in (env, clone):
+        e.mode = "attacker"
+    ra, rb = env.step((1, [0], [], 0)), clone.step((1, [0], [], 0))
+    assert ra[1] == rb[1] and np.array_equal(ra[0], rb[0]) and ra[4] == rb[4]
+    assert [d.isCompromised for d in env.simulator.subnet.net.values()] == [d.isCompromised for d in clone.simulator.subnet.net.values()]
+    env._rebuild_graph_cache()
+    assert int(np.unpackbits(env._snap()["blocked"].view(np.uint8)).sum()) == 0 and env.edges_blocked > 0
+    assert len(env.simulator.subnet.graph.get_edgelist()) == env.simulator.subnet.graph.ecount()
+    a = env.sample_action()
+    assert len(a[2]) == len(set(a[2])) and a[2] != sorted(a[2]) or len(a[2]) < 3  # draw order, not ascending
