@@ -30,6 +30,8 @@ E_INVAL, E_NOMEM, E_CUDA, E_STATE = -22, -12, -5, -71
 (S_STEP, S_EPOCH, S_FLAGS, S_PREV_X, S_DEF_STEP, S_ATT_STEP, S_LOGS, S_COMPCNT, S_WORK, S_DEFCOST,
  S_CLEANCOST, S_SCAN, S_REVERT, S_CKPT, S_EBLK, S_EADD) = range(16)
 FL_ERR_MASK = 0xF0
+FL_DET_TRAINED, FL_DET_PENDING = 0x4, 0x8
+DET_WORDS = 6160
 
 
 class CygConfig(C.Structure):
@@ -41,7 +43,7 @@ class CygConfig(C.Structure):
         ("scaling_vulnerability", C.c_int32), ("turbo", C.c_int32), ("zero_day", C.c_int32),
         ("zero_day_mask", C.c_uint32), ("att_space_n", C.c_int32), ("def_space_n", C.c_int32),
         ("default_high", C.c_int32), ("n_app_ids", C.c_int32), ("base_line", C.c_int32), ("tri_high", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("log_cap", C.c_int32),
         ("work_scale", C.c_float), ("comp_scale", C.c_float), ("def_scale", C.c_float), ("gamma", C.c_float),
         ("thr_p_add", C.c_uint64), ("thr_p_attacker", C.c_uint64),
         ("poisson_tab", C.c_uint32 * 16), ("tri_tab", C.c_uint32 * 8), ("seed", C.c_uint64),
@@ -59,7 +61,7 @@ class CygNetwork(C.Structure):
 class CygState(C.Structure):
     """struct cyg_state (device pointers, canonical layout)"""
     _fields_ = [("dev", C.c_void_p), ("ckpt", C.c_void_p), ("blocked", C.c_void_p), ("extra", C.c_void_p),
-                ("scal", C.c_void_p)]
+                ("scal", C.c_void_p), ("logs", C.c_void_p)]
 
 
 class CygActions(C.Structure):
@@ -81,7 +83,7 @@ class CygRolloutArgs(C.Structure):
 
 
 EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_set_base_line_per_env_steps", "cyg_internal_words",
-           "cyg_bind", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
+           "cyg_bind", "cyg_set_detectors", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
            "cyg_observe", "cyg_group_actions", "cyg_launch_count", "cyg_set_debug_cycles"]
 
 
@@ -177,6 +179,7 @@ def lib():
         L.cyg_set_base_line_per_env_steps.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.cyg_internal_words.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.cyg_bind.argtypes = [C.c_void_p, C.c_void_p]
+        L.cyg_set_detectors.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.cyg_import_state.argtypes = [C.c_void_p, C.POINTER(CygState), C.c_void_p]
         L.cyg_export_state.argtypes = [C.c_void_p, C.POINTER(CygState), C.c_void_p]
         L.cyg_step.argtypes = [C.c_void_p, C.POINTER(CygActions), C.c_uint32, C.POINTER(CygStepOut), C.c_void_p]
@@ -201,7 +204,7 @@ def check(rc):
         raise CygError(rc, lib().cyg_last_error().decode(errors="replace"))
 
 
-def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=5):
+def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=5, log_cap=0):
     """cfg: the attribute dict of a Network (network.py) -> struct cyg_config."""
     c = CygConfig()
     c.M, c.E, c.X, c.n_exploits, c.xcap = cfg["M"], E, cfg["X"], cfg["n_exploits"], xcap
@@ -214,6 +217,7 @@ def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=
     c.n_app_ids = cfg.get("n_app_ids", 0)
     c.base_line = BASE_LINES.get(base_line, 4)
     c.tri_high = tri_high
+    c.log_cap = int(log_cap)
     c.work_scale, c.comp_scale, c.def_scale, c.gamma = cfg["work_scale"], cfg["comp_scale"], cfg["def_scale"], cfg["gamma"]
     c.thr_p_add = DT.bernoulli_threshold(cfg["p_add"])
     c.thr_p_attacker = DT.bernoulli_threshold(cfg["p_attacker"])

@@ -380,6 +380,8 @@ struct Coop {
     if (nx <= 32 && lane < nx) xe = e.extra()[lane];
     __syncwarp();
     uint32_t logs_add = 0, zk = 0;
+    uint32_t log_base = e.scal(CYG_S_LOGS); /* hop-log index of the next record (uniform; only used with a log ring) */
+    const bool logging = e.logs != nullptr;
     for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
       int raw = a.ex(xi);
       uint32_t zx = 0;
@@ -416,6 +418,19 @@ struct Coop {
         const uint32_t conf = __ballot_sync(CYG_FULL, conflict);
         int c = conf ? (__ffs((int)conf) - 1) : 32;
         if (c > ns - pos) c = ns - pos;
+        if (logging) { /* uniform: the committed lanes write their hops, in source order, into the ring */
+          const uint32_t nrec = (valid && lane < c) ? (uint32_t)cnt + (v >= 0 ? 1u : 0u) : 0u;
+          uint32_t incl = nrec;
+#pragma unroll
+          for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t y = __shfl_up_sync(CYG_FULL, incl, dd);
+            if (lane >= dd) incl += y;
+          }
+          const uint32_t tot = __shfl_sync(CYG_FULL, incl, 31), cap = (uint32_t)e.n->cfg.log_cap;
+          const uint32_t end = log_base + tot;
+          if (nrec) e.log_source(s, v, has_blk, nx > 0 ? xrow : (const uint32_t*)nullptr, log_base + incl - nrec, end > cap ? end - cap : 0u);
+          log_base = end;
+        }
         if (valid && lane < c) {
           logs_add += (uint32_t)cnt + (v >= 0 ? 1u : 0u);
           if (v >= 0) {
@@ -722,6 +737,11 @@ struct BigCoop {
           }
         }
         if (hit < 0 && ve != 0x7FFFFFFF) hit = ve;
+        if (e.logs != nullptr && lane == 0) { /* one lane writes this source's hops (the ring is a diagnostic at this size) */
+          uint32_t xrow_l[W];
+          if (sx) e.extra_out_row(s, false, xrow_l);
+          e.log_source(s, hit, has_blk, sx ? xrow_l : (const uint32_t*)nullptr, e.scal(CYG_S_LOGS) + logs_add, 0u);
+        }
         if (sx) { /* unblocked extra edges of s in front of the hit (all of them when nothing is hit) */
           for (int base = 0; base < nx; base += 32) {
             const uint32_t xe = base + lane < nx ? xl[base + lane] : 0xFFFFFFFFu;

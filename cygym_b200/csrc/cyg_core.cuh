@@ -227,6 +227,13 @@ struct Stream {
 #ifdef __CUDACC__
 extern __shared__ __align__(128) uint32_t cyg_smem[];
 #endif
+/* defender action 5 with a TRAINED detector, as a stand-alone call that builds its own Env: the ~2 KB of local arrays
+ * (30 scored records, the CPython set emulation) and the tree walks stay out of the register allocation of the step
+ * kernels, and no Env of a hot path has its address taken.  Returns the _stall stream's draw index afterwards. */
+template <int W, int SM>
+CYG_HDN uint32_t scan_trained_call(const Net* n, uint32_t* rec, uint32_t ro, uint32_t to, uint32_t* logs, const uint32_t* det, uint32_t env_id,
+                                   uint32_t stall_k, int reps);
+
 template <int W, int SM = 0>
 struct Env {
   const Net* n;
@@ -236,6 +243,8 @@ struct Env {
   uint32_t ro, to; /* SM: word offsets of the record / the hot tables inside cyg_smem */
   uint32_t* ckpt;  /* canonical per-device checkpoint words of this env [M] (global memory) */
   uint32_t* xtra;  /* extra (attacker hub-star) edges of this env [xcap] (global memory) */
+  uint32_t* logs = nullptr;      /* hop-log ring of this env [cfg.log_cap] (global memory); nullptr: only the length is kept */
+  const uint32_t* det = nullptr; /* detector slot of this env (CYG_DET_WORDS, global memory); nullptr: none uploaded */
   Rng rng;
   Stream stall;    /* SITE_STALL is shared by every group of a grouped step */
   int bl;          /* base_line in effect for this env (CYG_BL_*): cfg.base_line unless the caller set one per env */
@@ -707,7 +716,8 @@ struct Env {
         }
       }
       cost += -1.0 * ds;
-      if (scal(CYG_S_LOGS) > 0) scal(CYG_S_FLAGS) |= CYG_FL_DET_TRAINED; /* sklearn fit: host territory */
+      if (scal(CYG_S_LOGS) > 0) /* detector.train(last <= 2000 logs): the fit is scikit-learn's, on the host (cygym_b200/detector.py) */
+        scal(CYG_S_FLAGS) |= CYG_FL_DET_TRAINED | (n->cfg.turbo ? 0u : CYG_FL_DET_PENDING);
     } else if (atype == 11) {
       int d = first_dev(a); /* the host raises ValueError when n_dev == 0 (volt:965-966) */
       if (d >= 0 && d < n->M) {
@@ -901,10 +911,11 @@ struct Env {
         upgrade_mask(act, a.app_index, up);
         stall_deposit(up, 0, c.default_high);
       } break;
-      case 5: /* volt:1020-1069 with an untrained detector: every prediction is "D" */
+      case 5: /* volt:1020-1069: an untrained detector predicts "D" for everything; a trained one is consulted */
         scal(CYG_S_SCAN) += (uint32_t)na;
         if (scal(CYG_S_LOGS) > 0) {
-          if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] */
+          if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) /* turbo: predictions = [] (volt:1055) */
+            stall.k = scan_trained_call<W, SM>(n, rec, ro, to, logs, det, rng.env, stall.k, na);
           cost += -0.5 * ds * na;
           defcost += 0.5 * ds * na;
         }
@@ -982,7 +993,8 @@ struct Env {
         case 5:
           scal(CYG_S_SCAN)++;
           if (scal(CYG_S_LOGS) > 0) {
-            if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] */
+            if ((scal(CYG_S_FLAGS) & CYG_FL_DET_TRAINED) && !n->cfg.turbo) /* turbo: predictions = [] (volt:1055) */
+              stall.k = scan_trained_call<W, SM>(n, rec, ro, to, logs, det, rng.env, stall.k, 1);
             cost += -0.5 * ds;
             defcost += 0.5 * ds;
           }
@@ -1104,6 +1116,156 @@ struct Env {
     rule3 = !is_dc && !devbit(n->o_reach, v);
     return v;
   }
+  /* The hop-log records of one source of the lateral-movement loop (log_communication, volt:1161 ->
+   * CDSimulator.py:667-673): every unblocked out-edge walked in front of the hit, then the hit -- base units in unit
+   * order, the unblocked extra edges (xrow, id space) at their place in ascending neighbour order.  Record k of the
+   * source gets log index idx0 + k and is written to the ring when that index is >= lo_keep (a warp that logs several
+   * sources at once only writes what a ring of log_cap records will still hold). */
+  CYG_HD void log_source(int s, int hit, bool has_blk, const uint32_t* xrow, uint32_t idx0, uint32_t lo_keep) {
+    const uint32_t cap = (uint32_t)n->cfg.log_cap;
+    uint32_t* ring = logs;
+    uint32_t xr[W];
+    for (int w = 0; w < W; w++) xr[w] = xrow ? xrow[w] : 0u;
+    uint32_t idx = idx0;
+    /* the extra edges with a neighbour id below v, ascending */
+    auto extras_below = [&](int v) {
+      for (int w = 0; w < W; w++) {
+        while (xr[w]) {
+          const int d = w * 32 + ctz(xr[w]);
+          if (d >= v) return;
+          xr[w] &= xr[w] - 1u;
+          if (idx >= lo_keep) ring[idx % cap] = (uint32_t)s | ((uint32_t)d << 16);
+          idx++;
+        }
+      }
+    };
+    const int a = ip(s), z = a + nout(s);
+    for (int q = a; q < z; q++) {
+      const int v = unit_other(unit(q));
+      if (hit >= 0 && v > hit) break;
+      if (hit >= 0 && v == hit) { /* the hit is this base pair: its first unit, nothing behind it */
+        extras_below(v);
+        if (idx >= lo_keep) ring[idx % cap] = (uint32_t)s | ((uint32_t)v << 16);
+        return;
+      }
+      if (has_blk && ubit(q)) continue;
+      extras_below(v);
+      if (idx >= lo_keep) ring[idx % cap] = (uint32_t)s | ((uint32_t)v << 16);
+      idx++;
+    }
+    if (hit >= 0) { /* the hit is an extra edge */
+      extras_below(hit);
+      if (idx >= lo_keep) ring[idx % cap] = (uint32_t)s | ((uint32_t)hit << 16);
+    } else {
+      extras_below(0x7FFFFFFF);
+    }
+  }
+
+  /* ---- trained detector: predict == two tree walks + the verdict bit of the leaf pair (include/cygym_b200.h CYG_DET_*;
+   *      CDSimulator.py:714-723).  sklearn: a float32 sample goes left when X[feature] <= threshold (float64). ---- */
+  CYG_HD int det_leaf(const uint32_t* tree, double from, double to) const {
+    int node = 0;
+    for (;;) {
+      const uint32_t* nd = tree + 4 * node;
+      const int feat = (int)(nd[3] & 0xFFFFu);
+      if (feat >= 2) return (int)(nd[3] >> 16);
+      const uint64_t bits = (uint64_t)nd[0] | ((uint64_t)nd[1] << 32);
+      double thr;
+#ifdef __CUDA_ARCH__
+      thr = __longlong_as_double((long long)bits);
+#else
+      __builtin_memcpy(&thr, &bits, 8);
+#endif
+      node = ((feat == 0 ? from : to) <= thr) ? (int)(nd[2] & 0xFFFFu) : (int)(nd[2] >> 16);
+    }
+  }
+  CYG_HD bool det_anomaly(int from, int to) const {
+    const int l0 = det_leaf(det + CYG_DET_TREE0, (double)from, (double)to);
+    const int l1 = det_leaf(det + CYG_DET_TREE0 + CYG_DET_TREE_STRIDE, (double)from, (double)to);
+    const uint32_t idx = (uint32_t)l0 * det[0] + (uint32_t)l1;
+    return (det[CYG_DET_TABLE + (idx >> 5)] >> (idx & 31)) & 1u;
+  }
+  /* Iteration order of the CPython set built by inserting the small non-negative ints vals[0..n) in that order: the
+   * reference walks `flagged_senders`, a set, handing out one _stall draw per member (volt:1062-1069).  Objects/
+   * setobject.c (3.12): hash(v) == v, open addressing with 9 linear probes, then i = i*5 + 1 + (perturb >>= 5);
+   * the table grows to the first power of two > 4 * used once fill * 5 >= mask * 3.  n <= 30 here. */
+  CYG_HD static int pyset_order(const int* vals, int cnt_in, int* out) {
+    int table[128], tmp[128];
+    int mask = 7, fill = 0;
+    for (int i = 0; i <= mask; i++) table[i] = -1;
+    for (int k = 0; k < cnt_in; k++) {
+      const int key = vals[k];
+      uint64_t perturb = (uint64_t)key;
+      uint32_t i = (uint32_t)key & (uint32_t)mask;
+      int placed = 0;
+      while (!placed) {
+        int probes = (i + 9u <= (uint32_t)mask) ? 9 : 0;
+        uint32_t j = i;
+        do {
+          if (table[j] < 0) { table[j] = key; fill++; placed = 1; break; }
+          if (table[j] == key) { placed = 2; break; }
+          j++;
+        } while (probes--);
+        if (placed) break;
+        perturb >>= 5;
+        i = (uint32_t)((i * 5ull + 1ull + perturb) & (uint64_t)mask);
+      }
+      if (placed == 1 && !((uint64_t)fill * 5ull < (uint64_t)mask * 3ull)) {
+        int newsize = 8;
+        while (newsize <= fill * 4) newsize <<= 1;
+        const int newmask = newsize - 1;
+        for (int q = 0; q <= newmask; q++) tmp[q] = -1;
+        for (int q = 0; q <= mask; q++) {
+          if (table[q] < 0) continue;
+          const int kk = table[q];
+          uint64_t pb = (uint64_t)kk;
+          uint32_t ii = (uint32_t)kk & (uint32_t)newmask;
+          for (;;) {
+            int probes = (ii + 9u <= (uint32_t)newmask) ? 9 : 0;
+            uint32_t jj = ii;
+            bool ok = false;
+            do { if (tmp[jj] < 0) { tmp[jj] = kk; ok = true; break; } jj++; } while (probes--);
+            if (ok) break;
+            pb >>= 5;
+            ii = (uint32_t)((ii * 5ull + 1ull + pb) & (uint64_t)newmask);
+          }
+        }
+        mask = newmask;
+        for (int q = 0; q <= mask; q++) table[q] = tmp[q];
+      }
+    }
+    int c = 0;
+    for (int q = 0; q <= mask; q++) if (table[q] >= 0) out[c++] = table[q];
+    return c;
+  }
+  /* `reps` iterations of the scan body volt:1052-1069 (one per listed active device; the log does not change in
+   * between, so the predictions are the same in each): the last 30 records are scored; with a majority of anomalies
+   * every flagged sender is un-compromised and stalled -- one _stall draw each per iteration, in set order, of which
+   * the last iteration's survive. */
+  CYG_HD void scan_trained_body(int reps) {
+    const cyg_config& c = n->cfg;
+    const uint32_t nlogs = scal(CYG_S_LOGS);
+    if (!det || !logs || (scal(CYG_S_FLAGS) & CYG_FL_DET_PENDING) || (c.log_cap < 30 && (uint32_t)c.log_cap < nlogs)) {
+      scal(CYG_S_FLAGS) |= CYG_FL_ERR_DETECTOR;
+      return;
+    }
+    const int nw = nlogs < 30u ? (int)nlogs : 30;
+    int senders[30], order[30], ns = 0, n_anom = 0;
+    for (int k = 0; k < nw; k++) {
+      const uint32_t r = logs[(nlogs - (uint32_t)nw + (uint32_t)k) % (uint32_t)c.log_cap];
+      const int from = (int)(r & 0xFFFFu), to = (int)(r >> 16);
+      if (det_anomaly(from, to)) { n_anom++; senders[ns++] = from; }
+    }
+    if (n_anom < nw / 2 + 1) return;
+    const int cnt = pyset_order(senders, ns, order);
+    stall.skip(rng, (uint32_t)(reps - 1) * (uint32_t)cnt);
+    for (int k = 0; k < cnt; k++) {
+      const int d = order[k];
+      clrb(P_COMP, d);
+      set_busy(d, stall_draw(0, c.default_high));
+    }
+  }
+
   /* the exploit slot an attack uses: zero-day remap (volt:1131-1146); -1 = no such exploit */
   CYG_HD int resolve_exploit(int raw, uint32_t zday_draw) {
     const cyg_config& c = n->cfg;
@@ -1145,6 +1307,7 @@ struct Env {
           uint32_t xrow[W];
           if (nx > 0) extra_out_row(s, false, xrow);
           const int v = attack_source(s, comp, kv, has_blk, nx > 0 ? xrow : (const uint32_t*)0, cnt, rule3);
+          if (this->logs) log_source(s, v, has_blk, nx > 0 ? xrow : (const uint32_t*)0, logs, 0u);
           logs += (uint32_t)cnt + (v >= 0 ? 1u : 0u);
           if (v >= 0) {
             const bool is_dc = devbit(n->o_dc, s);
@@ -1644,6 +1807,18 @@ struct Env {
     for (int w = 0; w < W; w++) if (w < n->Wm) mask[w] = pick[w];
   }
 };
+
+template <int W, int SM>
+CYG_HDN uint32_t scan_trained_call(const Net* n, uint32_t* rec, uint32_t ro, uint32_t to, uint32_t* logs, const uint32_t* det, uint32_t env_id,
+                                   uint32_t stall_k, int reps) {
+  Env<W, SM> e(n, rec, nullptr, nullptr, env_id, ro, to);
+  e.logs = logs;
+  e.det = det;
+  e.resume_epoch();
+  e.stall.k = stall_k;
+  e.scan_trained_body(reps);
+  return e.stall.k;
+}
 
 /* ---- canonical device word <-> bit-planes (include/cygym_b200.h) ------------ */
 template <int W>

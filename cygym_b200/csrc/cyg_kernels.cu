@@ -82,6 +82,9 @@ struct StepParams {
   uint32_t* pre_masks;
   float* obs;
   unsigned long long* dbg_cycles; /* optional [B]: SM cycles each env's step took (diagnostics) */
+  uint32_t* logs;                 /* [B][log_cap] hop-log rings (NULL when log_cap == 0) */
+  const uint32_t* det_slots;      /* uploaded detectors (cyg_set_detectors) */
+  const int32_t* det_of_env;      /* [B] slot of env, -1 none */
   const uint8_t* bl_env;          /* optional [B]: base_line per env (CYG_BL_*); NULL = cfg.base_line for all */
   int bl_stride;                  /* fused steps: bl_env row of step t starts at t * bl_stride (0: one row for all) */
   int B, env_id0, G, order_stride, obs_mode, block_envs;
@@ -304,6 +307,12 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
   Env<W, 1> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
                  (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
+  /* the hop-log ring and the uploaded detector of an env (both optional, global memory) */
+  auto bind_aux = [&](Env<W, 1>& ee, int env_i) {
+    ee.logs = p.logs ? p.logs + (size_t)env_i * p.net.cfg.log_cap : nullptr;
+    ee.det = (p.det_slots && p.det_of_env[env_i] >= 0) ? p.det_slots + (size_t)p.det_of_env[env_i] * CYG_DET_WORDS : nullptr;
+  };
+  if (tid < nb) bind_aux(e, env);
   long long t_begin = 0;
 #ifdef CYG_PHASE_TIMING
   long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -391,6 +400,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             Env<W, 1> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                             (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
             eb.resume_epoch();
+            if (kind == 1) eb.logs = p.logs ? p.logs + (size_t)env_b * p.net.cfg.log_cap : nullptr; /* the attack logs its hops */
             uint32_t act[4 + W];
             load_action(env_b, act);
             typename Env<W, 1>::Act a;
@@ -429,6 +439,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
           e = Env<W, 1>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
                            (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4)); /* nothing of it stays live across phase B */
           if (bl_t) e.bl = (int)bl_t[arow(env)];
+          bind_aux(e, env);
           e.resume_epoch();
           cost = (double)s_out[el];
           dirty = __float_as_int(s_out[NB + el]) != 0;
@@ -523,6 +534,8 @@ __global__ void __launch_bounds__(256) cyg_step_generic_kernel(const __grid_cons
   if (tid < nb) {
     Env<W, 2> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env), (uint32_t)(tid * S), tab_off);
     if (p.bl_env) e.bl = (int)p.bl_env[env];
+    e.logs = p.logs ? p.logs + (size_t)env * p.net.cfg.log_cap : nullptr;
+    e.det = (p.det_slots && p.det_of_env[env] >= 0) ? p.det_slots + (size_t)p.det_of_env[env] * CYG_DET_WORDS : nullptr;
     const uint32_t* hdr = p.hdr + (size_t)env * 4;
     const uint16_t* ord = p.order ? p.order + (size_t)env * p.order_stride : nullptr;
     mode = (int)((hdr[0] >> 8) & 1u);
@@ -544,6 +557,7 @@ __global__ void __launch_bounds__(256) cyg_step_generic_kernel(const __grid_cons
     const int env_b = env0 + el;
     Env<W, 2> e(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env_b), (uint32_t)(el * S), tab_off);
     if (p.bl_env) e.bl = (int)p.bl_env[env_b];
+    e.logs = p.logs ? p.logs + (size_t)env_b * p.net.cfg.log_cap : nullptr;
     e.resume_epoch();
     typename Env<W, 2>::Act a;
     Env<W, 2>::decode(p.hdr + (size_t)env_b * 4, p.mask + (size_t)env_b * Wm, nullptr, a);
@@ -633,6 +647,8 @@ struct ConvParams {
   uint32_t* xtra_int;
   uint32_t *dev, *ckpt, *blocked, *extra, *scal;
   int B;
+  uint32_t* logs_int; /* [B][log_cap] internal ring */
+  uint32_t* logs;     /* optional canonical [B][log_cap] */
 };
 
 template <int W>
@@ -695,6 +711,8 @@ __global__ void cyg_import_kernel(const __grid_constant__ ConvParams p) {
   for (int i = lane; i < n.cfg.xcap; i += 32) p.xtra_int[(size_t)warp * n.cfg.xcap + i] = p.extra[(size_t)warp * n.cfg.xcap + i];
   __syncwarp();
   if (lane == 0) rec[n.off_aux] = nblk;
+  if (p.logs_int) /* the hop-log ring (zeroed when the caller has none to import) */
+    for (int i = lane; i < n.cfg.log_cap; i += 32) p.logs_int[(size_t)warp * n.cfg.log_cap + i] = p.logs ? p.logs[(size_t)warp * n.cfg.log_cap + i] : 0u;
 }
 
 template <int W>
@@ -718,6 +736,8 @@ __global__ void cyg_export_kernel(const __grid_constant__ ConvParams p) {
     p.blocked[(size_t)warp * n.EW + i] = x;
   }
   for (int i = lane; i < n.cfg.xcap; i += 32) p.extra[(size_t)warp * n.cfg.xcap + i] = p.xtra_int[(size_t)warp * n.cfg.xcap + i];
+  if (p.logs && p.logs_int)
+    for (int i = lane; i < n.cfg.log_cap; i += 32) p.logs[(size_t)warp * n.cfg.log_cap + i] = p.logs_int[(size_t)warp * n.cfg.log_cap + i];
 }
 
 /* ---- IPPO / MAPPO glue: per-device action types -> the per-type action groups of one grouped step (IPPO.py:559-570),
@@ -885,6 +905,8 @@ struct cyg_env_s {
   uint32_t* state;   /* bound internal buffer: [B][S] records then [B][M] checkpoint words */
   int B, env_id0, device, W, NB, n_sms;
   unsigned long long* dbg_cycles;
+  const uint32_t* det_slots; /* uploaded detectors (device memory of the caller) */
+  const int32_t* det_of_env;
   const uint8_t* bl_env;
   int bl_rows;       /* rows of [B] codes behind bl_env (cyg_set_base_line_per_env_steps; 1 otherwise) */
   size_t smem_bytes;
@@ -969,6 +991,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   std::string err = build_tables(*cfg, *host_net, h->blob);
   if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
   h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr; h->bl_rows = 1;
+  h->det_slots = nullptr; h->det_of_env = nullptr;
   h->W = h->blob.net.W;
   DeviceGuard g(device);
   if (!g.ok) { delete h; return fail(CYG_E_CUDA, "cudaSetDevice failed"); }
@@ -1019,9 +1042,17 @@ int cyg_set_base_line_per_env_steps(cyg_handle h, const uint8_t* base_line, int3
   return CYG_OK;
 }
 
+int cyg_set_detectors(cyg_handle h, const uint32_t* slots, int32_t n_slots, const int32_t* det_of_env) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  if ((slots == nullptr) != (det_of_env == nullptr) || (slots && n_slots < 1)) return fail(CYG_E_INVAL, "slots and det_of_env go together");
+  h->det_slots = slots;
+  h->det_of_env = det_of_env;
+  return CYG_OK;
+}
+
 int cyg_internal_words(cyg_handle h, int64_t* words_per_env) {
   if (!h || !words_per_env) return fail(CYG_E_INVAL, "null argument");
-  *words_per_env = (int64_t)h->net.S + h->net.M + h->net.cfg.xcap;
+  *words_per_env = (int64_t)h->net.S + h->net.M + h->net.cfg.xcap + h->net.cfg.log_cap;
   return CYG_OK;
 }
 
@@ -1034,12 +1065,13 @@ int cyg_bind(cyg_handle h, uint32_t* internal_state) {
 
 static uint32_t* ckpt_of(cyg_handle h) { return h->state + (size_t)h->B * h->net.S; }
 static uint32_t* xtra_of(cyg_handle h) { return ckpt_of(h) + (size_t)h->B * h->net.M; }
+static uint32_t* logs_of(cyg_handle h) { return h->net.cfg.log_cap > 0 ? xtra_of(h) + (size_t)h->B * h->net.cfg.xcap : nullptr; }
 
 int cyg_import_state(cyg_handle h, const cyg_state* c, void* stream) {
   if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B, logs_of(h), c->logs};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
   wops(h->W)->import_state(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
@@ -1051,7 +1083,7 @@ int cyg_export_state(cyg_handle h, const cyg_state* c, void* stream) {
   if (!h || !c || !c->dev || !c->blocked || !c->extra || !c->scal) return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B};
+  ConvParams p = {h->net, h->state, ckpt_of(h), xtra_of(h), c->dev, c->ckpt, c->blocked, c->extra, c->scal, h->B, logs_of(h), c->logs};
   int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
   wops(h->W)->export_state(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
@@ -1098,6 +1130,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   p.flags = step_flags;
   p.T = n_steps;
   p.row_base = 0; p.envs_per_row = 0; p.n_rows = h->B; p.ret_acc = nullptr;
+  p.logs = logs_of(h); p.det_slots = h->det_slots; p.det_of_env = h->det_of_env;
   p.block_envs = h->NB;
   const bool plain = !(step_flags & CYG_STEP_GROUPED) && a->order == nullptr; /* the hot form: see cyg_step_kernel */
   int blocks = (h->B + h->NB - 1) / h->NB;
@@ -1136,6 +1169,7 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
   p.bl_env = a->base_line; p.bl_stride = a->base_line ? a->n_rows : 0;
   p.B = h->B; p.env_id0 = h->env_id0; p.G = 1; p.order_stride = 0; p.obs_mode = 0; p.flags = step_flags; p.T = a->n_steps;
   p.row_base = a->row_base; p.envs_per_row = a->envs_per_row; p.n_rows = a->n_rows; p.ret_acc = a->returns;
+  p.logs = logs_of(h); p.det_slots = h->det_slots; p.det_of_env = h->det_of_env;
   p.block_envs = h->NB;
   int blocks = (h->B + h->NB - 1) / h->NB;
   int threads = ((2 * h->NB + 31) / 32) * 32;

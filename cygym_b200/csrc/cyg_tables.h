@@ -43,6 +43,7 @@ inline std::string build_tables(const cyg_config& cfg, const cyg_network& hn, Ta
   if (cfg.n_exploits < 0 || cfg.n_exploits > X) return "n_exploits must be in 0..X";
   if (cfg.xcap < 0 || cfg.xcap > 4095) return "xcap out of range";
   if (cfg.evolve_period < 1) return "evolve_period must be >= 1";
+  if (cfg.log_cap < 0 || cfg.log_cap > 65536) return "log_cap must be in 0..65536";
   if (cfg.wl_period_max < 1) return "wl_period_max must be >= 1";
   const int W = M <= 32 * CYG_MAX_W ? (M + 31) / 32 : CYG_BIG_W; /* large networks: planes padded to 64 words */
   const int EW = E > 0 ? (E + 31) / 32 : 1;

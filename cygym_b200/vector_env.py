@@ -65,7 +65,10 @@ def _ptr(t):
 
 class VectorCyberDefenseEnv:
     def __init__(self, network: Network, num_envs, device="cuda:0", seed=0, env_id0=0, base_line="Nash", xcap=16,
-                 stream=None):
+                 stream=None, log_cap=0, detector_slots=0):
+        """log_cap: records of every env's hop log kept in a ring (simulator.logger.logs, CDSimulator.py:663-679): 0 = only
+        its length; >= 30 serves scans with a trained detector, 2000 what detector training reads.  detector_slots: how
+        many envs can hold a trained detector (IsolationForest fitted on the host by service_detectors())."""
         if not torch.cuda.is_available():
             raise RuntimeError("VectorCyberDefenseEnv needs a CUDA device (no CPU fallback)")
         self.L = K.lib()
@@ -77,14 +80,15 @@ class VectorCyberDefenseEnv:
         self.xcap = max(int(xcap), len(network.template.get("extra", ())))
         self.env_id0 = int(env_id0)
         self.base_line = base_line
-        self.cfg = K.make_config(network.cfg, network.E, seed=seed, xcap=self.xcap, base_line=base_line)
+        self.log_cap = int(log_cap)
+        self.cfg = K.make_config(network.cfg, network.E, seed=seed, xcap=self.xcap, base_line=base_line, log_cap=self.log_cap)
         hn = K.CygNetwork(network.row_ptr.ctypes.data, network.col.ctypes.data, network.mult.ctypes.data,
                           network.dev_static.ctypes.data, network.os_val.ctypes.data, network.ver_val.ctypes.data)
         self.h = C.c_void_p()
         K.check(self.L.cyg_create(C.byref(self.h), C.byref(self.cfg), C.byref(hn), self.B, self.env_id0, self.dev_index))
         words = C.c_int64()
         K.check(self.L.cyg_internal_words(self.h, C.byref(words)))
-        self.S = int(words.value) - self.M - self.xcap
+        self.S = int(words.value) - self.M - self.xcap - self.log_cap
         i32 = dict(dtype=torch.int32, device=self.device)
         self._state = torch.zeros(self.B * int(words.value), **i32)
         K.check(self.L.cyg_bind(self.h, _ptr(self._state)))
@@ -101,6 +105,12 @@ class VectorCyberDefenseEnv:
         self._stream = stream
         self._obs = {}
         self._pre = None
+        self._det_slots = self._det_of_env = None
+        self._n_det = 0
+        if detector_slots:
+            self._det_slots = torch.zeros(int(detector_slots), K.DET_WORDS, dtype=torch.int32, device=self.device)
+            self._det_of_env = torch.full((self.B,), -1, dtype=torch.int32, device=self.device)
+            K.check(self.L.cyg_set_detectors(self.h, _ptr(self._det_slots), int(detector_slots), _ptr(self._det_of_env)))
         self.reset()
 
     # ---- plumbing ----
@@ -150,12 +160,16 @@ class VectorCyberDefenseEnv:
 
     def _canon_alloc(self):
         u = dict(dtype=torch.int32, device=self.device)
-        return dict(dev=torch.zeros(self.B, self.M, **u), ckpt=torch.zeros(self.B, self.M, **u),
-                    blocked=torch.zeros(self.B, self.EW, **u), extra=torch.zeros(self.B, max(1, self.xcap), **u),
-                    scal=torch.zeros(self.B, K.NSCAL, **u))
+        d = dict(dev=torch.zeros(self.B, self.M, **u), ckpt=torch.zeros(self.B, self.M, **u),
+                 blocked=torch.zeros(self.B, self.EW, **u), extra=torch.zeros(self.B, max(1, self.xcap), **u),
+                 scal=torch.zeros(self.B, K.NSCAL, **u))
+        if self.log_cap:
+            d["logs"] = torch.zeros(self.B, self.log_cap, **u)
+        return d
 
     def _cstate(self, c):
-        return K.CygState(*[c[k].data_ptr() for k in ("dev", "ckpt", "blocked", "extra", "scal")])
+        return K.CygState(*[c[k].data_ptr() for k in ("dev", "ckpt", "blocked", "extra", "scal")],
+                          c["logs"].data_ptr() if c.get("logs") is not None else None)
 
     # ---- state in / out (reset(from_init=True) / snapshot load, volt:1904-1925) ----
     def import_state(self, canon):
@@ -169,6 +183,14 @@ class VectorCyberDefenseEnv:
             if a.shape[1] < width:
                 a = torch.nn.functional.pad(a, (0, width - a.shape[1]))
             c[k] = a.contiguous()
+        if self.log_cap and canon.get("logs") is not None:  # the hop-log ring travels with the state when the caller has one
+            a = canon["logs"]
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a).view(np.int32).reshape(self.B, -1))
+            a = a.to(self.device, torch.int32)
+            if a.shape[1] < self.log_cap:
+                a = torch.nn.functional.pad(a, (0, self.log_cap - a.shape[1]))
+            c["logs"] = a[:, : self.log_cap].contiguous()
         cs = self._cstate(c)
         K.check(self.L.cyg_import_state(self.h, C.byref(cs), self._s()))
         self._keep = c
@@ -372,6 +394,43 @@ class VectorCyberDefenseEnv:
             env_mask = env_mask.to(self.device, torch.uint8).contiguous()
             self._hold_mask = env_mask
         K.check(self.L.cyg_randomize(self.h, _ptr(env_mask), self._s()))
+
+    # ---- trained detectors (defender actions 10 / 5; the fit is scikit-learn's, on the host) ----
+    def log_records(self, b, last=2000):
+        """The last `last` hop-log records of env b in log order: int array [n, 2] of (from_device, to_device)."""
+        n = int(self.scalars[b, K.S_LOGS].item())
+        k = min(n, last)
+        if k > self.log_cap:
+            raise ValueError(f"the hop-log ring keeps {self.log_cap} records per env, {k} are needed (log_cap=)")
+        base = self.B * (self.S + self.M + self.xcap)
+        ring = self._state[base + b * self.log_cap: base + (b + 1) * self.log_cap].cpu().numpy().view(np.uint32)
+        r = ring[(np.arange(n - k, n) % max(1, self.log_cap)).astype(np.int64)]
+        return np.stack([r & 0xFFFF, r >> 16], axis=1).astype(np.int64)
+
+    def pending_detectors(self):
+        """Envs whose defender trained the detector (action 10 on a non-empty log) since the last service."""
+        return torch.nonzero(self.scalars[:, K.S_FLAGS] & K.FL_DET_PENDING).flatten().tolist()
+
+    def service_detectors(self, seed_of_env=None):
+        """Fit (scikit-learn IsolationForest on the env's last <= 2000 hop-log records: Detector.train,
+        CDSimulator.py:687-695) and upload the detector of every pending env; the next scan of that env consults it.
+        Call after a step that may have trained (the Gym drop-in does it itself).  seed_of_env(b) -> seed for numpy's
+        global stream before env b's fit (the reference's forest has random_state=None), or None."""
+        from . import detector as DET
+        pend = self.pending_detectors()
+        for b in pend:
+            if self._det_slots is None:
+                raise RuntimeError("no detector slots: construct the env with detector_slots=")
+            slot = int(self._det_of_env[b].item())
+            if slot < 0:
+                if self._n_det >= self._det_slots.shape[0]:
+                    raise RuntimeError(f"all {self._det_slots.shape[0]} detector slots are taken (detector_slots=)")
+                slot, self._n_det = self._n_det, self._n_det + 1
+                self._det_of_env[b] = slot
+            model = DET.fit_detector(self.log_records(b), None if seed_of_env is None else seed_of_env(b))
+            self._det_slots[slot] = torch.from_numpy(DET.pack_detector(model).view(np.int32)).to(self.device)
+            self.scalars[b, K.S_FLAGS] &= ~K.FL_DET_PENDING
+        return len(pend)
 
     def rebuild_graph_cache(self, env_mask=None):
         """_rebuild_graph_cache() from outside a step (volt_typhoon_env.py:456-483): every blocked edge is forgotten (:476)."""

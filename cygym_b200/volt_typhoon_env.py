@@ -127,9 +127,10 @@ class _ExploitView:
 
 
 class _LoggerView:
-    """`simulator.logger`: the hop log.  The kernels keep its LENGTH (CYG_S_LOGS); get_logs() returns a list of that
-    length whose records are placeholders -- callers on the step path only take len() and slices of it
-    (do_agent.py:51-62: the DoubleOracle checkpoint keeps the last 2000)."""
+    """`simulator.logger`: the hop log (CDSimulator.py:663-679).  The kernels keep its length (CYG_S_LOGS) and a ring of
+    the last `log_cap` records; get_logs() returns a list of the full length whose last log_cap entries are the records
+    ({"time_step", "from_device", "to_device", "kind"}; time_step is not tracked: the step path never reads it) and
+    whose older entries are None -- callers take len() and tail slices (do_agent.py:51-62 keeps the last 2000)."""
 
     def __init__(self, env):
         self._env = env
@@ -138,7 +139,15 @@ class _LoggerView:
         return int(self._env._snap()["scal"][K.S_LOGS])
 
     def get_logs(self):
-        return [None] * self._n()
+        n = self._n()
+        ring = self._env._snap().get("logs")
+        if ring is None or len(ring) == 0:
+            return [None] * n
+        cap = len(ring)
+        k = min(n, cap)
+        tail = [{"time_step": None, "from_device": int(r & 0xFFFF), "to_device": int(r >> 16), "kind": "A"}
+                for r in ring[(np.arange(n - k, n) % cap).astype(np.int64)]]
+        return [None] * (n - k) + tail
 
     logs = property(lambda s: s.get_logs())
 
@@ -169,7 +178,7 @@ class Volt_Typhoon_CyberDefenseEnv:
 
     MaxExploits = 6
 
-    def __init__(self, network: Network = None, device="cuda:0", seed=0, env_id=0, xcap=32, venv_cls=None):
+    def __init__(self, network: Network = None, device="cuda:0", seed=0, env_id=0, xcap=32, venv_cls=None, log_cap=2048):
         """venv_cls: the batched backend (default and only product backend: VectorCyberDefenseEnv on CUDA; the CPU test
         suite injects a stand-in built on the host compile of the device source, tests/emu/emu_venv.py)."""
         d = self.__dict__
@@ -190,7 +199,8 @@ class Volt_Typhoon_CyberDefenseEnv:
         self.private_exploit_id, self.private_exploit_ids, self.common_exploit_ids, self.unknown_pool_ids = None, [], [], []
         self.prior_pi = None
         self.alpha, self.khop, self.preknown = 0.5, 1, 0
-        self._device, self._seed, self._env_id, self._xcap = device, seed, env_id, xcap
+        self._device, self._seed, self._env_id, self._xcap, self._log_cap = device, seed, env_id, xcap, int(log_cap)
+        self.detector_fit_seed = None    # parity runs: seed of numpy's global stream before every detector fit
         self._net = network
         self._base_line = "Nash"
         self._scales = {}
@@ -222,7 +232,7 @@ class Volt_Typhoon_CyberDefenseEnv:
             self._net.cfg[k] = float(v)
             self._venv.close()
             self.__dict__["_venv"] = self._venv_cls(self._net, 1, device=self._device, seed=self._seed, env_id0=self._env_id,
-                                                    base_line=self._base_line, xcap=self._xcap)
+                                                    base_line=self._base_line, xcap=self._xcap, log_cap=self._log_cap, detector_slots=1)
             self._venv.import_state(st)
 
     work_scale = property(lambda s: s._cfg_get("work_scale"), lambda s, v: s._cfg_set("work_scale", v))
@@ -238,7 +248,7 @@ class Volt_Typhoon_CyberDefenseEnv:
         if self._venv is not None:
             self._venv.close()
         self.__dict__["_venv"] = self._venv_cls(self._net, 1, device=self._device, seed=self._seed, env_id0=self._env_id,
-                                                base_line=self._base_line, xcap=self._xcap)
+                                                base_line=self._base_line, xcap=self._xcap, log_cap=self._log_cap, detector_slots=1)
         self._sim = SimulatorView(self)
         self._host = None
         for name, value in list(self._pending.items()):  # counters a caller set before initialize_environment()
@@ -408,6 +418,10 @@ class Volt_Typhoon_CyberDefenseEnv:
         # one device->host copy: rewards, done and the pre-evolve masks; the counters come from the cached state copy
         out = torch.cat([v._out.view(torch.int32).reshape(-1), v.pre_masks().reshape(-1)]).cpu().numpy()
         self._host = None
+        if int(self._snap()["scal"][K.S_FLAGS]) & K.FL_DET_PENDING:  # defender action 10 trained the detector (volt:945-962)
+            seed = self.detector_fit_seed
+            self._venv.service_detectors(None if seed is None else (lambda b: seed))
+            self._host = None
         M, W = self._net.M, self._net.W
         pre = out[3:].view(np.uint32).reshape(3, W)
         bits = lambda row: ((pre[row, np.arange(M) >> 5] >> (np.arange(M) & 31)) & 1).astype(np.float64)

@@ -89,10 +89,15 @@ enum {
 };
 #define CYG_FL_HAS_CKPT 0x00000001u     /* env.checkpoint is not None */
 #define CYG_FL_SETS_INIT 0x00000002u    /* env._active_ids exists */
-#define CYG_FL_DET_TRAINED 0x00000004u  /* action 10 ran with a non-empty log: sklearn territory */
+#define CYG_FL_DET_TRAINED 0x00000004u  /* action 10 ran with a non-empty log: simulator.detector.trained (CDSimulator.py:693-694) */
+#define CYG_FL_DET_PENDING 0x00000008u  /* ... and the host has not yet fitted / uploaded that model (cyg_set_detectors): the
+                                           IsolationForest FIT is scikit-learn's, done on the host from the env's hop log;
+                                           the kernels only PREDICT (tree walks).  A scan that finds it set raises
+                                           CYG_FL_ERR_DETECTOR.  Never part of a reference-side state: cleared by the host. */
 #define CYG_FL_ERR_BUSY 0x00000010u     /* busy_time exceeded CYG_BUSY_MAX (kernel saturated it) */
 #define CYG_FL_ERR_XCAP 0x00000020u     /* more attacker-star edges than xcap */
-#define CYG_FL_ERR_DETECTOR 0x00000040u /* scan requested after the detector was trained */
+#define CYG_FL_ERR_DETECTOR 0x00000040u /* a scan needed the trained detector and the env had none uploaded (no slot, model
+                                           pending, or a hop-log ring shorter than the 30-record scan window) */
 #define CYG_FL_ERR_MASK 0x000000F0u
 #define CYG_FL_DISC_SHIFT 8             /* bit e: exploits[e].discovered */
 
@@ -149,7 +154,9 @@ typedef struct cyg_config {
   int32_t n_app_ids;         /* get_num_app_indices() */
   int32_t base_line;         /* CYG_BL_* */
   int32_t tri_high;          /* `high` of np.random.triangular(0, mode, high) (CDSimulator.py:308) */
-  int32_t reserved0;
+  int32_t log_cap;           /* hop-log ring per env: the last log_cap records of simulator.logger.logs (CDSimulator.py:663-679);
+                                0 = only the length is kept (CYG_S_LOGS).  30 serves the scan window (volt:1052), 2000 what
+                                detector training reads (volt:955-961) */
   float work_scale, comp_scale, def_scale, gamma;
   uint64_t thr_p_add;        /* random() < p_add      <=> x < thr (CyberDefenseEnv.py:679) */
   uint64_t thr_p_attacker;   /* random() < p_attacker <=> x < thr (CyberDefenseEnv.py:690) */
@@ -182,6 +189,8 @@ typedef struct cyg_state {
   uint32_t* blocked;  /* [B][ceil(E/32)] bit e: base pair e is in env._blocked (volt:73) */
   uint32_t* extra;    /* [B][xcap] */
   uint32_t* scal;     /* [B][16] */
+  uint32_t* logs;     /* optional [B][log_cap]: hop-log ring, record k of the env's log (k = 0 .. CYG_S_LOGS - 1) sits at
+                         k % log_cap as from_device | to_device << 16; NULL = not transferred */
 } cyg_state;
 
 typedef struct cyg_actions {
@@ -225,7 +234,8 @@ int cyg_set_base_line_per_env_steps(cyg_handle h, const uint8_t* base_line, int3
 /* uint32 words PER ENV the caller must allocate for the kernels' internal state.  The buffer holds, in this
  * order: B records of S words (16 scalars + bit-planes + the blocked-edge bitset in out- and in-list order;
  * what a CTA bulk-copies into shared memory), then B*M per-device checkpoint words (actions 11/12,
- * volt_typhoon_env.py:419-453), then B*xcap extra-edge words.  words_per_env = S + M + xcap. */
+ * volt_typhoon_env.py:419-453), then B*xcap extra-edge words, then B*log_cap hop-log ring words.
+ * words_per_env = S + M + xcap + log_cap. */
 int cyg_internal_words(cyg_handle h, int64_t* words_per_env);
 
 /* Bind the internal state buffer (device pointer, B * words_per_env uint32, 16-byte aligned). */
@@ -277,6 +287,21 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
  * do_agent.py:891-895; reset(from_init), volt:1933-1936): the rebuilt cache forgets every blocked edge (volt:476).
  * env_mask may be NULL. */
 int cyg_rebuild_graph_cache(cyg_handle h, const uint8_t* env_mask, void* stream);
+
+/* ---- trained detector (defender action 5 after action 10; volt_typhoon_env.py:1020-1069, CDSimulator.py:681-723) -----
+ * Detector = IsolationForest(n_estimators=2, max_samples=256).  The host fits it (scikit-learn, from the env's hop log)
+ * and uploads the two trees plus the forest's verdict for every pair of leaves; the kernels walk the trees.  One slot =
+ * CYG_DET_WORDS uint32:
+ *   [0]            L1 = leaves of tree 1 (row length of the verdict table)
+ *   [4 + t*2048 + 4*n .. +4), t = 0, 1, node n < 512:  threshold (float64, lo / hi word), left | right << 16,
+ *                  feature | leaf_index << 16   (feature 0 = from_device, 1 = to_device, 2 = leaf)
+ *   [4100 + (l0*L1 + l1) / 32]  bit (l0*L1 + l1) % 32: model.predict == -1 ("A") for a point in leaves (l0, l1)
+ * det_of_env[b] = slot of env b, -1 = none.  Both arrays are device memory owned by the caller; NULL switches it off. */
+#define CYG_DET_WORDS 6160
+#define CYG_DET_TREE0 4
+#define CYG_DET_TREE_STRIDE 2048
+#define CYG_DET_TABLE 4100
+int cyg_set_detectors(cyg_handle h, const uint32_t* slots, int32_t n_slots, const int32_t* det_of_env);
 
 /* Replaces sample_action() (CyberDefenseEnv.py:555-578) for every env; writes hdr[B][4], mask[B][W]. */
 int cyg_sample_actions(cyg_handle h, int32_t mode, uint32_t* hdr, uint32_t* mask, void* stream);

@@ -40,6 +40,10 @@ typedef struct {
   int32_t *in_ptr, *in_src, *in_eid; /* transpose of the base CSR (for _innbrs, volt:473) */
   uint32_t* dev_static;
   float *os_val, *ver_val;
+  /* optional per-env side arrays set by cyo_set_aux(): hop-log ring [B][log_cap], detector slots + slot of env */
+  uint32_t* logs;
+  const uint32_t* det_slots;
+  const int32_t* det_of_env;
 } cyo_t;
 
 /* ---- Philox4x32-10 (oracle/draws.py:philox4x32_10) ---------------------- */
@@ -77,6 +81,8 @@ void cyo_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philo
 typedef struct {
   const cyo_t* n;
   uint32_t *dev, *ckpt, *blocked, *extra, *scal;
+  uint32_t* logs;      /* hop-log ring of this env (NULL: length only) */
+  const uint32_t* det; /* detector slot of this env (NULL: none uploaded) */
   rng_t rng;
   double defcost, cleancost; /* float32 in HBM; accumulate in double per step then store */
 } env_t;
@@ -435,7 +441,10 @@ static void defender_meta(env_t* e, const act_t* a, int atype, int grouped, acc_
       }
     }
     acc->cost += -1.0 * ds;
-    if (scal[CYG_S_LOGS] > 0) scal[CYG_S_FLAGS] |= CYG_FL_DET_TRAINED; /* sklearn fit: out of scope */
+    if (scal[CYG_S_LOGS] > 0) { /* detector.train(last <= 2000 logs): the fit itself is scikit-learn's, on the host */
+      scal[CYG_S_FLAGS] |= CYG_FL_DET_TRAINED;
+      if (!c->turbo) scal[CYG_S_FLAGS] |= CYG_FL_DET_PENDING;
+    }
   } else if (atype == 11) {
     int d = dev_first(n, a); /* host raises ValueError when n_dev == 0 (volt:965-966) */
     uint32_t w = e->dev[d];
@@ -468,6 +477,110 @@ static void restore_device(env_t* e, int d) { /* _apply_device_state (volt:430-4
 }
 
 /* per-device defender actions (volt:989-1123) */
+/* ---- trained detector (CDSimulator.py:714-723: batch_predict == IsolationForest.predict) -------------------------
+ * The forest is fitted by scikit-learn on the host; a slot (include/cygym_b200.h, CYG_DET_*) holds its two trees and
+ * the forest's verdict for every pair of leaves.  predict = two tree walks (sklearn: X[:, feature] <= threshold goes
+ * left, X as float32 -- device ids are exact) + one table bit. */
+static int det_leaf(const uint32_t* tree, double from, double to) {
+  int node = 0;
+  for (;;) {
+    const uint32_t* nd = tree + 4 * node;
+    int feat = (int)(nd[3] & 0xFFFFu);
+    if (feat >= 2) return (int)(nd[3] >> 16);
+    double thr;
+    uint64_t bits = (uint64_t)nd[0] | ((uint64_t)nd[1] << 32);
+    memcpy(&thr, &bits, 8);
+    double x = feat == 0 ? from : to;
+    node = (x <= thr) ? (int)(nd[2] & 0xFFFFu) : (int)(nd[2] >> 16);
+  }
+}
+static int det_is_anomaly(const uint32_t* slot, int from, int to) {
+  int l0 = det_leaf(slot + CYG_DET_TREE0, (double)from, (double)to);
+  int l1 = det_leaf(slot + CYG_DET_TREE0 + CYG_DET_TREE_STRIDE, (double)from, (double)to);
+  uint32_t idx = (uint32_t)l0 * slot[0] + (uint32_t)l1;
+  return (int)((slot[CYG_DET_TABLE + (idx >> 5)] >> (idx & 31)) & 1u);
+}
+/* Iteration order of the CPython set {v_0, v_1, ...} built by inserting small non-negative ints in that order
+ * (hash(v) == v): the reference walks `flagged_senders`, a set, and hands out one _stall draw per member
+ * (volt:1062-1069).  Restates Objects/setobject.c (3.12): open addressing, 9 linear probes, perturb >>= 5,
+ * i = i*5 + 1 + perturb, growth to the first power of two > 4*used when fill*5 >= mask*3.  Returns the member count. */
+static int pyset_order(const int* vals, int n, int* out) {
+  int table[256], tmp[256];
+  int mask = 7, fill = 0;
+  for (int i = 0; i <= mask; i++) table[i] = -1;
+  for (int k = 0; k < n; k++) {
+    const int key = vals[k];
+    unsigned long long perturb = (unsigned long long)key;
+    unsigned i = (unsigned)key & (unsigned)mask;
+    int placed = 0;
+    while (!placed) {
+      int probes = (i + 9 <= (unsigned)mask) ? 9 : 0;
+      unsigned j = i;
+      do {
+        if (table[j] < 0) { table[j] = key; fill++; placed = 1; break; }
+        if (table[j] == key) { placed = 2; break; }
+        j++;
+      } while (probes--);
+      if (placed) break;
+      perturb >>= 5;
+      i = (unsigned)((i * 5ull + 1ull + perturb) & (unsigned long long)mask);
+    }
+    if (placed == 1 && !((unsigned long long)fill * 5ull < (unsigned long long)mask * 3ull)) {
+      int newsize = 8;
+      while (newsize <= fill * 4) newsize <<= 1;
+      const int newmask = newsize - 1;
+      for (int q = 0; q <= newmask; q++) tmp[q] = -1;
+      for (int q = 0; q <= mask; q++) {
+        if (table[q] < 0) continue;
+        const int kk = table[q];
+        unsigned long long pb = (unsigned long long)kk;
+        unsigned ii = (unsigned)kk & (unsigned)newmask;
+        for (;;) {
+          int probes = (ii + 9 <= (unsigned)newmask) ? 9 : 0;
+          unsigned jj = ii;
+          int ok = 0;
+          do { if (tmp[jj] < 0) { tmp[jj] = kk; ok = 1; break; } jj++; } while (probes--);
+          if (ok) break;
+          pb >>= 5;
+          ii = (unsigned)((ii * 5ull + 1ull + pb) & (unsigned long long)newmask);
+        }
+      }
+      mask = newmask;
+      for (int q = 0; q <= mask; q++) table[q] = tmp[q];
+    }
+  }
+  int cnt = 0;
+  for (int q = 0; q <= mask; q++) if (table[q] >= 0) out[cnt++] = table[q];
+  return cnt;
+}
+int cyo_pyset_order(const int* vals, int n, int* out) { return pyset_order(vals, n, out); }
+
+/* one iteration of defender action 5 with a TRAINED detector (volt:1052-1069): the last 30 log records are scored;
+ * with a majority of anomalies every flagged sender is un-compromised and stalled (one _stall draw each, set order) */
+static void scan_trained_once(env_t* e, acc_t* acc) {
+  const cyg_config* c = &e->n->cfg;
+  uint32_t nlogs = e->scal[CYG_S_LOGS];
+  if (!e->det || !e->logs || (e->scal[CYG_S_FLAGS] & CYG_FL_DET_PENDING) || (c->log_cap < 30 && (uint32_t)c->log_cap < nlogs)) {
+    e->scal[CYG_S_FLAGS] |= CYG_FL_ERR_DETECTOR;
+    return;
+  }
+  int nw = nlogs < 30 ? (int)nlogs : 30, n_anom = 0, senders[30], ns = 0, order[30];
+  for (int k = 0; k < nw; k++) {
+    uint32_t r = e->logs[(nlogs - (uint32_t)nw + (uint32_t)k) % (uint32_t)c->log_cap];
+    int from = (int)(r & 0xFFFFu), to = (int)(r >> 16);
+    if (det_is_anomaly(e->det, from, to)) { n_anom++; senders[ns++] = from; }
+  }
+  if (n_anom >= nw / 2 + 1) {
+    int cnt = pyset_order(senders, ns, order);
+    for (int k = 0; k < cnt; k++) {
+      int d = order[k];
+      e->dev[d] &= ~CYG_DEV_COMP;
+      e->dev[d] = set_busy(e->dev[d], stall(e, 0, c->default_high));
+    }
+  }
+  (void)acc;
+}
+
 static void defender_per_device(env_t* e, const act_t* a, int atype, acc_t* acc, nbr_t* tmp) {
   const cyo_t* n = e->n;
   const cyg_config* c = &n->cfg;
@@ -489,7 +602,7 @@ static void defender_per_device(env_t* e, const act_t* a, int atype, acc_t* acc,
       case 5:
         scal[CYG_S_SCAN]++;
         if (scal[CYG_S_LOGS] > 0) { /* window non-empty (volt:1052-1059); untrained detector -> all "D" */
-          if ((scal[CYG_S_FLAGS] & CYG_FL_DET_TRAINED) && !c->turbo) scal[CYG_S_FLAGS] |= CYG_FL_ERR_DETECTOR; /* turbo: predictions = [] (volt:1055) */
+          if ((scal[CYG_S_FLAGS] & CYG_FL_DET_TRAINED) && !c->turbo) scan_trained_once(e, acc); /* turbo: predictions = [] (volt:1055) */
           acc->cost += -0.5 * ds;
           add_defcost(e, 0.5 * ds);
         }
@@ -565,7 +678,8 @@ static void attacker_act(env_t* e, const act_t* a, int atype, acc_t* acc, nbr_t*
           if (is_blocked(e, tmp[j].eid)) continue;
           int v = tmp[j].v;
           for (int rep = 0; rep < tmp[j].mult && !done; rep++) {
-            e->scal[CYG_S_LOGS]++; /* log_communication (volt:1161) */
+            if (e->logs) e->logs[e->scal[CYG_S_LOGS] % (uint32_t)c->log_cap] = (uint32_t)s | ((uint32_t)v << 16);
+            e->scal[CYG_S_LOGS]++; /* log_communication (volt:1161 -> CDSimulator.py:667-673) */
             uint32_t w = e->dev[v];
             if (is_dc) {
               e->dev[v] = w | CYG_DEV_COMP | ((1u << raw) << CYG_DEV_CBY_SHIFT);
@@ -868,6 +982,10 @@ void cyo_destroy(void* h) {
   free(n->in_ptr); free(n->in_src); free(n->in_eid); free(n);
 }
 void cyo_set_base_line(void* h, int32_t bl) { ((cyo_t*)h)->cfg.base_line = bl; }
+void cyo_set_aux(void* h, uint32_t* logs, const uint32_t* det_slots, const int32_t* det_of_env) {
+  cyo_t* n = (cyo_t*)h;
+  n->logs = logs; n->det_slots = det_slots; n->det_of_env = det_of_env;
+}
 
 static void bind_env(env_t* e, const cyo_t* n, int b, int env_id0, uint32_t* dev, uint32_t* ckpt, uint32_t* blocked,
                      uint32_t* extra, uint32_t* scal) {
@@ -877,6 +995,8 @@ static void bind_env(env_t* e, const cyo_t* n, int b, int env_id0, uint32_t* dev
   e->blocked = blocked + (size_t)b * n->EW;
   e->extra = extra + (size_t)b * n->cfg.xcap;
   e->scal = scal + (size_t)b * CYG_NSCAL;
+  e->logs = (n->logs && n->cfg.log_cap > 0) ? n->logs + (size_t)b * n->cfg.log_cap : NULL;
+  e->det = (n->det_slots && n->det_of_env && n->det_of_env[b] >= 0) ? n->det_slots + (size_t)n->det_of_env[b] * CYG_DET_WORDS : NULL;
   e->rng.seed = n->cfg.seed;
   e->rng.env = (uint32_t)(env_id0 + b);
 }

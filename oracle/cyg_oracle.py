@@ -29,7 +29,7 @@ class CygConfig(C.Structure):
         ("scaling_vulnerability", C.c_int32), ("turbo", C.c_int32), ("zero_day", C.c_int32),
         ("zero_day_mask", C.c_uint32), ("att_space_n", C.c_int32), ("def_space_n", C.c_int32),
         ("default_high", C.c_int32), ("n_app_ids", C.c_int32), ("base_line", C.c_int32), ("tri_high", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("log_cap", C.c_int32),
         ("work_scale", C.c_float), ("comp_scale", C.c_float), ("def_scale", C.c_float), ("gamma", C.c_float),
         ("thr_p_add", C.c_uint64), ("thr_p_attacker", C.c_uint64),
         ("poisson_tab", C.c_uint32 * 16), ("tri_tab", C.c_uint32 * 8), ("seed", C.c_uint64),
@@ -47,7 +47,7 @@ def build():
     return _SO
 
 
-def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=5, n_app_ids=0):
+def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=5, n_app_ids=0, log_cap=0):
     """cfg: the dict produced by ref_harness.extract_network()/the network generator."""
     c = CygConfig()
     c.M, c.E, c.X, c.n_exploits, c.xcap = cfg["M"], E, cfg["X"], cfg["n_exploits"], xcap
@@ -60,6 +60,7 @@ def make_config(cfg, E, seed=0, xcap=16, base_line="Nash", tri_mode=2, tri_high=
     c.n_app_ids = cfg.get("n_app_ids", n_app_ids)
     c.base_line = BL.get(base_line, 4)
     c.tri_high = tri_high
+    c.log_cap = int(log_cap)
     c.work_scale, c.comp_scale, c.def_scale, c.gamma = cfg["work_scale"], cfg["comp_scale"], cfg["def_scale"], cfg["gamma"]
     c.thr_p_add = D.bernoulli_threshold(cfg["p_add"])
     c.thr_p_attacker = D.bernoulli_threshold(cfg["p_attacker"])
@@ -90,6 +91,8 @@ def lib():
         L.cyo_create.argtypes = [C.POINTER(CygConfig)] + [C.c_void_p] * 6
         L.cyo_destroy.argtypes = [C.c_void_p]
         L.cyo_set_base_line.argtypes = [C.c_void_p, C.c_int32]
+        L.cyo_set_aux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cyo_pyset_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.cyo_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int]
         L.cyo_randomize.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.cyo_sample_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -107,8 +110,11 @@ def _p(a):
 class OracleState:
     """Canonical per-env state as numpy arrays (include/cygym_b200.h layout)."""
 
-    def __init__(self, B, M, E, xcap):
-        self.B, self.M, self.E, self.xcap = B, M, E, xcap
+    def __init__(self, B, M, E, xcap, log_cap=0):
+        self.B, self.M, self.E, self.xcap, self.log_cap = B, M, E, xcap, int(log_cap)
+        self.logs = np.zeros((B, max(1, self.log_cap)), np.uint32)  # hop-log ring (from | to << 16), record k at k % log_cap
+        self.det_slots = None                                        # [n_slots, CYG_DET_WORDS] uploaded detectors
+        self.det_of_env = np.full(B, -1, np.int32)
         self.dev = np.zeros((B, M), np.uint32)
         self.ckpt = np.zeros((B, M), np.uint32)
         self.blocked = np.zeros((B, max(1, (E + 31) // 32)), np.uint32)
@@ -118,10 +124,21 @@ class OracleState:
 
     def copy(self):
         o = OracleState.__new__(OracleState)
-        o.B, o.M, o.E, o.xcap = self.B, self.M, self.E, self.xcap
-        for k in ("dev", "ckpt", "blocked", "extra", "scal"):
+        o.B, o.M, o.E, o.xcap, o.log_cap = self.B, self.M, self.E, self.xcap, self.log_cap
+        for k in ("dev", "ckpt", "blocked", "extra", "scal", "logs", "det_of_env"):
             setattr(o, k, getattr(self, k).copy())
+        o.det_slots = None if self.det_slots is None else self.det_slots.copy()
         return o
+
+    def log_records(self, b, last=2000):
+        """The last `last` hop-log records of env b in log order, int array [n, 2] of (from, to)."""
+        n = int(self.scal[b, 6])
+        k = min(n, last)
+        if k > self.log_cap:
+            raise ValueError(f"the ring keeps {self.log_cap} records, {k} are needed")
+        idx = (np.arange(n - k, n) % max(1, self.log_cap)).astype(np.int64)
+        r = self.logs[b, idx]
+        return np.stack([r & 0xFFFF, r >> 16], axis=1).astype(np.int64)
 
     def set_env(self, b, st):
         """st: dict from ref_harness.extract_state()."""
@@ -158,7 +175,28 @@ class Oracle:
         self.L.cyo_set_base_line(self.h, BL.get(name, 4))
 
     def new_state(self, B):
-        return OracleState(B, self.M, self.E, self.cfg.xcap)
+        return OracleState(B, self.M, self.E, self.cfg.xcap, self.cfg.log_cap)
+
+    def _aux(self, st):
+        self._keep_aux = (st.logs, st.det_slots, st.det_of_env)
+        self.L.cyo_set_aux(self.h, _p(st.logs) if st.log_cap > 0 else None, _p(st.det_slots) if st.det_slots is not None else None,
+                           _p(st.det_of_env))
+
+    def service_detectors(self, st, seed_of_env=None):
+        """Fit + upload the detector of every env whose action 10 left CYG_FL_DET_PENDING (volt:945-962 ->
+        CDSimulator.py:687-695), as the product's host side does (cygym_b200/detector.py is shared: the fit is sklearn's)."""
+        from cygym_b200 import detector as DET
+        pend = np.nonzero(st.scal[:, 2] & 8)[0]
+        for b in pend:
+            model = DET.fit_detector(st.log_records(int(b)), None if seed_of_env is None else seed_of_env(int(b)))
+            slot = DET.pack_detector(model)
+            if st.det_of_env[b] < 0:
+                st.det_of_env[b] = 0 if st.det_slots is None else len(st.det_slots)
+                st.det_slots = slot[None].copy() if st.det_slots is None else np.concatenate([st.det_slots, slot[None]])
+            else:
+                st.det_slots[st.det_of_env[b]] = slot
+            st.scal[b, 2] &= ~np.uint32(8)
+        return len(pend)
 
     def step(self, st, hdr, mask, order=None, flags=0, n_threads=1, want_pre=False):
         """hdr [G,B,4] or [B,4] uint32; mask [G,B,W] or [B,W]."""
@@ -179,6 +217,7 @@ class Oracle:
         done = np.zeros(B, np.int32)
         ex = np.zeros(B, np.int32)
         pre = np.zeros((B, 3, self.W), np.uint32) if want_pre else None
+        self._aux(st)
         self.L.cyo_step(self.h, B, self.env_id0, _p(st.dev), _p(st.ckpt), _p(st.blocked), _p(st.extra), _p(st.scal),
                         _p(hdr), _p(mask), _p(order), ostride, G, flags, _p(raw), _p(shaped), _p(done), _p(ex), _p(pre),
                         n_threads)

@@ -26,6 +26,12 @@ CASES = {
     "m33_odd": dict(numOfDevice=25, M=33, seed=8, T=150, randomize_every=11),
     "c2_m50_turbo": dict(numOfDevice=40, M=50, seed=29, T=200, keep_training=True,
                          env_attrs=dict(turbo=True, workload_period_base=4, workload_period_max=12, turbo_ramp_steps=40)),
+    # real detector training (defender 10: IsolationForest fit on the hop log) and scans that consult it (defender 5,
+    # volt:1052-1069): the hop log's content is part of the state (log_cap)
+    "c2_m50_detector": dict(numOfDevice=40, M=50, seed=31, T=240, keep_training=True, log_cap=2048, grouped_every=0,
+                            def_types=[5, 5, 5, 10, 10, 1, 8, 6, 13, 7]),
+    "c1_m30_detector_busy_log": dict(numOfDevice=20, M=30, seed=32, T=400, keep_training=True, log_cap=2048, grouped_every=0,
+                                     randomize_every=0, def_types=[5, 5, 5, 5, 10, 8, 8, 6, 9], att_types=[1, 1, 1, 2]),
     # M > 500: lazy workload placement (CDSimulator.py:318-343) and the sparse attacker star (volt:1399-1429);
     # M = 2000 is BASELINE.json's config C4 shape (the generic 64-word layout / large-network kernel)
     "c4_m600_lazy": dict(numOfDevice=590, M=600, seed=9, T=64, xcap=512, randomize_every=23,

@@ -270,6 +270,12 @@ def context():
     return _CTX
 
 
+def seed_numpy_global(seed):
+    """numpy's global stream (the REAL module, not the proxy the reference modules see): scikit-learn estimators with
+    random_state=None draw from it (Detector, CDSimulator.py:683)."""
+    _real_np.random.seed(int(seed))
+
+
 def build_env(numOfDevice=10, Max_network_size=20, seed=1, quiet=True, **attrs):
     """initialize_environment() exactly as init_experiments.py:36-51 configures it, then
     rebuild the graph cache the way DoubleOracle.restore / reset(from_init=True) do

@@ -33,8 +33,25 @@ def _policy_ops(rng, T, M, n_logs_fn, grouped_every=9, randomize_every=41, basel
             yield ("step", mode)
 
 
+LOG_TAIL = 64
+
+
+def _log_tail(env):
+    """The last LOG_TAIL records of simulator.logger.logs as from_device | to_device << 16 (zero padded at the front)."""
+    logs = env.simulator.logger.logs[-LOG_TAIL:]
+    out = np.zeros(LOG_TAIL, np.uint32)
+    for k, l in enumerate(logs):
+        out[LOG_TAIL - len(logs) + k] = np.uint32(int(l["from_device"]) | (int(l["to_device"]) << 16))
+    return out
+
+
 def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, grouped_every=9,
-           randomize_every=41, baseline_every=0, none_every=13, env_attrs=None, env_id=0, keep_training=False):
+           randomize_every=41, baseline_every=0, none_every=13, env_attrs=None, env_id=0, keep_training=False, log_cap=0,
+           def_types=None, att_types=None):
+    """log_cap > 0: the hop log's content is part of the recording (its last LOG_TAIL records after every op) and, with
+    keep_training, detector training is real: numpy's global stream -- what the reference's IsolationForest(random_state=
+    None) draws from -- is seeded right before every step that trains, and the seed is recorded (`train_seed`).
+    def_types: optional list the defender's sampled action TYPE is redrawn from (more scans / trainings per file)."""
     from . import cyg_oracle as O
     from . import ref_harness as H
 
@@ -49,7 +66,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
     init = H.extract_state(env, netw, ctx.epoch)
     rec = dict(kind=[], mode=[], n_groups=[], hdr=[], mask=[], order=[], baseline=[],
                dev=[], ckpt=[], blocked=[], scal=[], extra=[], n_extra=[], raw=[], shaped=[], done=[], exec_atype=[],
-               pre=[], obs_def=[], obs_att=[], sa_first=[])
+               pre=[], obs_def=[], obs_att=[], sa_first=[], train_seed=[], logs_tail=[])
 
     def snap(raw=0.0, shaped=0.0, done=False, ex=0, state=None):
         st = H.extract_state(env, netw, ctx.epoch)
@@ -67,6 +84,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
                     if s6[i, col] > 0.5:
                         pre[row, i >> 5] |= np.uint32(1 << (i & 31))
         rec["pre"].append(pre)
+        rec["logs_tail"].append(_log_tail(env))
         rec["obs_def"].append(np.asarray(env._get_defender_state(), np.float32))
         rec["obs_att"].append(np.asarray(env._get_attacker_state(), np.float32))
 
@@ -74,6 +92,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
         sf = np.full(G_MAX, -1, np.int16)
         sf[:len(firsts)] = firsts
         rec["sa_first"].append(sf)  # device_indices[0] of each sampled group in the reference's draw order
+        rec["train_seed"].append(-1)
         hdr = np.zeros((G_MAX, 4), np.uint32); mask = np.zeros((G_MAX, W), np.uint32); order = np.zeros((G_MAX, M), np.uint16)
         for g, a in enumerate(groups):
             h, m, o = O.pack_action(a, mode, M, order_form)
@@ -108,10 +127,23 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
         elif op[0] == "step":
             a0 = H.ref_sample_action(env, op[1])
             a = fix(a0, op[1])
+            if def_types and op[1] == "defender":  # a scripted type on the sampled device list (more scans / trainings)
+                at = int(rng.choice(def_types))
+                if at == 10 and len(env.simulator.logger.logs) > 0 and not keep_training:
+                    at = 8
+                a = (at, a[1], a[2], a[3])
+            if att_types and op[1] == "attacker":
+                a = (int(rng.choice(att_types)), a[1], a[2], a[3])
             push_op_args = (OP_STEP, op[1], [a], 0, [a0[2][0]])
+            trains = op[1] == "defender" and a[0] == 10 and len(env.simulator.logger.logs) > 0 and keep_training and env.base_line == "Nash"
+            tseed = 100000 + len(rec["kind"])
+            if trains:
+                H.seed_numpy_global(tseed)  # IsolationForest(random_state=None).fit draws from numpy's global stream
             # sample_action consumed an epoch on the reference side: record it as an explicit epoch bump
             raw, shaped, done, info, state = H.ref_step(env, op[1], a)
             push_op(*push_op_args)
+            if trains:
+                rec["train_seed"][-1] = tseed
             snap(raw, shaped, done, info["executed_atype"], state)
         else:  # grouped
             mode = op[1]
@@ -139,7 +171,7 @@ def record(numOfDevice, M, seed, T, draw_seed=2024, order_form=False, xcap=32, g
     for k in ("dev", "ckpt", "blocked", "extra", "scal"):
         out["init_" + k] = init[k]
     meta = dict(cfg=netw["cfg"], draw_seed=draw_seed, env_id=env_id, xcap=xcap, order_form=bool(order_form),
-                numOfDevice=numOfDevice, M=M, seed=seed, T=T)
+                numOfDevice=numOfDevice, M=M, seed=seed, T=T, log_cap=int(log_cap), scripted_def_types=bool(def_types or att_types))
     out["meta"] = np.asarray(json.dumps(meta))
     return out
 
@@ -148,7 +180,7 @@ class Mismatch(AssertionError):
     pass
 
 
-def _check_sampled(g, t, gi, kind, order_form, got, label):
+def _check_sampled(g, t, gi, kind, order_form, got, label, scripted_def=False):
     """sample_action() parity: `got` = (hdr[4], mask[W], order[M]) an implementation sampled where the reference's own
     sample_action() produced the recorded group `gi` of op `t`.  The recorder rewrites two things afterwards (record():
     fix() turns defender 10 into 8 while the detector has logs; grouped defender steps get a scripted action type), the
@@ -157,7 +189,7 @@ def _check_sampled(g, t, gi, kind, order_form, got, label):
     rh = np.asarray(g["hdr"][t][gi], np.uint32)
     mode = int(g["mode"][t])
     sat, rat = int(h[0]) & 0xFF, int(rh[0]) & 0xFF
-    if kind == OP_STEP and not (sat == rat or (mode == 0 and sat == 10 and rat == 8)):
+    if kind == OP_STEP and not scripted_def and not (sat == rat or (mode == 0 and sat == 10 and rat == 8)):
         raise Mismatch(f"{label}: op {t}: sample_action type {sat} != recorded {rat}")
     if (int(h[0]) >> 8) != (int(rh[0]) >> 8) or int(h[1]) != int(rh[1]) or int(h[3]) != int(rh[3]):
         raise Mismatch(f"{label}: op {t} group {gi}: sample_action header {[hex(int(x)) for x in h]} != {[hex(int(x)) for x in rh]}")
@@ -188,6 +220,7 @@ def replay(g, impl, check_obs=True, rtol=1e-5, label="impl", check_sample=True):
     meta = json.loads(str(g["meta"]))
     M = meta["M"]
     order_form = meta["order_form"]
+    has_logs = meta.get("log_cap", 0) > 0 and "logs_tail" in g
     impl.load({k: np.array(g["init_" + k]) for k in ("dev", "ckpt", "blocked", "extra", "scal")})
     T = len(g["kind"])
     for t in range(T):
@@ -206,7 +239,7 @@ def replay(g, impl, check_obs=True, rtol=1e-5, label="impl", check_sample=True):
             sampled = [gi for gi in range(G) if (int(hdr[gi, 0, 0]) & 0xFF) != 0x80]
             if check_sample and hasattr(impl, "sample_action"):
                 for gi in sampled:
-                    _check_sampled(g, t, gi, kind, order_form, impl.sample_action(int(g["mode"][t])), label)
+                    _check_sampled(g, t, gi, kind, order_form, impl.sample_action(int(g["mode"][t])), label, meta.get("scripted_def_types", False))
             else:
                 impl.bump_epoch(len(sampled))
             out = impl.step(hdr, mask, order, 1 if kind == OP_GROUPED else 0)
@@ -221,7 +254,12 @@ def replay(g, impl, check_obs=True, rtol=1e-5, label="impl", check_sample=True):
             if "pre_masks" in out and out["pre_masks"] is not None:
                 if not np.array_equal(np.asarray(out["pre_masks"][0]), g["pre"][t]):
                     raise Mismatch(f"{label}: op {t}: pre-evolve state masks differ")
+        if has_logs and int(g["train_seed"][t]) >= 0:
+            impl.service_detector(int(g["train_seed"][t]))  # the reference trained inside that step (volt:945-962)
         st = impl.state()
+        if has_logs and "logs_tail" in st:
+            if not np.array_equal(np.asarray(st["logs_tail"], np.uint32), np.asarray(g["logs_tail"][t], np.uint32)):
+                raise Mismatch(f"{label}: op {t}: hop-log records differ")
         for k in ("dev", "ckpt", "blocked"):
             if not np.array_equal(np.asarray(st[k]), g[k][t]):
                 bad = np.nonzero(np.asarray(st[k]) != g[k][t])[0]
@@ -247,6 +285,15 @@ def replay(g, impl, check_obs=True, rtol=1e-5, label="impl", check_sample=True):
     return T
 
 
+def log_tail_of_ring(ring, n, cap):
+    """The last LOG_TAIL records of a hop-log ring (record k at k % cap), zero padded at the front."""
+    k = min(n, LOG_TAIL, cap)
+    out = np.zeros(LOG_TAIL, np.uint32)
+    if k:
+        out[LOG_TAIL - k:] = np.asarray(ring, np.uint32)[(np.arange(n - k, n) % cap).astype(np.int64)]
+    return out
+
+
 class OracleImpl:
     """The replay() protocol on top of the C oracle (B = 1)."""
 
@@ -255,7 +302,8 @@ class OracleImpl:
         meta = json.loads(str(g["meta"]))
         self.meta = meta
         netw = {k: np.array(g["net_" + k]) for k in ("row_ptr", "col", "mult", "dev_static", "os_val", "ver_val")}
-        self.cfg = O.make_config(meta["cfg"], len(netw["col"]), seed=meta["draw_seed"], xcap=meta["xcap"], base_line=base_line)
+        self.cfg = O.make_config(meta["cfg"], len(netw["col"]), seed=meta["draw_seed"], xcap=meta["xcap"], base_line=base_line,
+                                 log_cap=meta.get("log_cap", 0))
         self.orc = O.Oracle(netw, self.cfg, env_id0=meta["env_id"])
         self.st = self.orc.new_state(1)
 
@@ -282,7 +330,13 @@ class OracleImpl:
         self.orc.set_base_line(name)
 
     def state(self):
-        return dict(dev=self.st.dev[0], ckpt=self.st.ckpt[0], blocked=self.st.blocked[0], extra=self.st.extra[0], scal=self.st.scal[0])
+        d = dict(dev=self.st.dev[0], ckpt=self.st.ckpt[0], blocked=self.st.blocked[0], extra=self.st.extra[0], scal=self.st.scal[0])
+        if self.st.log_cap > 0:
+            d["logs_tail"] = log_tail_of_ring(self.st.logs[0], int(self.st.scal[0, 6]), self.st.log_cap)
+        return d
+
+    def service_detector(self, seed):
+        self.orc.service_detectors(self.st, lambda b: seed)
 
     def observe(self, mode):
         return self.orc.observe(self.st, mode)[0]

@@ -24,7 +24,8 @@ class CudaImpl:
         self.torch = torch
         net, meta = network_from_golden(g)
         self.meta = meta
-        self.env = VectorCyberDefenseEnv(net, 1, seed=meta["draw_seed"], env_id0=meta["env_id"], xcap=meta["xcap"])
+        self.env = VectorCyberDefenseEnv(net, 1, seed=meta["draw_seed"], env_id0=meta["env_id"], xcap=meta["xcap"],
+                                         log_cap=meta.get("log_cap", 0), detector_slots=1 if meta.get("log_cap", 0) else 0)
 
     def load(self, init):
         self.env.import_state({k: np.asarray(v, np.uint32)[None] for k, v in init.items()})
@@ -63,7 +64,14 @@ class CudaImpl:
     def state(self):
         c = self.env.export_state()
         self.torch.cuda.synchronize()
-        return {k: v.cpu().numpy().view(np.uint32)[0] for k, v in c.items()}
+        d = {k: v.cpu().numpy().view(np.uint32)[0] for k, v in c.items()}
+        if "logs" in d:
+            from oracle.trajectory import log_tail_of_ring
+            d["logs_tail"] = log_tail_of_ring(d["logs"], int(d["scal"][6]), self.env.log_cap)
+        return d
+
+    def service_detector(self, seed):
+        self.env.service_detectors(lambda b: seed)
 
     def observe(self, mode):
         o = self.env.observe(mode)

@@ -22,6 +22,9 @@ using namespace cyg;
 struct Emu {
   TableBlob blob;
   Net net;
+  uint32_t* logs = nullptr;            /* [B][log_cap] hop-log rings */
+  const uint32_t* det_slots = nullptr; /* uploaded detectors */
+  const int32_t* det_of_env = nullptr;
 };
 
 static std::string g_err;
@@ -67,6 +70,8 @@ static void step_w(Emu* em, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, u
     const uint32_t* m = mask + (size_t)b * n.Wm;
     const uint16_t* o = order ? order + (size_t)b * order_stride : nullptr;
     Env<W> e(&n, rec.data(), ckpt + (size_t)b * n.M, extra + (size_t)b * n.cfg.xcap, (uint32_t)(env_id0 + b));
+    if (em->logs && n.cfg.log_cap > 0) e.logs = em->logs + (size_t)b * n.cfg.log_cap;
+    if (em->det_slots && em->det_of_env && em->det_of_env[b] >= 0) e.det = em->det_slots + (size_t)em->det_of_env[b] * CYG_DET_WORDS;
     int atype = e.step(h, m, o, (size_t)B * 4, (size_t)B * n.Wm, (size_t)B * order_stride, G, flags, raw + b, shaped + b,
                        done + b, pre_masks ? pre_masks + (size_t)b * 3 * n.Wm : nullptr);
     if (exec_atype) exec_atype[b] = atype;
@@ -149,6 +154,11 @@ void* emu_create(const cyg_config* cfg, const int32_t* row_ptr, const int32_t* c
 const char* emu_last_error(void) { return g_err.c_str(); }
 void emu_destroy(void* h) { delete (Emu*)h; }
 void emu_set_base_line(void* h, int32_t bl) { ((Emu*)h)->net.cfg.base_line = bl; }
+void emu_set_aux(void* h, uint32_t* logs, const uint32_t* det_slots, const int32_t* det_of_env) {
+  Emu* em = (Emu*)h;
+  em->logs = logs; em->det_slots = det_slots; em->det_of_env = det_of_env;
+}
+int emu_pyset_order(const int* vals, int n, int* out) { return Env<1>::pyset_order(vals, n, out); }
 int emu_record_words(void* h) { return ((Emu*)h)->net.S; }
 int emu_step(void* h, int B, int env_id0, uint32_t* dev, uint32_t* ckpt, uint32_t* blocked, uint32_t* extra, uint32_t* scal,
              const uint32_t* hdr, const uint32_t* mask, const uint16_t* order, int order_stride, int G, uint32_t flags,

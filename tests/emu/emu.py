@@ -41,6 +41,8 @@ def lib():
         L.emu_record_words.argtypes = [C.c_void_p]
         L.emu_step.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_uint32] + [C.c_void_p] * 5
         L.emu_randomize.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.emu_set_aux.argtypes = [C.c_void_p] * 4
+        L.emu_pyset_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.emu_rebuild.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.emu_sample_actions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.emu_observe.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -95,6 +97,9 @@ class Emu:
         raw = np.zeros(B, np.float32); shaped = np.zeros(B, np.float32)
         done = np.zeros(B, np.int32); ex = np.zeros(B, np.int32)
         pre = np.zeros((B, 3, self.W), np.uint32) if want_pre else None
+        self._keep_aux = (st.logs, st.det_slots, st.det_of_env)
+        self.L.emu_set_aux(self.h, _p(st.logs) if getattr(st, "log_cap", 0) > 0 else None,
+                           _p(st.det_slots) if st.det_slots is not None else None, _p(st.det_of_env))
         self.L.emu_step(self.h, B, self.env_id0, _p(st.dev), _p(st.ckpt), _p(st.blocked), _p(st.extra), _p(st.scal),
                         _p(hdr), _p(mask), _p(order), ostride, G, flags, _p(raw), _p(shaped), _p(done), _p(ex), _p(pre))
         out = dict(raw=raw, shaped=shaped, done=done, exec_atype=ex)
@@ -131,9 +136,10 @@ class EmuImpl:
         from oracle import cyg_oracle as O
         meta = json.loads(str(g["meta"]))
         netw = {k: np.array(g["net_" + k]) for k in ("row_ptr", "col", "mult", "dev_static", "os_val", "ver_val")}
-        self.cfg = O.make_config(meta["cfg"], len(netw["col"]), seed=meta["draw_seed"], xcap=meta["xcap"])
+        self.cfg = O.make_config(meta["cfg"], len(netw["col"]), seed=meta["draw_seed"], xcap=meta["xcap"], log_cap=meta.get("log_cap", 0))
         self.emu = Emu(netw, self.cfg, env_id0=meta["env_id"])
-        self.st = O.OracleState(1, self.cfg.M, self.cfg.E, self.cfg.xcap)
+        self.st = O.OracleState(1, self.cfg.M, self.cfg.E, self.cfg.xcap, self.cfg.log_cap)
+        self._orc = O.Oracle(netw, self.cfg, env_id0=meta["env_id"])  # only its host-side detector service (sklearn fit + pack)
 
     def load(self, init):
         self.st.dev[0] = init["dev"]; self.st.ckpt[0] = init["ckpt"]
@@ -158,7 +164,14 @@ class EmuImpl:
         self.emu.set_base_line(name)
 
     def state(self):
-        return dict(dev=self.st.dev[0], ckpt=self.st.ckpt[0], blocked=self.st.blocked[0], extra=self.st.extra[0], scal=self.st.scal[0])
+        d = dict(dev=self.st.dev[0], ckpt=self.st.ckpt[0], blocked=self.st.blocked[0], extra=self.st.extra[0], scal=self.st.scal[0])
+        if self.st.log_cap > 0:
+            from oracle.trajectory import log_tail_of_ring
+            d["logs_tail"] = log_tail_of_ring(self.st.logs[0], int(self.st.scal[0, 6]), self.st.log_cap)
+        return d
+
+    def service_detector(self, seed):
+        self._orc.service_detectors(self.st, lambda b: seed)
 
     def observe(self, mode):
         return self.emu.observe(self.st, mode)[0]

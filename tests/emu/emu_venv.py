@@ -25,13 +25,15 @@ class _Scalars:
 
 
 class EmuVectorEnv:
-    def __init__(self, network, num_envs, device=None, seed=0, env_id0=0, base_line="Nash", xcap=16, stream=None):
+    def __init__(self, network, num_envs, device=None, seed=0, env_id0=0, base_line="Nash", xcap=16, stream=None, log_cap=0, detector_slots=0):
         self.net, self.B, self.M, self.W = network, int(num_envs), network.M, network.W
         self.xcap = max(int(xcap), len(network.template.get("extra", ())))
-        self.cfg = O.make_config(network.cfg, network.E, seed=seed, xcap=self.xcap, base_line=base_line)
+        self.cfg = O.make_config(network.cfg, network.E, seed=seed, xcap=self.xcap, base_line=base_line, log_cap=log_cap)
         self.emu = emu.Emu(dict(row_ptr=network.row_ptr, col=network.col, mult=network.mult, dev_static=network.dev_static,
                                 os_val=network.os_val, ver_val=network.ver_val), self.cfg, env_id0=env_id0)
-        self.st = O.OracleState(self.B, self.M, network.E, self.xcap)
+        self.st = O.OracleState(self.B, self.M, network.E, self.xcap, log_cap)
+        self._orc = O.Oracle(dict(row_ptr=network.row_ptr, col=network.col, mult=network.mult, dev_static=network.dev_static,
+                                  os_val=network.os_val, ver_val=network.ver_val), self.cfg, env_id0=env_id0)  # host-side detector service only
         self.scalars = _Scalars(self.st)
         self._out = torch.zeros(3, self.B, dtype=torch.float32)
         self._pre = torch.zeros(self.B, 3, self.W, dtype=torch.int32)
@@ -61,10 +63,20 @@ class EmuVectorEnv:
             dst[:] = 0
             w = min(dst.shape[1], a.shape[1])
             dst[:, :w] = a[:, :w]
+        if self.st.log_cap and canon.get("logs") is not None:
+            a = canon["logs"]
+            a = (a.cpu().numpy() if hasattr(a, "cpu") else np.asarray(a)).view(np.uint32).reshape(self.B, -1)
+            self.st.logs[:, : min(self.st.log_cap, a.shape[1])] = a[:, : self.st.log_cap]
         return self
 
     def export_state(self):
-        return {k: torch.from_numpy(getattr(self.st, k).view(np.int32).copy()) for k in ("dev", "ckpt", "blocked", "extra", "scal")}
+        d = {k: torch.from_numpy(getattr(self.st, k).view(np.int32).copy()) for k in ("dev", "ckpt", "blocked", "extra", "scal")}
+        if self.st.log_cap:
+            d["logs"] = torch.from_numpy(self.st.logs.view(np.int32).copy())
+        return d
+
+    def service_detectors(self, seed_of_env=None):
+        return self._orc.service_detectors(self.st, seed_of_env)
 
     def to_device(self, hdr, mask, order=None):
         f = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a).view(dt).copy())

@@ -116,7 +116,9 @@ def test_unmodified_double_oracle_runs_on_the_dropin(numOfDevice, M, seed):
         assert (d_ref.device_type == "DomainController") == (d_our.device_type == "DomainController")  # the one type the step path reads
         assert int(d_ref.busy_time) == int(d_our.busy_time) and (d_ref.workload is None) == (d_our.workload is None)
     assert sorted(ref.simulator.subnet.graph.get_edgelist()) == sorted(ours.simulator.subnet.graph.get_edgelist())
-    assert len(ref.simulator.logger.get_logs()) == len(ours.simulator.logger.get_logs())
+    la, lb = ref.simulator.logger.get_logs(), ours.simulator.logger.get_logs()
+    assert len(la) == len(lb)
+    assert [(l["from_device"], l["to_device"]) for l in la[-2000:]] == [(l["from_device"], l["to_device"]) for l in lb[-2000:]]
     assert [e.discovered for e in ref.simulator.exploits] == [e.discovered for e in ours.simulator.exploits]
 
 
@@ -149,3 +151,35 @@ def test_dropin_pickles_and_info_counters():
     assert ra[1] == rb[1] and ra[3] == rb[3] and np.array_equal(ra[0], rb[0]) and ra[4]["Compromised_devices"] == rb[4]["Compromised_devices"]
     with pytest.raises(AttributeError):
         env.simulator.subnet.net[0].isCompromised = True
+
+
+def test_dropin_trains_and_consults_the_detector_like_the_reference():
+    """Defender action 10 fits the IsolationForest on the hop log (scikit-learn, on the host, from the ring the kernels
+    keep) and later scans (action 5) consult it on the device (volt:945-962, :1020-1069): same 6-tuples, same device
+    state, same log as the reference, step by step, with numpy's global stream seeded alike before every fit."""
+    warnings.filterwarnings("ignore")
+    ref, ours = _pair(20, 30, 41)
+    rng = np.random.default_rng(5)
+    trained = scans_that_cleaned = 0
+    for t in range(260):
+        mode = "defender" if t % 2 == 0 else "attacker"
+        ref.mode = ours.mode = mode
+        a, b = ref.sample_action(), ours.sample_action()
+        assert int(a[0]) == int(b[0]) and list(map(int, a[2])) == list(map(int, b[2]))
+        at = int(rng.choice([5, 5, 5, 10, 8, 6])) if mode == "defender" else int(rng.choice([1, 1, 2]))
+        act = (at, a[1], a[2], a[3])
+        if at == 10 and len(ref.simulator.logger.get_logs()) > 0:
+            H.seed_numpy_global(9000 + t)
+            ours.detector_fit_seed = 9000 + t
+            trained += 1
+        before = sum(d.isCompromised for d in ref._get_ordered_devices())
+        ra, rb = ref.step(act), ours.step(act)
+        if at == 5 and sum(d.isCompromised for d in ref._get_ordered_devices()) < before:
+            scans_that_cleaned += 1
+        assert abs(ra[1] - rb[1]) <= 1e-5 * max(1.0, abs(ra[1])) and ra[3] == rb[3], t
+        assert np.array_equal(np.asarray(ra[0]), rb[0]), t
+        for x, y in zip(ref._get_ordered_devices(), ours._get_ordered_devices()):
+            assert x.isCompromised == y.isCompromised and int(x.busy_time) == int(y.busy_time), (t, x.id)
+    la, lb = ref.simulator.logger.get_logs(), ours.simulator.logger.get_logs()
+    assert [(l["from_device"], l["to_device"]) for l in la[-2000:]] == [(l["from_device"], l["to_device"]) for l in lb[-2000:]]
+    assert ours.simulator.detector.trained and trained >= 5 and scans_that_cleaned >= 1, (trained, scans_that_cleaned)
