@@ -97,7 +97,7 @@ SPILL_LIMIT = 256   # bytes of spill stores tolerated in the config-C3 step kern
 THREAD_CAPS = (640, 512)  # threads per CTA -> 93 / 127 registers per thread at one CTA per SM (640 measured fastest)
 
 
-def _step_kernel_spill(ptxas_log, mangled="_Z15cyg_step_kernelILi4ELb1EEv10StepParams"):
+def _step_kernel_spill(ptxas_log, mangled="_Z15cyg_step_kernelILi4ELb1ELb0ELb0EEv10StepParams"):
     """Bytes of spill stores ptxas reports for the plain-step W = 4 kernel (None when the log has no such entry)."""
     import re
     m = re.search(r"Function properties for " + re.escape(mangled) + r"\s+\d+ bytes stack frame, (\d+) bytes spill stores", ptxas_log)

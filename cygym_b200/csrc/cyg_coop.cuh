@@ -366,6 +366,7 @@ struct Coop {
    * consecutive sources of the snapshot.  A source's scan depends on earlier sources only through isCompromised
    * of its own hit (a "not yet compromised" hit is invalid if a lower lane hit the same device), so a round
    * commits the lanes below the first such lane and restarts from it: bit-identical to the sequential loop. */
+  template <bool LOG = true>
   static __device__ __forceinline__ void attack(E& e, const typename E::Act& a) {
     const int lane = lane_id();
     uint32_t src[W];
@@ -381,7 +382,7 @@ struct Coop {
     __syncwarp();
     uint32_t logs_add = 0, zk = 0;
     uint32_t log_base = e.scal(CYG_S_LOGS); /* hop-log index of the next record (uniform; only used with a log ring) */
-    const bool logging = e.logs != nullptr;
+    const bool logging = LOG && e.logs != nullptr;
     for (int xi = 0; xi < a.n_ex; xi++) { /* uniform */
       int raw = a.ex(xi);
       uint32_t zx = 0;

@@ -198,7 +198,13 @@ __host__ __device__ inline SmemPlan smem_plan(uint32_t hot_words, int S, int NB)
 /* PLAIN: one ungrouped action per env, device lists as sets (no order array) -- the hot form: thread-per-env phases
  * A / C plus the warp-per-env phase B.  !PLAIN: grouped steps and explicit order lists, everything thread-per-env
  * (the sequential forms of every action live only in this instantiation). */
-template <int W, bool PLAIN>
+/* ROLL: the cyg_rollout form of the plain kernel -- action rows shared by runs of envs, raw rewards summed per env.  A
+ * separate instantiation: compiled into the step kernel proper, the row indexing and the accumulation cost it 4.5 us per
+ * step (registers) although no step ever takes those branches. */
+/* LOG: the env keeps a hop-log ring and may hold a trained detector (cfg.log_cap > 0): the lateral-movement scan writes
+ * its hops, scans consult the detector.  Also its own instantiation (the handles that keep only the log's length --
+ * every throughput run -- take the kernel without that code: ~1 us per step). */
+template <int W, bool PLAIN, bool ROLL = false, bool LOG = true>
 __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(const __grid_constant__ StepParams p) {
   unsigned char* smem = reinterpret_cast<unsigned char*>(cyg_smem);
   const int NB = p.block_envs, NT = blockDim.x, tid = threadIdx.x; /* NB envs, NT >= NB threads */
@@ -231,15 +237,18 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   const int lane = tid & 31;
   for (int t = 0; t < T; t++) { /* the steps fused into this launch; the records stay in shared memory */
   const bool last = t == T - 1;
-  const uint32_t* hdr_t = p.hdr + (size_t)t * p.n_rows * 4 * (PLAIN ? 1 : 0);
-  const uint32_t* mask_t = p.mask + (size_t)t * p.n_rows * W * (PLAIN ? 1 : 0);
-  float* raw_t = p.raw ? p.raw + (size_t)t * p.B : nullptr;
-  float* shaped_t = p.shaped ? p.shaped + (size_t)t * p.B : nullptr;
-  int32_t* done_t = p.done ? p.done + (size_t)t * p.B : nullptr;
+  const uint32_t* hdr_t = p.hdr + (size_t)t * (ROLL ? p.n_rows : p.B) * 4 * (PLAIN ? 1 : 0);
+  const uint32_t* mask_t = p.mask + (size_t)t * (ROLL ? p.n_rows : p.B) * W * (PLAIN ? 1 : 0);
+  float* raw_t = p.raw + (size_t)t * p.B;
+  float* shaped_t = p.shaped + (size_t)t * p.B;
+  int32_t* done_t = p.done + (size_t)t * p.B;
   const uint8_t* bl_t = p.bl_env ? p.bl_env + (size_t)t * p.bl_stride : nullptr; /* base_line rows may change per step */
-  /* the action row of env (index into this step's n_rows rows) */
-  auto arow = [&](int env_i) -> size_t { return p.envs_per_row ? (size_t)((p.row_base + env_i) / p.envs_per_row) : (size_t)env_i; };
-  if (PLAIN && !last && tid < nb && !p.envs_per_row) { /* the next step's action rows of this block: into L2 while this step runs */
+  /* the action row of env (index into this step's rows) */
+  auto arow = [&](int env_i) -> size_t {
+    if constexpr (ROLL) return (size_t)(((uint32_t)p.row_base + (uint32_t)env_i) / (uint32_t)p.envs_per_row);
+    else return (size_t)env_i;
+  };
+  if (PLAIN && !ROLL && !last && tid < nb) { /* the next step's action rows of this block: into L2 while this step runs */
     asm volatile("prefetch.global.L2 [%0];" ::"l"(hdr_t + ((size_t)p.B + env0 + tid) * 4));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_t + ((size_t)p.B + env0 + tid) * W));
   }
@@ -309,8 +318,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
                  (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
   /* the hop-log ring and the uploaded detector of an env (both optional, global memory) */
   auto bind_aux = [&](Env<W, 1>& ee, int env_i) {
-    ee.logs = p.logs ? p.logs + (size_t)env_i * p.net.cfg.log_cap : nullptr;
-    ee.det = (p.det_slots && p.det_of_env[env_i] >= 0) ? p.det_slots + (size_t)p.det_of_env[env_i] * CYG_DET_WORDS : nullptr;
+    if constexpr (LOG) {
+      ee.logs = p.logs ? p.logs + (size_t)env_i * p.net.cfg.log_cap : nullptr;
+      ee.det = (p.det_slots && p.det_of_env[env_i] >= 0) ? p.det_slots + (size_t)p.det_of_env[env_i] * CYG_DET_WORDS : nullptr;
+    }
   };
   if (tid < nb) bind_aux(e, env);
   long long t_begin = 0;
@@ -400,7 +411,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             Env<W, 1> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
                             (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
             eb.resume_epoch();
-            if (kind == 1) eb.logs = p.logs ? p.logs + (size_t)env_b * p.net.cfg.log_cap : nullptr; /* the attack logs its hops */
+            if (LOG && kind == 1) eb.logs = p.logs ? p.logs + (size_t)env_b * p.net.cfg.log_cap : nullptr; /* the attack logs its hops */
             uint32_t act[4 + W];
             load_action(env_b, act);
             typename Env<W, 1>::Act a;
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             if (kind == 0) {
               Coop<W>::template flip<32>(eb, a, (int)(act[0] & 0xFFu), tcost, tdirty); /* flip keys only hold executed types 6 / 9 == the header's */
             } else if (kind == 1) {
-              Coop<W>::attack(eb, a);
+              Coop<W>::template attack<LOG>(eb, a);
             } else {
               const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[arow(env_b)] : p.net.cfg.base_line);
               Coop<W>::defender(eb, a, atype_b, tcost, tdirty);
@@ -451,8 +462,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       float raw, shaped;
       int32_t done;
       e.step_post(mode, cost, dirty, p.flags, &raw, &shaped, &done, p.pre_masks ? p.pre_masks + (size_t)env * 3 * W : nullptr);
-      if (raw_t) { raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done; }
-      if (p.ret_acc) p.ret_acc[(size_t)mode * p.B + env] += (double)raw;
+      if constexpr (ROLL) p.ret_acc[(size_t)mode * p.B + env] += (double)raw;
+      else { raw_t[env] = raw; shaped_t[env] = shaped; done_t[env] = done; }
     }
     if (pass == 0 && tid < nb) {
 #ifdef CYG_PHASE_TIMING
@@ -825,6 +836,7 @@ __global__ void cyg_observe_kernel(const __grid_constant__ ObsParams p) {
 struct WOps {
   cudaError_t (*set_smem_optin)(int max_optin);
   void (*step)(bool plain, int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p);
+  void (*rollout)(int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p);
   void (*import_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
   void (*export_state)(int blocks, int threads, cudaStream_t st, const ConvParams& p);
   void (*randomize)(int blocks, int threads, cudaStream_t st, const SimpleParams& p);
@@ -845,6 +857,10 @@ struct WImpl {
     if constexpr (KW <= CYG_MAX_W) {
       cudaError_t e = cudaFuncSetAttribute(cyg_step_kernel<KW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
       if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(cyg_step_kernel<KW, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(cyg_step_kernel<KW, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+      if (e != cudaSuccess) return e;
       return cudaFuncSetAttribute(cyg_step_kernel<KW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
     } else {
       return cudaFuncSetAttribute(cyg_step_generic_kernel<KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
@@ -852,11 +868,15 @@ struct WImpl {
   }
   static void step(bool plain, int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p) {
     if constexpr (KW <= CYG_MAX_W) {
-      if (plain) cyg_step_kernel<KW, true><<<blocks, threads, smem, st>>>(p);
+      if (plain && !p.logs) cyg_step_kernel<KW, true, false, false><<<blocks, threads, smem, st>>>(p);
+      else if (plain) cyg_step_kernel<KW, true><<<blocks, threads, smem, st>>>(p);
       else cyg_step_kernel<KW, false><<<blocks, threads, smem, st>>>(p);
     } else {
       cyg_step_generic_kernel<KW><<<blocks, threads, smem, st>>>(p);
     }
+  }
+  static void rollout(int blocks, int threads, size_t smem, cudaStream_t st, const StepParams& p) {
+    if constexpr (KW <= CYG_MAX_W) cyg_step_kernel<KW, true, true, false><<<blocks, threads, smem, st>>>(p);
   }
   static void import_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_import_kernel<KW><<<blocks, threads, 0, st>>>(p); }
   static void export_state(int blocks, int threads, cudaStream_t st, const ConvParams& p) { cyg_export_kernel<KW><<<blocks, threads, 0, st>>>(p); }
@@ -867,7 +887,7 @@ struct WImpl {
 };
 extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
   typedef WImpl<CYG_TU_W> I;
-  static const WOps ops = {I::set_smem_optin, I::step, I::import_state, I::export_state, I::randomize, I::rebuild, I::sample, I::observe};
+  static const WOps ops = {I::set_smem_optin, I::step, I::rollout, I::import_state, I::export_state, I::randomize, I::rebuild, I::sample, I::observe};
   return &ops;
 }
 #else /* ---- the C-ABI translation unit ---- */
@@ -1156,7 +1176,8 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
   if (!h || !a || !a->hdr || !a->mask || !a->returns) return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   if (h->W > CYG_MAX_W) return fail(CYG_E_INVAL, "cyg_rollout: networks of at most 128 device slots");
-  if (a->n_steps < 1 || a->n_rows < 1 || a->envs_per_row < 1 || a->row_base < 0) return fail(CYG_E_INVAL, "cyg_rollout: bad sizes");
+  if (h->net.cfg.log_cap > 0) return fail(CYG_E_INVAL, "cyg_rollout: handles with a hop-log ring (log_cap > 0) step through cyg_step");
+  if (a->n_steps < 1 || a->n_rows < 1 || a->envs_per_row < 1 || a->row_base < 0 || a->row_base + h->B > 0x7FFFFFFFll) return fail(CYG_E_INVAL, "cyg_rollout: bad sizes");
   if ((a->row_base + h->B - 1) / a->envs_per_row >= a->n_rows) return fail(CYG_E_INVAL, "cyg_rollout: an env's action row is beyond n_rows");
   if (step_flags & CYG_STEP_GROUPED) return fail(CYG_E_INVAL, "cyg_rollout: plain steps only");
   if (((uintptr_t)a->hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
@@ -1175,7 +1196,7 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
   int threads = ((2 * h->NB + 31) / 32) * 32;
   if (threads > CYG_MAX_BLOCK_THREADS) threads = CYG_MAX_BLOCK_THREADS;
   if (threads < h->NB) threads = ((h->NB + 31) / 32) * 32;
-  wops(h->W)->step(true, blocks, threads, h->smem_bytes, (cudaStream_t)stream, p);
+  wops(h->W)->rollout(blocks, threads, h->smem_bytes, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;
