@@ -379,6 +379,7 @@ def main():
         ms, Kh, launches = head["ms_single"], head["steps_single"], head["launches"]
     ms1, K1 = head["ms_single"], head["steps_single"]
     errs = int(max(int(s.error_flags().max().item()) for s in sets))
+    rec_words, n_env_sets_bytes = sets[0].S, a.sets * B * (sets[0].S + net.M) * 4
 
     # ---- e2e: the public host-buffer call VectorCyberDefenseEnv.step_host(): every step copies that step's actions
     #      from pinned host memory, launches the kernel, reads (raw, shaped, done) back and synchronises ----
@@ -529,6 +530,52 @@ def main():
                       "note": "a single 20-device env is launch- and PCIe-latency bound on a GPU; the reference's pure-Python step is "
                               "the faster one at this size -- the batched VectorCyberDefenseEnv is the product"}
 
+    # ================= C5: the payoff-matrix evaluation, sharded over the ranks + ONE all-reduce =================
+    c5 = None
+    if not a.no_legs and not a.obs:
+        from cygym_b200.payoff import Strategy, evaluate_payoff_matrix_batched
+        rng5 = np.random.default_rng(0)
+
+        def seq(mode, L):
+            out = []
+            for _ in range(L):
+                n = int(rng5.integers(1, 40))
+                devs = sorted(int(d) for d in rng5.choice(a.devices, size=n, replace=False))
+                at = int(rng5.choice([1, 2, 3, 4, 5, 6, 7, 9, 11, 12, 13])) if mode == 0 else int(rng5.integers(1, 3))
+                out.append((at, [int(rng5.integers(0, 2))], devs, int(rng5.integers(0, 7))))
+            return out
+
+        nS, N5, T5 = 32, 1024, 100
+        defs = [Strategy(baseline_name="No Defense"), Strategy(baseline_name="Preset"), Strategy(baseline_name="Nash")] + \
+               [Strategy(actions=seq(0, 5)) for _ in range(nS - 3)]
+        atts = [Strategy(baseline_name="No Attack"), Strategy(baseline_name="Nash")] + [Strategy(actions=seq(1, 4)) for _ in range(nS - 2)]
+        del sets, ring  # the evaluation allocates its own envs (1 M at N = 1)
+        torch.cuda.empty_cache()
+        # one untimed evaluation of the full size first: CUDA module load, allocator growth, NCCL's first all-reduce
+        evaluate_payoff_matrix_batched(net, defs, atts, N5, steps_per_episode=T5, seed=1, device=dev, rank=rank, world=world)
+        barrier()
+        samples = []
+        for _ in range(3):  # the evaluation is host-driven (a dozen launches and copies): three samples, the best one is reported
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            out5 = evaluate_payoff_matrix_batched(net, defs, atts, N5, steps_per_episode=T5, seed=1, device=dev, rank=rank, world=world)
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            t5 = torch.tensor([ev0.elapsed_time(ev1), wall * 1e3], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            samples.append((float(t5[0]), float(t5[1])))
+        t5 = min(samples)
+        c5 = {"what": f"C5: DOAR payoff-matrix evaluation, {nS}x{nS} strategy pairs x {N5} rollouts x {T5} turns (baseline names + fixed "
+                      "sequences), the (pair, rollout) index sharded over the ranks, per-pair action tables gathered inside ONE cyg_rollout "
+                      "launch per rank, then ONE all-reduce(SUM) of the [32, 32, 10] sums (NCCL)",
+              "n_gpus": world, "seconds": float(t5[0]) * 1e-3, "wall_seconds": float(t5[1]) * 1e-3, "samples_seconds": [x[0] * 1e-3 for x in samples],
+              "env_steps_per_s": nS * nS * N5 * T5 / (float(t5[0]) * 1e-3), "checksum": float(out5.sum().item()),
+              "collective": "all_reduce(SUM) of 10 240 float64 (NCCL)" if world > 1 else "none (1 rank)"}
+
     # ---- max over ranks ----
     t = torch.tensor([ms, e2e[0] if e2e else 0.0, e2e[4] if e2e else 0.0, ms1], dtype=torch.float64, device=dev)
     if world > 1:
@@ -557,24 +604,26 @@ def main():
             "ms_per_step": ms / Kh, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(a), "envs_per_gpu": B, "device_slots": a.devices, "edges": net.E,
-                       "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": sets[0].S * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
+                       "obs_mode": a.obs, "env_sets": a.sets, "record_bytes": rec_words * 4, "actions": "pre-generated ring of sample_action batches resident in HBM; defender 10 (detector training) -> no-op",
                        "randomized_ownership": bool(a.randomize), "steps_per_launch": F, "preheat_launches": max(PREHEAT, (Wm + F - 1) // F),
                        "fusion": (f"{F} plain steps per launch (step_many / cyg_step_multi): open-loop action batches resident in HBM, records stay in "
                                   "shared memory between the steps of a launch, so per-step HBM traffic is actions in + rewards out; "
                                   "single_step_launch below is the same workload at one launch per step") if F > 1 else "one launch per step",
-                       "l2_policy": f"rotating {a.sets} env sets ({a.sets * B * (sets[0].S + net.M) * 4 / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
+                       "l2_policy": f"rotating {a.sets} env sets ({n_env_sets_bytes / 1e6:.0f} MB of state > 126 MB L2) and {2 * a.ring} action batches",
                        "parallelism": f"env-sharded x{world}, no per-step collective", "error_flags": errs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic if F == 1 else traffic_f, "traffic_source": traffic_src if F == 1 else traffic_f_src,
                          "algorithmic_bytes_per_env_step": alg, "envs_per_launch": B,
                          "env_steps_per_launch": B * F, "launch_us": launch_s * 1e6, "peak_source": peak_src,
-                         "actual_bytes_per_env_step": (2 * sets[0].S * 4) / F + 4 * (4 + net.W) + 12,
+                         "actual_bytes_per_env_step": (2 * rec_words * 4) / F + 4 * (4 + net.W) + 12,
                          "note": ("algorithmic bytes are SURVEY 8(d)'s per-step figure x env-steps per launch; a fused launch moves less than that "
                                   "(state in/out once per launch), which 8(d) allows for") if F > 1 else None},
             "single_step_launch": {"value": world * B * K1 / (ms1 * 1e-3), "unit": UNIT, "launch_us": ms1 * 1e3 / K1, "steps": K1,
                                    "roofline_frac": alg * B / (ms1 * 1e-3 / K1) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src},
             "clocks": clocks, "gpu_launches": int(launches),
         }
+        if c5:
+            legs["c5"] = c5
         if legs:
             line["legs"] = legs
         if e2e:

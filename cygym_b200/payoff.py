@@ -120,22 +120,60 @@ def decode_actions(raw, mode, n_types, M, X, n_app, W):
     return hdr.contiguous(), _pack_mask(dev, W).contiguous()
 
 
-def _strategy_tables(def_strategies, att_strategies, T, M):
-    """Per-STRATEGY action rows of every turn (host, tiny): hdr [T, S, 4], mask [T, S, W], base_line code [T, S] (255 =
-    the strategy does not touch env.base_line on that turn), S = the side that moves on turn t."""
+def _strategy_rows(def_strategies, att_strategies, T, M):
+    """The distinct action rows of every strategy, packed once on the host, and which row each strategy plays on each
+    turn: per side (hdr rows [R, 4], mask rows [R, W], row index [T, S], base_line code [S] (255 = the strategy does not
+    touch env.base_line)).  A fixed sequence of L actions is L rows indexed by t % L."""
     from .vector_env import ActionBatch
     from . import _capi as K
-    hdr_s, mask_s, bl_s = [], [], []
-    for t in range(T):
-        mode = t & 1
-        decided = [(None, None) if st.actor is not None else st.decide(t) for st in (def_strategies if mode == 0 else att_strategies)]
-        for a, _ in decided:
-            if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
-                raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
-        h, m, _ = ActionBatch.pack([a for a, _ in decided], mode, M)
-        hdr_s.append(h.view(np.int32)); mask_s.append(m.view(np.int32))
-        bl_s.append(np.array([K.BASE_LINES.get(b, 4) if b is not None else 255 for _, b in decided], np.uint8))
-    return hdr_s, mask_s, bl_s
+    out = []
+    for mode, sts in ((0, def_strategies), (1, att_strategies)):
+        hs, ms, first, length, bls, n_rows = [], [], [], [], [], 0
+        for st in sts:
+            key = (mode, M)
+            cached = st.__dict__.setdefault("_packed_rows", {}).get(key)  # a strategy is evaluated again and again as the matrices grow
+            if cached is None:
+                if st.actor is not None:
+                    acts, bl = [None], 255
+                elif st.baseline_name is not None:
+                    acts, bl = [None], K.BASE_LINES.get(st.baseline_name, 4)
+                elif st.actions:
+                    acts, bl = list(st.actions), 255
+                else:
+                    acts, bl = [None], K.BASE_LINES["Nash"]
+                for a in acts:
+                    if a is not None and list(a[2]) != sorted(set(int(d) for d in a[2])):
+                        raise NotImplementedError("unsorted device_indices: use evaluate_payoff_matrix()")
+                h, m, _ = ActionBatch.pack(acts, mode, M)
+                cached = st._packed_rows[key] = (h.view(np.int32), m.view(np.int32), bl)
+            h, m, bl = cached
+            first.append(n_rows); length.append(len(h)); bls.append(bl)
+            n_rows += len(h)
+            hs.append(h); ms.append(m)
+        t = np.arange(T)[:, None]
+        ridx = np.asarray(first)[None, :] + t % np.asarray(length)[None, :]
+        out.append((np.concatenate(hs), np.concatenate(ms), ridx.astype(np.int64), np.asarray(bls, np.uint8)))
+    return out
+
+
+_ENV_CACHE = {}
+
+
+def _cached_env(network, nloc, lo, device, seed, xcap):
+    """The evaluation's env batch, kept between calls (a Double-Oracle run evaluates the same network again and again:
+    build_payoff_matrices, do_agent.py:1666-1870): re-creating 1 M envs costs ~15 ms of allocation and table upload per
+    call, a reset() of the kept ones ~2 ms."""
+    from .vector_env import VectorCyberDefenseEnv
+    key = (id(network), int(nloc), int(lo), str(device), int(seed), int(xcap))
+    env = _ENV_CACHE.get(key)
+    if env is None:
+        for k in list(_ENV_CACHE):
+            _ENV_CACHE.pop(k).close()
+        env = _ENV_CACHE[key] = VectorCyberDefenseEnv(network, nloc, device=device, seed=seed, env_id0=lo, xcap=xcap)
+    else:
+        env.reset()
+        env.set_base_line_per_env(None)
+    return env
 
 
 def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_rollouts, steps_per_episode=100, seed=0,
@@ -163,7 +201,7 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
     sums = torch.zeros(P, len(COLUMNS), dtype=torch.float64, device=device)
     if nloc > 0:
         M, W = network.M, network.W
-        env = VectorCyberDefenseEnv(network, nloc, device=device, seed=seed, env_id0=lo, xcap=xcap)
+        env = _cached_env(network, nloc, lo, device, seed, xcap)
         pair_of_env = (torch.arange(lo, hi, device=device) // n_rollouts)
         i_of_pair = np.arange(P) // na
         j_of_pair = np.arange(P) % na
@@ -171,20 +209,31 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
         s = env.scalars
         for slot in (K.S_STEP, K.S_DEF_STEP, K.S_ATT_STEP, K.S_WORK, K.S_CKPT, K.S_DEFCOST, K.S_CLEANCOST, K.S_REVERT, K.S_SCAN):
             s[:, slot] = 0
-        hdr_s, mask_s, bl_s = _strategy_tables(def_strategies, att_strategies, T, M)
-        # per-pair tables: the moving side's row of every turn, and the base_line each pair's env carries on that turn
-        # (a strategy that sets no base_line leaves it as the other player's last baseline left it, do_agent.py:716-719)
-        hdr_p = np.stack([hdr_s[t][i_of_pair if t % 2 == 0 else j_of_pair] for t in range(T)])
-        mask_p = np.stack([mask_s[t][i_of_pair if t % 2 == 0 else j_of_pair] for t in range(T)])
-        bl_p = np.zeros((T, P), np.uint8)
-        cur = np.full(P, K.BASE_LINES["Nash"], np.uint8)
-        for t in range(T):
-            nb = bl_s[t][i_of_pair if t % 2 == 0 else j_of_pair]
-            cur = np.where(nb == 255, cur, nb)
-            bl_p[t] = cur
-        hdr_d = torch.from_numpy(hdr_p).to(device).contiguous()
-        mask_d = torch.from_numpy(mask_p).to(device).contiguous()
-        bl_d = torch.from_numpy(bl_p).to(device).contiguous()
+        # per-pair tables, assembled on the device from the strategies' packed rows: the moving side's row of every turn,
+        # and the base_line each pair's env carries on that turn (a strategy that sets no base_line leaves it as the
+        # other player's last baseline left it, do_agent.py:716-719)
+        sides = _strategy_rows(def_strategies, att_strategies, T, M)
+        tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        of_pair = (tt(i_of_pair), tt(j_of_pair))
+        hdr_side = [tt(h)[tt(r)][:, of_pair[m_]] for m_, (h, _, r, _) in enumerate(sides)]    # [T, P, 4] per side
+        mask_side = [tt(m)[tt(r)][:, of_pair[m_]] for m_, (_, m, r, _) in enumerate(sides)]  # [T, P, W]
+        even = (torch.arange(T, device=device) % 2 == 0)[:, None, None]
+        hdr_d = torch.where(even, hdr_side[0], hdr_side[1]).contiguous()
+        mask_d = torch.where(even, mask_side[0], mask_side[1]).contiguous()
+        bl_def, bl_att = tt(sides[0][3])[of_pair[0]], tt(sides[1][3])[of_pair[1]]                # [P] code each side sets (255: none)
+        nash = torch.full((P,), K.BASE_LINES["Nash"], dtype=torch.uint8, device=device)
+        # base_line after the defender's turn / after the attacker's turn, in the steady state of the alternation
+        after_def0 = torch.where(bl_def == 255, nash, bl_def)                      # turn 0: nothing was set before
+        after_att = torch.where(bl_att == 255, after_def0, bl_att)                 # turn 1
+        after_def = torch.where(bl_def == 255, after_att, bl_def)                  # turns 2, 4, ...: the attacker's value may persist
+        after_att2 = torch.where(bl_att == 255, after_def, bl_att)                 # turns 3, 5, ...
+        bl_d = torch.empty(T, P, dtype=torch.uint8, device=device)
+        bl_d[0::2] = after_def
+        bl_d[1::2] = after_att2
+        bl_d[0] = after_def0
+        if T > 1:
+            bl_d[1] = after_att
+        bl_d = bl_d.contiguous()
         ret = torch.zeros(2, nloc, dtype=torch.float64, device=device)
         any_nn = any(st.actor is not None for st in list(def_strategies) + list(att_strategies))
         if not any_nn and W <= 4:
@@ -220,7 +269,6 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
                             info["Scan_count"].double(), info["defensive_cost"].double(), info["checkpoint_count"].double(),
                             info["revert_count"].double(), info["Edges Blocked"].double(), info["Edges Added"].double()], dim=1)
         sums.index_add_(0, pair_of_env, cols)
-        env.close()
     sums = sums.view(nd, na, len(COLUMNS))
     if not reduce:
         return sums
