@@ -346,6 +346,33 @@ def main():
             if F == 1:
                 out["launches"] = l1
         out["steps_single"] = K1
+        if not flushed and not obs and n_sets > 1:
+            # the same one-launch-per-step workload with every env set on its OWN stream (each set still steps in order:
+            # closed loop per set): a launch's CTAs move onto SMs as the previous launch's CTAs leave them, so the
+            # slowest-CTA tail and the load / store phases of one set overlap the compute of another
+            streams = [torch.cuda.Stream(dev) for _ in range(n_sets)]
+            cur = torch.cuda.current_stream(dev)
+
+            def one_step_streams(i):
+                s_i = i % n_sets
+                streams[s_i].wait_stream(cur) if i < n_sets else None
+                with torch.cuda.stream(streams[s_i]):
+                    one_step(i)
+
+            def run(n):
+                for i in range(n):
+                    one_step_streams(i)
+                for st_ in streams:
+                    cur.wait_stream(st_)
+
+            run(max(Wm, PREHEAT))
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run(K1)
+            e1.record()
+            barrier()
+            out["ms_single_streams"] = e0.elapsed_time(e1)
         return out
 
     def leg_record(net, nB, r, fuse, obs=False, extra=None):
@@ -357,6 +384,11 @@ def main():
                           "roofline": {"bound": "hbm", "achieved": alg * nB / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": alg * nB / (us * 1e-6) / 1e9 / peak}}
         us1 = r["ms_single"] * 1e3 / r["steps_single"]
+        if "ms_single_streams" in r:
+            uss = r["ms_single_streams"] * 1e3 / r["steps_single"]
+            d["single_on_streams"] = {"us_per_step": uss, "value": world * nB / (uss * 1e-6), "unit": UNIT, "streams": "one per env set",
+                                      "roofline": {"bound": "hbm", "achieved": alg * nB / (uss * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                                   "frac": alg * nB / (uss * 1e-6) / 1e9 / peak}}
         d["single"] = {"launch_us": us1, "value": world * nB / (us1 * 1e-6), "unit": UNIT,
                        "roofline": {"bound": "hbm", "achieved": alg * nB / (us1 * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": alg * nB / (us1 * 1e-6) / 1e9 / peak}}
@@ -622,6 +654,12 @@ def main():
                                    "roofline_frac": alg * B / (ms1 * 1e-3 / K1) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src},
             "clocks": clocks, "gpu_launches": int(launches),
         }
+        if "ms_single_streams" in head:
+            uss = head["ms_single_streams"] * 1e3 / K1
+            line["single_step_launch"]["on_streams"] = {
+                "us_per_step": uss, "value": world * B * 1e6 / uss, "unit": UNIT, "roofline_frac": alg * B / (uss * 1e-6) / 1e9 / peak,
+                "how": f"the same one-launch-per-step workload with each of the {a.sets} env sets on its own stream (every set steps in order); "
+                       "launch_us above stays the duration of ONE launch on one stream"}
         if c5:
             legs["c5"] = c5
         if legs:
