@@ -79,11 +79,11 @@ class CygStepOut(C.Structure):
 class CygRolloutArgs(C.Structure):
     """struct cyg_rollout_args"""
     _fields_ = [("hdr", C.c_void_p), ("mask", C.c_void_p), ("base_line", C.c_void_p), ("n_steps", C.c_int32), ("n_rows", C.c_int32),
-                ("row_base", C.c_int64), ("envs_per_row", C.c_int32), ("reserved", C.c_int32), ("returns", C.c_void_p)]
+                ("row_base", C.c_int64), ("envs_per_row", C.c_int32), ("reserved", C.c_int32), ("returns", C.c_void_p), ("block_order", C.c_void_p)]
 
 
 EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_set_base_line_per_env_steps", "cyg_internal_words",
-           "cyg_bind", "cyg_set_detectors", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
+           "cyg_bind", "cyg_set_detectors", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_block_envs", "cyg_set_env_id_stride", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
            "cyg_observe", "cyg_group_actions", "cyg_launch_count", "cyg_set_debug_cycles"]
 
 
@@ -185,6 +185,8 @@ def lib():
         L.cyg_step.argtypes = [C.c_void_p, C.POINTER(CygActions), C.c_uint32, C.POINTER(CygStepOut), C.c_void_p]
         L.cyg_step_multi.argtypes = [C.c_void_p, C.POINTER(CygActions), C.c_int32, C.c_uint32, C.POINTER(CygStepOut), C.c_void_p]
         L.cyg_rollout.argtypes = [C.c_void_p, C.POINTER(CygRolloutArgs), C.c_uint32, C.c_void_p]
+        L.cyg_set_env_id_stride.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.cyg_block_envs.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.cyg_randomize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_rebuild_graph_cache.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_sample_actions.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -93,6 +93,8 @@ struct StepParams {
    * the n_rows rows of a step (envs_per_row == 0: one row per env, n_rows == B) -- and the raw rewards are summed per env */
   long long row_base;
   int envs_per_row, n_rows;
+  int id_run, id_stride; /* cyg_set_env_id_stride (ROLL only): see strided_index() */
+  const int32_t* block_order; /* optional (ROLL only): CTA b steps the envs [block_order[b] * block_envs, +block_envs) */
   double* ret_acc;      /* optional [2][B]: += raw reward, row 0 defender turns, row 1 attacker turns */
   int T;                /* plain steps fused into this launch (cyg_step_multi): hdr / mask hold T consecutive batches,
                            raw / shaped / done T consecutive [B] rows; the records stay in shared memory in between */
@@ -110,6 +112,12 @@ struct StepParams {
                                     kernel (4 fused steps / one launch per step): 896 threads (72 registers, 88 B of spills)
                                     46.4 / 56.6 us, 768: 44.1 / 54.7, 640: 42.5 / 53.7, 576: 43.2 / 55.8, 512: 44.0 / 56.8 */
 #endif
+
+/* cyg_set_env_id_stride: env index (env id minus env_id0) of a slot -- runs of `run` consecutive ids, `stride` ids apart */
+__host__ __device__ __forceinline__ uint32_t strided_index(uint32_t slot, uint32_t run, uint32_t stride) {
+  const uint32_t c = slot / run;
+  return c * stride + (slot - c * run);
+}
 
 /* one record from shared to global memory by one warp: 4 bytes per lane, 128 words per round, predicated tail */
 __device__ __forceinline__ void copy_record(uint32_t* dst, const uint32_t* src, int S, int lane) {
@@ -210,7 +218,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   const int NB = p.block_envs, NT = blockDim.x, tid = threadIdx.x; /* NB envs, NT >= NB threads */
   CYG_CTA_MARK(0);
   const int S = p.net.S, M = p.net.M;
-  const int env0 = blockIdx.x * NB;
+  int blk_i = (int)blockIdx.x;
+  if constexpr (ROLL) { if (p.block_order) blk_i = p.block_order[blockIdx.x]; }
+  const int env0 = blk_i * NB;
   const int nb = min(NB, p.B - env0);
   const SmemPlan sp = smem_plan(p.net.hot_words, S, NB);
   uint32_t* s_tab = (uint32_t*)(smem + sp.off_tables);
@@ -244,8 +254,15 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   int32_t* done_t = p.done + (size_t)t * p.B;
   const uint8_t* bl_t = p.bl_env ? p.bl_env + (size_t)t * p.bl_stride : nullptr; /* base_line rows may change per step */
   /* the action row of env (index into this step's rows) */
+  /* env id (draw streams, action row) of slot env_i minus env_id0: the slot itself unless the rollout handle strides */
+  auto idx_of = [&](int env_i) -> uint32_t {
+    if constexpr (ROLL) {
+      if (p.id_run > 0) return strided_index((uint32_t)env_i, (uint32_t)p.id_run, (uint32_t)p.id_stride);
+    }
+    return (uint32_t)env_i;
+  };
   auto arow = [&](int env_i) -> size_t {
-    if constexpr (ROLL) return (size_t)(((uint32_t)p.row_base + (uint32_t)env_i) / (uint32_t)p.envs_per_row);
+    if constexpr (ROLL) return (size_t)(((uint32_t)p.row_base + idx_of(env_i)) / (uint32_t)p.envs_per_row);
     else return (size_t)env_i;
   };
   if (PLAIN && !ROLL && !last && tid < nb) { /* the next step's action rows of this block: into L2 while this step runs */
@@ -261,9 +278,10 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   int key = 0;
   if (tid < nb) {
     if (!grouped) {
-      const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + arow(env0 + tid) * 4);
+      const size_t r0 = arow(env0 + tid);
+      const uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + r0 * 4);
       const uint32_t h0 = hv.x;
-      const int blk = bl_t ? (int)bl_t[arow(env0 + tid)] : p.net.cfg.base_line;
+      const int blk = bl_t ? (int)bl_t[r0] : p.net.cfg.base_line;
       const int xt = Env<W, 1>::exec_type(p.net.cfg, h0, blk) & 15;
       key = (int)(((h0 >> 8) & 1u) << 4) | xt;
       if (PLAIN && (key == 6 || key == 9)) { /* longest-processing-time first: 8 buckets of 16 listed devices */
@@ -315,7 +333,8 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   bool deferred = false;
   const int el = tid < nb ? (int)s_perm[tid] : 0, env = env0 + el;
   Env<W, 1> e(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap,
-                 (uint32_t)(p.env_id0 + env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
+                 (uint32_t)p.env_id0 + idx_of(env), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4));
+  const size_t my_row = arow(env); /* this step's action row of the env this thread owns */
   /* the hop-log ring and the uploaded detector of an env (both optional, global memory) */
   auto bind_aux = [&](Env<W, 1>& ee, int env_i) {
     if constexpr (LOG) {
@@ -348,13 +367,13 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
       const uint16_t* ord = (!PLAIN && p.order) ? p.order + (size_t)env * p.order_stride : nullptr;
       int atype = 0;
       if (tid < nb) {
-        uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + arow(env) * 4);
+        uint4 hv = *reinterpret_cast<const uint4*>(hdr_t + my_row * 4);
         act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-        for (int w = 0; w < W; w++) act[4 + w] = mask_t[arow(env) * W + w];
+        for (int w = 0; w < W; w++) act[4 + w] = mask_t[my_row * W + w];
         t_begin = p.dbg_cycles ? clock64() : 0;
         mode = (int)((act[0] >> 8) & 1u);
-        if (bl_t) e.bl = (int)bl_t[arow(env)];
+        if (bl_t) e.bl = (int)bl_t[my_row];
         atype = e.step_pre(act, p.flags);
         deferred = coop_ok && Coop<W>::is_heavy(e, mode, atype) && !(mode == CYG_MODE_ATTACKER && e.bl == CYG_BL_NO_ATTACK);
       }
@@ -381,11 +400,11 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   CYG_CTA_MARK(3);
         if (lane == 0) while (atomicAdd(&s_cnt[CYG_NKEYS + 6], 0u) < (uint32_t)((nb + 31) >> 5)) __nanosleep(32);
         __syncwarp();
-        auto load_action = [&](int env_b, uint32_t* act) {
-          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hdr_t + arow(env_b) * 4)); /* phase A read these lines: L1 */
+        auto load_action = [&](size_t row_b, uint32_t* act) {
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hdr_t + row_b * 4)); /* phase A read these lines: L1 */
           act[0] = hv.x; act[1] = hv.y; act[2] = hv.z; act[3] = hv.w;
 #pragma unroll
-          for (int w = 0; w < W; w++) act[4 + w] = __ldg(mask_t + arow(env_b) * W + w);
+          for (int w = 0; w < W; w++) act[4 + w] = __ldg(mask_t + row_b * W + w);
         };
         /* B1: block / unblock (keys 6, 9; the longest lists first), B2: attacker exploit + lateral movement (key 16|1),
          * B3: clean / revert / upgrade (keys 1, 3, 4).  One env per warp; perm[] holds each kind as a contiguous run. */
@@ -409,11 +428,12 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             const int el_b = s_perm[ppos];
             const int env_b = env0 + el_b;
             Env<W, 1> eb(&p.net, nullptr, p.ckpt + (size_t)env_b * M, p.xtra + (size_t)env_b * p.net.cfg.xcap,
-                            (uint32_t)(p.env_id0 + env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+                            (uint32_t)p.env_id0 + idx_of(env_b), (uint32_t)(sp.off_recs / 4) + (uint32_t)(el_b * S), (uint32_t)(sp.off_tables / 4));
+            const size_t row_b = arow(env_b);
             eb.resume_epoch();
             if (LOG && kind == 1) eb.logs = p.logs ? p.logs + (size_t)env_b * p.net.cfg.log_cap : nullptr; /* the attack logs its hops */
             uint32_t act[4 + W];
-            load_action(env_b, act);
+            load_action(row_b, act);
             typename Env<W, 1>::Act a;
             Env<W, 1>::decode(act, act + 4, nullptr, a);
             double tcost = 0.0;
@@ -425,7 +445,7 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
             } else if (kind == 1) {
               Coop<W>::template attack<LOG>(eb, a);
             } else {
-              const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[arow(env_b)] : p.net.cfg.base_line);
+              const int atype_b = Env<W, 1>::exec_type(p.net.cfg, act[0], bl_t ? (int)bl_t[row_b] : p.net.cfg.base_line);
               Coop<W>::defender(eb, a, atype_b, tcost, tdirty);
             }
             if (lane == 0) {
@@ -447,9 +467,9 @@ __global__ void __launch_bounds__(CYG_MAX_BLOCK_THREADS, 1) cyg_step_kernel(cons
   CYG_CTA_MARK(4);
         /* ---- phase C, thread per env again: the rest of the step for the envs phase B handled ---- */
         if (deferred) {
-          e = Env<W, 1>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env),
+          e = Env<W, 1>(&p.net, nullptr, p.ckpt + (size_t)env * M, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)p.env_id0 + idx_of(env),
                            (uint32_t)(sp.off_recs / 4) + (uint32_t)(el * S), (uint32_t)(sp.off_tables / 4)); /* nothing of it stays live across phase B */
-          if (bl_t) e.bl = (int)bl_t[arow(env)];
+          if (bl_t) e.bl = (int)bl_t[my_row];
           bind_aux(e, env);
           e.resume_epoch();
           cost = (double)s_out[el];
@@ -613,6 +633,10 @@ struct SimpleParams {
   int B, env_id0, mode;
   uint16_t* order;  /* optional [B][order_stride]: device_indices in draw order (cyg_sample_actions_ordered) */
   int order_stride;
+  int id_run, id_stride; /* cyg_set_env_id_stride */
+  __device__ __forceinline__ uint32_t env_id(int slot) const {
+    return (uint32_t)env_id0 + (id_run > 0 ? strided_index((uint32_t)slot, (uint32_t)id_run, (uint32_t)id_stride) : (uint32_t)slot);
+  }
 };
 
 template <int W>
@@ -620,7 +644,7 @@ __global__ void cyg_randomize_kernel(const __grid_constant__ SimpleParams p) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.B) return;
   if (p.env_mask && !p.env_mask[env]) return;
-  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, p.env_id(env));
   e.randomize();
 }
 
@@ -631,7 +655,7 @@ __global__ void cyg_rebuild_kernel(const __grid_constant__ SimpleParams p) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= p.B) return;
   if (p.env_mask && !p.env_mask[env]) return;
-  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, p.recs + (size_t)env * p.net.S, nullptr, p.xtra + (size_t)env * p.net.cfg.xcap, p.env_id(env));
   e.rebuild_cache();
 }
 
@@ -642,7 +666,7 @@ __global__ void cyg_sample_kernel(const __grid_constant__ SimpleParams p) {
   uint32_t rec[CYG_NSCAL];
   uint32_t* g = p.recs + (size_t)env * p.net.S;
   for (int i = 0; i < CYG_NSCAL; i++) rec[i] = g[i];
-  Env<W> e(&p.net, rec, nullptr, nullptr, (uint32_t)(p.env_id0 + env));
+  Env<W> e(&p.net, rec, nullptr, nullptr, p.env_id(env));
   uint32_t h[4], m[W];
   e.sample_action(p.mode, h, m, p.order ? p.order + (size_t)env * p.order_stride : nullptr);
   g[CYG_S_EPOCH] = rec[CYG_S_EPOCH];
@@ -929,6 +953,7 @@ struct cyg_env_s {
   const int32_t* det_of_env;
   const uint8_t* bl_env;
   int bl_rows;       /* rows of [B] codes behind bl_env (cyg_set_base_line_per_env_steps; 1 otherwise) */
+  int id_run, id_stride; /* cyg_set_env_id_stride (0: env id = env_id0 + slot) */
   size_t smem_bytes;
   int64_t launches;
 };
@@ -1010,7 +1035,7 @@ int cyg_create(cyg_handle* out, const cyg_config* cfg, const cyg_network* host_n
   if (!h) return fail(CYG_E_NOMEM, "out of host memory");
   std::string err = build_tables(*cfg, *host_net, h->blob);
   if (!err.empty()) { delete h; return fail(CYG_E_INVAL, err); }
-  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr; h->bl_rows = 1;
+  h->B = B; h->env_id0 = env_id0; h->device = device; h->state = nullptr; h->launches = 0; h->dbg_cycles = nullptr; h->bl_env = nullptr; h->bl_rows = 1; h->id_run = 0; h->id_stride = 0;
   h->det_slots = nullptr; h->det_of_env = nullptr;
   h->W = h->blob.net.W;
   DeviceGuard g(device);
@@ -1044,6 +1069,21 @@ int cyg_destroy(cyg_handle h) {
 int cyg_set_base_line(cyg_handle h, int32_t base_line) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   h->net.cfg.base_line = base_line;
+  return CYG_OK;
+}
+
+int cyg_block_envs(cyg_handle h, int32_t* block_envs) {
+  if (!h || !block_envs) return fail(CYG_E_INVAL, "null argument");
+  *block_envs = h->NB;
+  return CYG_OK;
+}
+
+int cyg_set_env_id_stride(cyg_handle h, int32_t run, int32_t stride) {
+  if (!h) return fail(CYG_E_INVAL, "null handle");
+  if (run <= 0) { h->id_run = 0; h->id_stride = 0; return CYG_OK; }
+  if (stride < run || h->B % run != 0) return fail(CYG_E_INVAL, "cyg_set_env_id_stride: run must divide B and stride >= run");
+  if ((int64_t)(h->B / run - 1) * stride + run - 1 + h->env_id0 > 0x7FFFFFFFll) return fail(CYG_E_INVAL, "cyg_set_env_id_stride: env ids beyond 2^31");
+  h->id_run = run; h->id_stride = stride;
   return CYG_OK;
 }
 
@@ -1133,6 +1173,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   if (!h || !a || !out || !a->hdr || !a->mask || !out->raw_reward || !out->shaped_reward || !out->done)
     return fail(CYG_E_INVAL, "null argument");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
+  if (h->id_run > 0) return fail(CYG_E_INVAL, "strided env ids (cyg_set_env_id_stride): cyg_rollout only");
   const bool grouped = (step_flags & CYG_STEP_GROUPED) != 0;
   if (a->n_groups < 1 || (!grouped && a->n_groups != 1)) return fail(CYG_E_INVAL, "n_groups must be 1 unless CYG_STEP_GROUPED");
   if (a->order && a->order_stride < 1) return fail(CYG_E_INVAL, "order_stride must be >= 1 with an order array");
@@ -1149,7 +1190,7 @@ static int step_impl(cyg_handle h, const cyg_actions* a, int n_steps, uint32_t s
   p.obs_mode = out->obs ? out->obs_mode : 0;
   p.flags = step_flags;
   p.T = n_steps;
-  p.row_base = 0; p.envs_per_row = 0; p.n_rows = h->B; p.ret_acc = nullptr;
+  p.row_base = 0; p.envs_per_row = 0; p.n_rows = h->B; p.ret_acc = nullptr; p.id_run = 0; p.id_stride = 0; p.block_order = nullptr;
   p.logs = logs_of(h); p.det_slots = h->det_slots; p.det_of_env = h->det_of_env;
   p.block_envs = h->NB;
   const bool plain = !(step_flags & CYG_STEP_GROUPED) && a->order == nullptr; /* the hot form: see cyg_step_kernel */
@@ -1178,7 +1219,8 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
   if (h->W > CYG_MAX_W) return fail(CYG_E_INVAL, "cyg_rollout: networks of at most 128 device slots");
   if (h->net.cfg.log_cap > 0) return fail(CYG_E_INVAL, "cyg_rollout: handles with a hop-log ring (log_cap > 0) step through cyg_step");
   if (a->n_steps < 1 || a->n_rows < 1 || a->envs_per_row < 1 || a->row_base < 0 || a->row_base + h->B > 0x7FFFFFFFll) return fail(CYG_E_INVAL, "cyg_rollout: bad sizes");
-  if ((a->row_base + h->B - 1) / a->envs_per_row >= a->n_rows) return fail(CYG_E_INVAL, "cyg_rollout: an env's action row is beyond n_rows");
+  const int64_t last_idx = h->id_run > 0 ? (int64_t)strided_index((uint32_t)(h->B - 1), (uint32_t)h->id_run, (uint32_t)h->id_stride) : (int64_t)h->B - 1;
+  if (a->row_base + last_idx > 0x7FFFFFFFll || (a->row_base + last_idx) / a->envs_per_row >= a->n_rows) return fail(CYG_E_INVAL, "cyg_rollout: an env's action row is beyond n_rows");
   if (step_flags & CYG_STEP_GROUPED) return fail(CYG_E_INVAL, "cyg_rollout: plain steps only");
   if (((uintptr_t)a->hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
   DeviceGuard g(h->device);
@@ -1190,6 +1232,7 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
   p.bl_env = a->base_line; p.bl_stride = a->base_line ? a->n_rows : 0;
   p.B = h->B; p.env_id0 = h->env_id0; p.G = 1; p.order_stride = 0; p.obs_mode = 0; p.flags = step_flags; p.T = a->n_steps;
   p.row_base = a->row_base; p.envs_per_row = a->envs_per_row; p.n_rows = a->n_rows; p.ret_acc = a->returns;
+  p.id_run = h->id_run; p.id_stride = h->id_stride; p.block_order = a->block_order;
   p.logs = logs_of(h); p.det_slots = h->det_slots; p.det_of_env = h->det_of_env;
   p.block_envs = h->NB;
   int blocks = (h->B + h->NB - 1) / h->NB;
@@ -1206,7 +1249,7 @@ int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream) {
   if (!h) return fail(CYG_E_INVAL, "null handle");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0};
+  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0, h->id_run, h->id_stride};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->randomize(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
@@ -1218,7 +1261,7 @@ int cyg_rebuild_graph_cache(cyg_handle h, const uint8_t* env_mask, void* stream)
   if (!h) return fail(CYG_E_INVAL, "null handle");
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0};
+  SimpleParams p = {h->net, h->state, xtra_of(h), env_mask, nullptr, nullptr, h->B, h->env_id0, 0, nullptr, 0, h->id_run, h->id_stride};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->rebuild(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
@@ -1237,7 +1280,7 @@ int cyg_sample_actions_ordered(cyg_handle h, int32_t mode, uint32_t* hdr, uint32
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   if (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER) return fail(CYG_E_INVAL, "mode must be 0 or 1");
   DeviceGuard g(h->device);
-  SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode, order, order_stride};
+  SimpleParams p = {h->net, h->state, xtra_of(h), nullptr, hdr, mask, h->B, h->env_id0, mode, order, order_stride, h->id_run, h->id_stride};
   int threads = 128, blocks = (h->B + threads - 1) / threads;
   wops(h->W)->sample(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;

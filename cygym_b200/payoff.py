@@ -176,11 +176,48 @@ def _cached_env(network, nloc, lo, device, seed, xcap):
     return env
 
 
+# rough SM cycles per env of one turn by executed action type (profiles/type_cycles.py: warp-per-env tasks shared by
+# the 20 warps of a CTA, thread-per-env types by 14 warps of 32 lanes); only the ORDER of the blocks depends on them
+_DEF_PER_DEVICE = {6: 11.0, 9: 9.0, 1: 3.75, 3: 2.75, 4: 2.25}
+_TURN_BASE, _ATTACK_COST, _BASELINE_COST = 25.0, 185.0, 60.0
+
+
+def _block_order(env, sides, i_of_pair, j_of_pair, pair_of_env, T):
+    """CTA indices of the rollout launch, most expensive first (longest processing time first): the blocks of a launch
+    hold one to four strategy pairs each and the pairs differ by an order of magnitude in cost (a sequence of block /
+    unblock actions over 40 devices against the no-op), so the launch used to end with whichever expensive blocks
+    started last.  The estimate needs no measurement: action types and list lengths of the strategies' rows."""
+    import torch
+    from . import _capi as K
+    cost_side = []
+    for mode, (h, _, ridx, bls) in enumerate(sides):
+        t = (h[:, 0] & 0xFF).astype(np.int64)
+        n = (h[:, 2] & 0xFFFF).astype(np.float64)
+        if mode == 0:
+            c = _TURN_BASE + np.array([_DEF_PER_DEVICE.get(int(x), 0.0) for x in t]) * n
+        else:
+            c = _TURN_BASE + np.where(t == 1, _ATTACK_COST, 0.0)
+        c = c + np.where(t == K.ATYPE_NONE, _BASELINE_COST, 0.0)  # a baseline acts by itself (volt:836-853)
+        turns = np.arange(mode, T, 2)
+        cs = c[ridx[turns]].mean(axis=0) if len(turns) else np.zeros(ridx.shape[1])  # [n strategies]
+        idle = np.isin(bls, [K.BASE_LINES["No Defense"], K.BASE_LINES["No Attack"]])
+        cost_side.append(np.where(idle, _TURN_BASE, cs))
+    pair_cost = torch.from_numpy(cost_side[0][i_of_pair] + cost_side[1][j_of_pair]).to(pair_of_env.device)
+    nb = env.block_envs()
+    n_blocks = (env.B + nb - 1) // nb
+    per_slot = pair_cost[pair_of_env]
+    pad = n_blocks * nb - env.B
+    if pad:
+        per_slot = torch.cat([per_slot, per_slot.new_zeros(pad)])
+    return torch.argsort(per_slot.view(n_blocks, nb).sum(1), descending=True, stable=True).to(torch.int32)
+
+
 def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_rollouts, steps_per_episode=100, seed=0,
                                    device="cuda:0", rank=0, world=1, xcap=16, group=None, reduce=True, steps_per_launch=None):
     """Same result as evaluate_payoff_matrix(), with ALL (pair, rollout) combinations in one batch: the flattened
-    index g = pair * n_rollouts + rollout is split contiguously over the ranks (env id == g, so the draw streams do not
-    depend on the number of ranks).
+    index g = pair * n_rollouts + rollout is split over the ranks (env id == g, so the draw streams do not depend on the
+    number of ranks): every rank takes the same slice of rollouts of every pair when n_rollouts divides evenly (balanced
+    work), a contiguous slice of g otherwise.
 
     Strategies that need no observation (baseline names, fixed sequences, the no-op) become per-PAIR tables of action
     rows and base_line codes for all turns, uploaded ONCE and gathered inside the kernel (cyg_rollout): the whole
@@ -196,13 +233,23 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
     from . import _capi as K
     nd, na = len(def_strategies), len(att_strategies)
     P, T = nd * na, int(steps_per_episode)
-    lo, hi = shard_range(P * n_rollouts, rank, world)
-    nloc = hi - lo
+    M, W = network.M, network.W
+    any_nn = any(st.actor is not None for st in list(def_strategies) + list(att_strategies))
+    # Sharding.  Table-driven rollouts with n_rollouts divisible by the ranks: rank r takes rollouts [r * run, (r + 1) *
+    # run) of EVERY pair (strided env ids, cyg_set_env_id_stride) -- every rank steps the same mix of cheap and expensive
+    # pairs.  Otherwise a contiguous slice of the flattened (pair, rollout) index.  Env ids, hence all sums, are the same.
+    strided = world > 1 and not any_nn and W <= 4 and n_rollouts % world == 0
+    if strided:
+        run = n_rollouts // world
+        lo, nloc = rank * run, P * run
+    else:
+        lo, hi = shard_range(P * n_rollouts, rank, world)
+        nloc = hi - lo
     sums = torch.zeros(P, len(COLUMNS), dtype=torch.float64, device=device)
     if nloc > 0:
-        M, W = network.M, network.W
         env = _cached_env(network, nloc, lo, device, seed, xcap)
-        pair_of_env = (torch.arange(lo, hi, device=device) // n_rollouts)
+        env.set_env_id_stride(run if strided else 0, n_rollouts)
+        pair_of_env = (lo + env.env_index_of_slot()) // n_rollouts
         i_of_pair = np.arange(P) // na
         j_of_pair = np.arange(P) % na
         env.randomize_compromise_and_ownership()
@@ -235,12 +282,12 @@ def evaluate_payoff_matrix_batched(network, def_strategies, att_strategies, n_ro
             bl_d[1] = after_att
         bl_d = bl_d.contiguous()
         ret = torch.zeros(2, nloc, dtype=torch.float64, device=device)
-        any_nn = any(st.actor is not None for st in list(def_strategies) + list(att_strategies))
         if not any_nn and W <= 4:
             spl = T if not steps_per_launch else max(1, int(steps_per_launch))
+            order = _block_order(env, sides, i_of_pair, j_of_pair, pair_of_env, T)
             for t0 in range(0, T, spl):
                 t1 = min(T, t0 + spl)
-                env.rollout(hdr_d[t0:t1], mask_d[t0:t1], bl_d[t0:t1], n_rollouts, lo, returns=ret)  # the mode of a turn is in its headers
+                env.rollout(hdr_d[t0:t1], mask_d[t0:t1], bl_d[t0:t1], n_rollouts, lo, returns=ret, block_order=order)  # the mode of a turn is in its headers
         else:
             X, n_app = network.X, int(network.cfg.get("n_app_ids", 0))
             side_of_env = [torch.from_numpy(i_of_pair).to(device)[pair_of_env], torch.from_numpy(j_of_pair).to(device)[pair_of_env]]

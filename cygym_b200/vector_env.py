@@ -267,9 +267,15 @@ class VectorCyberDefenseEnv:
         self._hold = (hdr, mask, out)
         return out
 
-    def rollout(self, hdr, mask, base_line, envs_per_row, row_base, returns=None, flags=0):
+    def block_envs(self):
+        """Slots per CTA of this handle's rollout launches (cyg_block_envs): what rollout(block_order=...) indexes."""
+        nb = C.c_int32(0)
+        K.check(self.L.cyg_block_envs(self.h, C.byref(nb)))
+        return int(nb.value)
+
+    def rollout(self, hdr, mask, base_line, envs_per_row, row_base, returns=None, flags=0, block_order=None):
         """n_steps plain steps of every env in ONE launch from per-ROW action tables (cyg_rollout): hdr [T, R, 4],
-        mask [T, R, W] int32, base_line [T, R] uint8 or None; env b reads row (row_base + b) // envs_per_row.
+        mask [T, R, W] int32, base_line [T, R] uint8 or None; slot b reads row (row_base + env_index_of_slot()[b]) // envs_per_row.
         `returns` [2, B] float64 accumulates the raw rewards of defender / attacker turns.  The loop body of
         DoubleOracle.simulate_game (do_agent.py:1875-2089) for the strategies that need no observation."""
         T, R = int(hdr.shape[0]), int(hdr.shape[1])
@@ -279,11 +285,26 @@ class VectorCyberDefenseEnv:
         if base_line is not None:
             base_line = base_line.to(self.device, torch.uint8).contiguous()
             assert base_line.shape == (T, R)
+        if block_order is not None:  # a permutation of the CTA indices: expensive blocks first
+            block_order = block_order.to(self.device, torch.int32).contiguous()
+            assert block_order.numel() == (self.B + self.block_envs() - 1) // self.block_envs()
         a = K.CygRolloutArgs(hdr.data_ptr(), mask.data_ptr(), None if base_line is None else base_line.data_ptr(), T, R,
-                             int(row_base), int(envs_per_row), 0, returns.data_ptr())
+                             int(row_base), int(envs_per_row), 0, returns.data_ptr(), None if block_order is None else block_order.data_ptr())
         K.check(self.L.cyg_rollout(self.h, C.byref(a), flags, self._s()))
-        self._hold = (hdr, mask, base_line, returns)
+        self._hold = (hdr, mask, base_line, returns, block_order)
         return returns
+
+    def set_env_id_stride(self, run, stride):
+        """Slot s holds env env_id0 + (s // run) * stride + s % run (cyg_set_env_id_stride; run divides B; run <= 0: the
+        default, env_id0 + s).  For rollout(): a rank takes the same slice of rollouts of every strategy pair."""
+        K.check(self.L.cyg_set_env_id_stride(self.h, int(run), int(stride)))
+        self._id_stride = (int(run), int(stride)) if run > 0 else None
+
+    def env_index_of_slot(self):
+        """int64 [B] on the device: env id minus env_id0 of every slot."""
+        s = torch.arange(self.B, device=self.device)
+        st = getattr(self, "_id_stride", None)
+        return s if st is None else (s // st[0]) * st[1] + s % st[0]
 
     # ---- host-buffer front end: what a CPU-side caller (the reference's rollout loops) uses ----
     def host_buffers(self):

@@ -277,8 +277,25 @@ typedef struct cyg_rollout_args {
   int32_t envs_per_row;
   int32_t reserved;
   double* returns;          /* [2][B] */
+  const int32_t* block_order; /* optional [ceil(B / cyg_block_envs)], a PERMUTATION of the block indices: the launch's
+                                 i-th CTA steps slots [block_order[i] * block_envs, +block_envs).  CTAs start in index
+                                 order, so listing the expensive blocks first (longest processing time first) shortens
+                                 the tail of a launch whose blocks differ a lot in cost -- strategy pairs do */
 } cyg_rollout_args;
+/* Slots per CTA of this handle's step / rollout launches (what block_order indexes). */
+int cyg_block_envs(cyg_handle h, int32_t* block_envs);
 int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, void* stream);
+
+/* Which env a slot of the handle holds.  Default: slot s is env env_id0 + s.  With run > 0 (run divides B, stride >= run)
+ * slot s is env env_id0 + (s / run) * stride + s % run: runs of `run` consecutive env ids, `stride` ids apart.  The payoff
+ * evaluation numbers its envs (strategy pair, rollout) row-major; a rank that takes rollouts [r * run, (r + 1) * run) of
+ * EVERY pair (run = rollouts per pair / ranks, stride = rollouts per pair, env_id0 = r * run) gets the same mix of cheap
+ * and expensive pairs as every other rank, where a contiguous slice of the id range would hand whole defender strategies
+ * to single ranks (the imbalance of the reference's pool workers, do_agent.py:1737-1753).  The env id keys the draw
+ * streams and, in cyg_rollout, the action row ((row_base + id - env_id0) / envs_per_row), so per-env results do not depend
+ * on the layout.  Honoured by cyg_rollout, cyg_randomize, cyg_rebuild_graph_cache and cyg_sample_actions; cyg_step /
+ * cyg_step_multi refuse a handle with strided ids.  run <= 0 restores the default. */
+int cyg_set_env_id_stride(cyg_handle h, int32_t run, int32_t stride);
 
 /* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
