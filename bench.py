@@ -417,6 +417,7 @@ def main():
     #      from pinned host memory, launches the kernel, reads (raw, shaped, done) back and synchronises ----
     e2e = None
     if not a.no_e2e:
+        from cygym_b200.vector_env import compact_action_rows
         Ke = max(200, a.e2e_steps)
         groups = sets[:3]  # every env set of the rotation is one group with its own stream
         host_actions = {}
@@ -425,7 +426,8 @@ def main():
             env.host_buffers()
             for mode in (0, 1):
                 ab = ring[mode][gi % len(ring[mode])]
-                host_actions[gi, mode] = torch.cat([ab.hdr, ab.mask], dim=1).cpu().pin_memory()  # [B, 4 + W] rows: hdr | mask
+                # [B, 2 + W] compact rows (include/cygym_b200.h: a 2-word header + the device mask, 24 bytes per env at W = 4)
+                host_actions[gi, mode] = torch.from_numpy(compact_action_rows(ab.hdr.cpu(), ab.mask.cpu())).pin_memory()
         out_host = groups[0].host_buffers()[2]
         torch.cuda.synchronize()
 
@@ -667,7 +669,7 @@ def main():
         if e2e:
             line["e2e"] = {"value": world * B * e2e[1] / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[2],
                            "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1], "preheat_steps": 3 * PREHEAT,
-                           "how": f"VectorCyberDefenseEnv.step_host(act=pinned rows, sync=False) / wait_host() over {e2e[6]} env groups of "
+                           "how": f"VectorCyberDefenseEnv.step_host(act=pinned compact rows [B, 2 + W], sync=False) / wait_host() over {e2e[6]} env groups of "
                                   f"{B} envs on {e2e[6]} streams: each group waits for its own previous (raw, shaped, done) before its next "
                                   "step; the copies of one group overlap the kernel of the other",
                            "one_group_synchronous": {"value": world * B * e2e[5] / (ems1 * 1e-3), "unit": UNIT,

@@ -839,6 +839,38 @@ __global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
 }
 #endif
 
+/* cyg_unpack_actions: compact action rows [B][2 + Wm] (include/cygym_b200.h) -> hdr [B][4] + mask [B][Wm].  One thread
+ * per env; the rows are what a host-buffer step moves over PCIe (24 bytes per env at M <= 128 instead of 32). */
+struct UnpackParams {
+  const uint32_t* rows;
+  uint32_t* hdr;
+  uint32_t* mask;
+  int B, Wm;
+};
+#if defined(CYG_TU_W) && CYG_TU_W == 4
+__global__ void cyg_unpack_kernel(const __grid_constant__ UnpackParams p) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= p.B) return;
+  const uint32_t* r = p.rows + (size_t)env * (2 + p.Wm);
+  const uint32_t w0 = r[0], w1 = r[1];
+  uint32_t exw = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { /* four signed 4-bit exploit indices -> four signed bytes */
+    const int x = (int)((w1 >> (4 * i)) & 15u);
+    exw |= (uint32_t)((x >= 8 ? x - 16 : x) & 0xFF) << (8 * i);
+  }
+  const int app = (int)(int16_t)(w1 >> 16);
+  uint4 h;
+  h.x = (w0 & 0x1FFu) | (((w0 >> 9) & 7u) << 16);       /* type | mode << 8 | n_ex << 16 */
+  h.y = exw;
+  h.z = ((w0 >> 12) & 0xFFFu) | ((w0 >> 24) << 16);     /* n_dev | (first + 1) << 16 */
+  h.w = (uint32_t)app;
+  *reinterpret_cast<uint4*>(p.hdr + (size_t)env * 4) = h;
+  for (int w = 0; w < p.Wm; w++) p.mask[(size_t)env * p.Wm + w] = r[2 + w];
+}
+extern "C" void cyg_unpack_launch(int blocks, int threads, cudaStream_t st, const UnpackParams& p) { cyg_unpack_kernel<<<blocks, threads, 0, st>>>(p); }
+#endif
+
 struct ObsParams {
   Net net;
   const uint32_t* recs;
@@ -917,6 +949,7 @@ extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
 #else /* ---- the C-ABI translation unit ---- */
 extern "C" {
 void cyg_group_launch(int blocks, int threads, cudaStream_t st, const GroupParams& p);
+void cyg_unpack_launch(int blocks, int threads, cudaStream_t st, const UnpackParams& p);
 const WOps* cyg_wops_4(void);
 #ifndef CYG_FAST_BUILD /* profiling builds link the W = 4 unit only (config C3) */
 const WOps* cyg_wops_1(void);
@@ -1299,6 +1332,19 @@ int cyg_observe(cyg_handle h, int32_t obs_mode, float* obs, void* stream) {
   int blocks = (int)((total + threads - 1) / threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
   wops(h->W)->observe(blocks, threads, (cudaStream_t)stream, p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_unpack_actions(cyg_handle h, const uint32_t* rows, uint32_t* hdr, uint32_t* mask, void* stream) {
+  if (!h || !rows || !hdr || !mask) return fail(CYG_E_INVAL, "null argument");
+  if (((uintptr_t)hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
+  if (h->net.M > 254) return fail(CYG_E_INVAL, "compact action rows: networks of at most 254 device slots");
+  DeviceGuard g(h->device);
+  UnpackParams p = {rows, hdr, mask, h->B, h->net.Wm};
+  const int threads = 256, blocks = (h->B + threads - 1) / threads;
+  cyg_unpack_launch(blocks, threads, (cudaStream_t)stream, p);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

@@ -59,6 +59,40 @@ class ActionBatch:
         return hdr, mask, order
 
 
+def compact_action_rows(hdr, mask):
+    """hdr [B, 4] + mask [B, W] (numpy or CPU torch, the arrays of ActionBatch.pack) -> compact rows [B, 2 + W] int32
+    (include/cygym_b200.h, cyg_unpack_actions): what a host-buffer step copies over PCIe.  Raises ValueError when an
+    action does not fit the compact ranges (exploit indices -8..7, app_index -32768..32767, device_indices[0] < 255)."""
+    h = np.ascontiguousarray(hdr.numpy() if hasattr(hdr, "numpy") else hdr).view(np.uint32)
+    m = np.ascontiguousarray(mask.numpy() if hasattr(mask, "numpy") else mask).view(np.uint32)
+    n_ex = (h[:, 0] >> 16) & 0xFF
+    n_dev, first1 = h[:, 2] & 0xFFFF, h[:, 2] >> 16
+    app = h[:, 3].view(np.int32)
+    ex = ((h[:, 1][:, None] >> (8 * np.arange(4, dtype=np.uint32))) & 0xFF).astype(np.uint8).view(np.int8).astype(np.int32)
+    if (h[:, 0] >> 24).any() or ((h[:, 0] >> 9) & 0x7F).any() or (n_ex > 4).any() or (n_dev > 4095).any() or (first1 > 255).any() \
+            or (app < -32768).any() or (app > 32767).any() or (ex < -8).any() or (ex > 7).any():
+        raise ValueError("action outside the compact row ranges: use the full hdr / mask arrays")
+    rows = np.empty((h.shape[0], 2 + m.shape[1]), np.uint32)
+    rows[:, 0] = (h[:, 0] & 0x1FF) | (n_ex << 9) | (n_dev << 12) | (first1 << 24)
+    rows[:, 1] = ((ex & 15).astype(np.uint32) << (4 * np.arange(4, dtype=np.uint32))).sum(1, dtype=np.uint32) | ((app & 0xFFFF).astype(np.uint32) << 16)
+    rows[:, 2:] = m
+    return rows.view(np.int32)
+
+
+def expand_action_rows(rows):
+    """The inverse of compact_action_rows on the host (what cyg_unpack_actions does on the device): (hdr, mask) uint32."""
+    r = np.ascontiguousarray(rows).view(np.uint32)
+    w0, w1 = r[:, 0], r[:, 1]
+    x = ((w1[:, None] >> (4 * np.arange(4, dtype=np.uint32))) & 15).astype(np.int32)
+    x = np.where(x >= 8, x - 16, x)
+    hdr = np.empty((r.shape[0], 4), np.uint32)
+    hdr[:, 0] = (w0 & 0x1FF) | (((w0 >> 9) & 7) << 16)
+    hdr[:, 1] = ((x & 0xFF).astype(np.uint32) << (8 * np.arange(4, dtype=np.uint32))).sum(1, dtype=np.uint32)
+    hdr[:, 2] = ((w0 >> 12) & 0xFFF) | ((w0 >> 24) << 16)
+    hdr[:, 3] = (w1 >> 16).astype(np.uint16).view(np.int16).astype(np.int32).view(np.uint32)
+    return hdr, r[:, 2:].copy()
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -316,13 +350,17 @@ class VectorCyberDefenseEnv:
                 mask=torch.empty(self.B, self.W, dtype=torch.int32).pin_memory(),
                 out=torch.empty(3, self.B, dtype=torch.float32).pin_memory(),
                 d_act=torch.empty(self.B, 4 + self.W, dtype=torch.int32, device=self.device),
+                d_rows=torch.empty(self.B, 2 + self.W, dtype=torch.int32, device=self.device),
                 d_hdr=torch.empty(self.B, 4, dtype=torch.int32, device=self.device),
                 d_mask=torch.empty(self.B, self.W, dtype=torch.int32, device=self.device))
         return self._host["hdr"], self._host["mask"], self._host["out"]
 
     def _host_ops(self, hdr, mask, flags):
         h = self._host
-        if mask is None:  # combined [B, 4 + W] rows: ONE host->device copy, split on the device
+        if mask is None and hdr.shape[1] == 2 + self.W:  # compact rows (compact_action_rows): the smallest copy, expanded on the device
+            h["d_rows"].copy_(hdr, non_blocking=True)
+            K.check(self.L.cyg_unpack_actions(self.h, _ptr(h["d_rows"]), _ptr(h["d_hdr"]), _ptr(h["d_mask"]), self._s()))
+        elif mask is None:  # combined [B, 4 + W] rows: ONE host->device copy, split on the device
             h["d_act"].copy_(hdr, non_blocking=True)
             h["d_hdr"].copy_(h["d_act"][:, :4])
             h["d_mask"].copy_(h["d_act"][:, 4:])
@@ -338,6 +376,8 @@ class VectorCyberDefenseEnv:
         (raw, shaped, done) into host_buffers()[2], then a stream synchronise (the caller reads the rewards before
         choosing the next action).  The four operations are captured once per (hdr, mask) buffer pair into a CUDA
         graph and replayed, so a step costs one graph launch on the host.  Returns (raw, shaped, done) host views.
+        The graph holds the ADDRESS of the caller's pinned buffer: keep one staging buffer per env group alive and
+        refill it (a pinned tensor freed after it was captured leaves the host allocator waiting on a captured event).
 
         sync=False returns right after the enqueue (the host views are valid after wait_host()): a caller that drives
         two env groups on two streams (`stream=` of the constructor) chooses the actions of one group while the other
@@ -346,7 +386,8 @@ class VectorCyberDefenseEnv:
         if self._host is None:
             self.host_buffers()
         h = self._host
-        if act is not None:  # pinned [B, 4 + W] int32 rows (hdr | mask): one larger copy moves faster than two small ones
+        if act is not None:  # pinned int32 rows, [B, 4 + W] (hdr | mask) or [B, 2 + W] (compact_action_rows): ONE copy
+            assert act.shape[1] in (4 + self.W, 2 + self.W)
             hdr, mask = act, None
         else:
             hdr = h["hdr"] if hdr is None else hdr

@@ -297,6 +297,17 @@ int cyg_rollout(cyg_handle h, const cyg_rollout_args* a, uint32_t step_flags, vo
  * cyg_step_multi refuse a handle with strided ids.  run <= 0 restores the default. */
 int cyg_set_env_id_stride(cyg_handle h, int32_t run, int32_t stride);
 
+/* Compact action rows for callers that keep their actions in HOST memory: the copy over PCIe is what bounds a host-buffer
+ * step, so the header of a set-form action travels in two words instead of four.  Row of env b =
+ * [w0, w1, mask[0..Wm)] (2 + Wm words):
+ *   w0 = action_type (bits 0-7, CYG_ATYPE_NONE as in hdr[0]) | mode << 8 | n_exploits << 9 (0..4) | n_devices << 12 (0..4095)
+ *        | (device_indices[0] + 1) << 24 (0: none given)
+ *   w1 = exploit index i as a signed 4-bit field at bit 4 i (-8..7) | app_index as a signed 16-bit field << 16
+ * Actions outside those ranges (and networks above 254 device slots) use the full hdr / mask arrays.
+ * cyg_unpack_actions expands B rows (device memory) into hdr [B][4] + mask [B][Wm] for cyg_step; it is one small launch
+ * on `stream` and replaces nothing of the reference -- it is the decode of what volt_typhoon_env.py:876 unpacks. */
+int cyg_unpack_actions(cyg_handle h, const uint32_t* rows, uint32_t* hdr, uint32_t* mask, void* stream);
+
 /* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);
 

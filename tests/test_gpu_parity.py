@@ -257,6 +257,19 @@ def test_step_host_matches_device_step():
     for _ in range(1):
         raw, shaped, done = b.step_host(act=rows)
     assert torch.equal(raw, r[0].cpu()) and torch.equal(done, r[2].cpu())
+    # compact [B, 2 + W] rows (24 bytes per env over PCIe instead of 32), expanded on the device by cyg_unpack_actions
+    from cygym_b200.vector_env import compact_action_rows, expand_action_rows
+    rows_c = torch.empty(B, 2 + a.W, dtype=torch.int32).pin_memory()  # ONE staging buffer, kept: the replayed graph holds its address
+    for t in range(4):
+        ab = a.sample_actions(t & 1)
+        b.sample_actions(t & 1)
+        torch.cuda.synchronize()
+        r = [x.clone() for x in a.step(ab)]
+        rows_c.copy_(torch.from_numpy(compact_action_rows(ab.hdr.cpu(), ab.mask.cpu())))
+        raw, shaped, done = b.step_host(act=rows_c)
+        assert torch.equal(raw, r[0].cpu()) and torch.equal(shaped, r[1].cpu()) and torch.equal(done, r[2].cpu()), t
+        h2, m2 = expand_action_rows(rows_c.numpy())
+        assert np.array_equal(b._host["d_hdr"].cpu().numpy().view(np.uint32), h2) and np.array_equal(b._host["d_mask"].cpu().numpy().view(np.uint32), m2)
     ca, cb = a.export_state(), b.export_state()
     for k in ca:
         assert torch.equal(ca[k], cb[k]), k

@@ -47,6 +47,31 @@ def test_action_pack_roundtrip_and_errors():
     assert list(o[0, :3]) == [5, 2, 5] and h[0, 2] == 3
 
 
+def test_compact_action_rows_roundtrip_and_ranges():
+    """The 2-word header of the host-buffer rows (include/cygym_b200.h, cyg_unpack_actions) holds everything hdr[4] holds
+    inside its documented ranges, and refuses what it cannot hold."""
+    from cygym_b200.vector_env import ActionBatch, compact_action_rows, expand_action_rows
+    rng = np.random.default_rng(5)
+    acts, modes = [], []
+    for b in range(400):
+        if b % 17 == 0:
+            acts.append(None)
+        else:
+            devs = sorted(int(d) for d in rng.choice(100, size=int(rng.integers(0, 100)), replace=False))
+            acts.append((int(rng.integers(-3, 16)), [int(x) for x in rng.integers(-8, 8, size=int(rng.integers(0, 5)))], devs, int(rng.integers(-500, 500))))
+        modes.append(int(rng.integers(0, 2)))
+    hdr, mask, _ = ActionBatch.pack(acts, modes, 100)
+    hdr[5, 2] |= np.uint32(77 << 16)                       # device_indices[0] + 1 as sample_action writes it
+    rows = compact_action_rows(hdr, mask)
+    assert rows.shape == (400, 2 + 4) and rows.dtype == np.int32
+    h2, m2 = expand_action_rows(rows)
+    assert np.array_equal(h2, hdr) and np.array_equal(m2, mask)
+    for bad in ((1, [9], [1], 0), (1, [0], [1], 40000), (1, [-9], [1], 0)):
+        h, m, _ = ActionBatch.pack([bad], 0, 100)
+        with pytest.raises(ValueError):
+            compact_action_rows(h, m)
+
+
 @pytest.mark.parametrize("M,subnets", [(20, 1), (50, 3), (100, 8), (2000, 64)])
 def test_synthetic_network_invariants(M, subnets):
     from cygym_b200 import synthetic_network
