@@ -33,6 +33,22 @@ def test_sweep(case):
     from cygym_b200 import synthetic_network
     rng = np.random.default_rng(case["M"])
     net = _dense_multi(synthetic_network(case["M"], n_subnets=case["sub"], seed=case["M"] * 3 + 1, **case["kw"]), rng)
+    _sweep(net, rng)
+
+
+def test_snapshot_of_a_reference_env():
+    """The committed snapshot of a reference env 30 steps into an episode (oracle/gen_snapshot.py, flattened by
+    cygym_b200.snapshot.from_reference_env) loads without the reference and steps from that state -- device source and
+    oracle agree (the GPU twin is tests/test_gpu_parity.py::test_snapshot_of_a_reference_env_steps_like_the_oracle)."""
+    import os
+    from cygym_b200 import snapshot
+    from tests.common import ROOT
+    net = snapshot.load_npz(os.path.join(ROOT, "tests", "golden", "snapshots", "ref_m30_step30.npz"))
+    assert net.M == 30 and int(net.template["scal"][0]) == 30 and int((net.template["dev"] & 1).sum()) > 0
+    _sweep(net, np.random.default_rng(30))
+
+
+def _sweep(net, rng):
     xcap, B, T = 200, 40, 70
     W = net.W
     for base_line in ("Nash", "No Defense", "Preset", "No Attack"):

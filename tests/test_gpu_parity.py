@@ -36,11 +36,12 @@ def test_cuda_replays_golden(path):
     assert n == len(g["kind"])
 
 
-def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64, dense_multi=False, base_line="Nash", **kw):
+def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64, dense_multi=False, base_line="Nash", net=None, **kw):
     import torch
     from cygym_b200 import synthetic_network
     from cygym_b200.vector_env import VectorCyberDefenseEnv, ActionBatch
-    net = synthetic_network(M, n_subnets=subnets, seed=seed, **kw)
+    if net is None:
+        net = synthetic_network(M, n_subnets=subnets, seed=seed, **kw)
     if dense_multi:  # ~10 % of the pairs become multi-edges of multiplicity 2..4 (> 2 per list -> the general routines)
         rng = np.random.default_rng(M)
         m = net.mult.copy()
@@ -76,6 +77,20 @@ def _rollout_vs_oracle(M, subnets, B, T, seed=5, env_id0=3, obs_every=7, xcap=64
             assert np.array_equal(env.observe(om).cpu().numpy(), orc.observe(so, om)), f"observe mode {om} t={t}"
     assert int(env.error_flags().max().item()) == 0
     assert env.launch_count > T
+
+
+def test_snapshot_of_a_reference_env_steps_like_the_oracle():
+    """f2: tests/golden/snapshots/ref_m30_step30.npz is a reference env 30 steps into an episode, flattened by
+    cygym_b200.snapshot.from_reference_env and saved by save_npz (oracle/gen_snapshot.py; the flattening itself is checked
+    against the harness in tests/test_oracle_vs_reference.py).  Loaded here without the reference, its state (compromised
+    devices, workloads in flight, busy timers, counters) is the template of 512 envs that then step bit-exactly with the
+    oracle from that state."""
+    import os
+    from cygym_b200 import snapshot
+    from tests.common import ROOT
+    net = snapshot.load_npz(os.path.join(ROOT, "tests", "golden", "snapshots", "ref_m30_step30.npz"))
+    assert net.M == 30 and int((net.template["dev"] & 1).sum()) > 0 and int(net.template["scal"][0]) == 30
+    _rollout_vs_oracle(net.M, 1, 512, 120, net=net)
 
 
 def test_c1_default_network_rollout():
