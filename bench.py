@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--randomize", action="store_true", help="headline on envs after randomize_compromise_and_ownership() (the `randomized` leg as the main line)")
     ap.add_argument("--obs", type=int, default=0, help="fused observation mode inside the step (0 none, 1 defender, 2 attacker)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--e2e-groups", type=int, default=5, help="env groups (of --envs envs each, one stream each, every one closed-loop) the e2e leg keeps in flight")
     ap.add_argument("--e2e-steps", type=int, default=240, help="host-buffer steps of the e2e leg (fixed: the leg is host / PCIe paced and noisy when short)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -441,7 +442,13 @@ def main():
     if not a.no_e2e:
         from cygym_b200.vector_env import compact_action_rows
         Ke = max(200, a.e2e_steps)
-        groups = sets[:3]  # every env set of the rotation is one group with its own stream
+        # env groups in flight: the env sets of the rotation plus extra ones, every group closed-loop on its own stream.  One
+        # group's step is a ~130 us chain (H2D, expand, kernel, D2H, the host's wake-up and next launch); three groups leave
+        # the copy engines and the SMs idle part of the time, five keep them busy (profiles/NOTES_r02.md)
+        n_groups = max(1, a.e2e_groups)
+        groups = list(sets[:n_groups])
+        if len(groups) < n_groups:
+            groups += make_sets(net, B, n_groups - len(groups), a.randomize, id_base=(world * a.sets + 7) * B)
         host_actions = {}
         for gi, env in enumerate(groups):
             env._stream = torch.cuda.Stream(dev)  # one stream per env group
@@ -476,7 +483,7 @@ def main():
             barrier()
             return t0.elapsed_time(t1)
 
-        run_e2e(len(groups), 3 * PREHEAT)
+        run_e2e(len(groups), len(groups) * PREHEAT)
         ems = run_e2e(len(groups), Ke)
         run_e2e(1, PREHEAT)
         ems1 = run_e2e(1, Ke // 2)
@@ -484,6 +491,9 @@ def main():
         for env in groups:
             env._stream = None
         torch.cuda.synchronize()
+        for env in groups[len(sets):]:
+            env.close()
+        del groups[len(sets):]
 
     # ================= the other shapes (N = 1: kernel diagnostics, not scaling points) =================
     legs = {}
@@ -696,7 +706,7 @@ def main():
             line["legs"] = legs
         if e2e:
             line["e2e"] = {"value": world * B * e2e[1] / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[2],
-                           "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1], "preheat_steps": 3 * PREHEAT,
+                           "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1], "preheat_steps": e2e[6] * PREHEAT,
                            "how": f"VectorCyberDefenseEnv.step_host(act=pinned compact rows [B, 2 + W], sync=False) / wait_host() over {e2e[6]} env groups of "
                                   f"{B} envs on {e2e[6]} streams: each group waits for its own previous (raw, shaped, done) before its next "
                                   "step; the copies of one group overlap the kernel of the other",
