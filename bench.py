@@ -457,7 +457,6 @@ def main():
                 ab = ring[mode][gi % len(ring[mode])]
                 # [B, 2 + W] compact rows (include/cygym_b200.h: a 2-word header + the device mask, 24 bytes per env at W = 4)
                 host_actions[gi, mode] = torch.from_numpy(compact_action_rows(ab.hdr.cpu(), ab.mask.cpu())).pin_memory()
-        out_host = groups[0].host_buffers()[2]
         torch.cuda.synchronize()
 
         def run_e2e(n_groups, steps):
@@ -475,7 +474,7 @@ def main():
                 g = i % n_groups
                 env = groups[g]
                 env.wait_host()
-                env.step_host(act=host_actions[g, turn[g] & 1], sync=False)
+                env.step_host(act=host_actions[g, turn[g] & 1], sync=False, packed_done=True)
                 turn[g] += 1
             for g in range(n_groups):
                 groups[g].wait_host()
@@ -487,7 +486,7 @@ def main():
         ems = run_e2e(len(groups), Ke)
         run_e2e(1, PREHEAT)
         ems1 = run_e2e(1, Ke // 2)
-        e2e = (ems, Ke, host_actions[0, 0].numel() * 4, out_host.numel() * 4, ems1, Ke // 2, len(groups))
+        e2e = (ems, Ke, host_actions[0, 0].numel() * 4, groups[0].host_result_bytes(True), ems1, Ke // 2, len(groups))
         for env in groups:
             env._stream = None
         torch.cuda.synchronize()
@@ -707,7 +706,7 @@ def main():
         if e2e:
             line["e2e"] = {"value": world * B * e2e[1] / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e[2],
                            "d2h_bytes_per_step": e2e[3], "steps": e2e[1], "ms_per_step": ems / e2e[1], "preheat_steps": e2e[6] * PREHEAT,
-                           "how": f"VectorCyberDefenseEnv.step_host(act=pinned compact rows [B, 2 + W], sync=False) / wait_host() over {e2e[6]} env groups of "
+                           "how": f"VectorCyberDefenseEnv.step_host(act=pinned compact rows [B, 2 + W], sync=False, packed_done=True) / wait_host() (results: raw f32, shaped f32, one done bit per env) over {e2e[6]} env groups of "
                                   f"{B} envs on {e2e[6]} streams: each group waits for its own previous (raw, shaped, done) before its next "
                                   "step; the copies of one group overlap the kernel of the other",
                            "one_group_synchronous": {"value": world * B * e2e[5] / (ems1 * 1e-3), "unit": UNIT,

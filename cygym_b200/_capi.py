@@ -83,7 +83,7 @@ class CygRolloutArgs(C.Structure):
 
 
 EXPORTS = ["cyg_version", "cyg_last_error", "cyg_create", "cyg_destroy", "cyg_set_base_line", "cyg_set_base_line_per_env", "cyg_set_base_line_per_env_steps", "cyg_internal_words",
-           "cyg_bind", "cyg_set_detectors", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_unpack_actions", "cyg_block_envs", "cyg_set_env_id_stride", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
+           "cyg_bind", "cyg_set_detectors", "cyg_import_state", "cyg_export_state", "cyg_step", "cyg_step_multi", "cyg_rollout", "cyg_unpack_actions", "cyg_pack_done", "cyg_block_envs", "cyg_set_env_id_stride", "cyg_randomize", "cyg_rebuild_graph_cache", "cyg_sample_actions", "cyg_sample_actions_ordered",
            "cyg_observe", "cyg_group_actions", "cyg_launch_count", "cyg_set_debug_cycles"]
 
 
@@ -188,6 +188,7 @@ def lib():
         L.cyg_set_env_id_stride.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.cyg_block_envs.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.cyg_unpack_actions.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.cyg_pack_done.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_randomize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_rebuild_graph_cache.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cyg_sample_actions.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -869,6 +869,15 @@ __global__ void cyg_unpack_kernel(const __grid_constant__ UnpackParams p) {
   for (int w = 0; w < p.Wm; w++) p.mask[(size_t)env * p.Wm + w] = r[2 + w];
 }
 extern "C" void cyg_unpack_launch(int blocks, int threads, cudaStream_t st, const UnpackParams& p) { cyg_unpack_kernel<<<blocks, threads, 0, st>>>(p); }
+/* cyg_pack_done: done flags [B] (int32) -> one bit per env (bit b % 32 of word b / 32) */
+__global__ void cyg_pack_done_kernel(const int32_t* done, uint32_t* bits, int B) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, env < B && done[env] != 0);
+  if ((threadIdx.x & 31) == 0 && env < B) bits[env >> 5] = m;
+}
+extern "C" void cyg_pack_done_launch(int blocks, int threads, cudaStream_t st, const int32_t* done, uint32_t* bits, int B) {
+  cyg_pack_done_kernel<<<blocks, threads, 0, st>>>(done, bits, B);
+}
 #endif
 
 struct ObsParams {
@@ -950,6 +959,7 @@ extern "C" const WOps* CYG_WOPS_NAME(CYG_TU_W)(void) {
 extern "C" {
 void cyg_group_launch(int blocks, int threads, cudaStream_t st, const GroupParams& p);
 void cyg_unpack_launch(int blocks, int threads, cudaStream_t st, const UnpackParams& p);
+void cyg_pack_done_launch(int blocks, int threads, cudaStream_t st, const int32_t* done, uint32_t* bits, int B);
 const WOps* cyg_wops_4(void);
 #ifndef CYG_FAST_BUILD /* profiling builds link the W = 4 unit only (config C3) */
 const WOps* cyg_wops_1(void);
@@ -1345,6 +1355,16 @@ int cyg_unpack_actions(cyg_handle h, const uint32_t* rows, uint32_t* hdr, uint32
   UnpackParams p = {rows, hdr, mask, h->B, h->net.Wm};
   const int threads = 256, blocks = (h->B + threads - 1) / threads;
   cyg_unpack_launch(blocks, threads, (cudaStream_t)stream, p);
+  h->launches++;
+  CU(cudaGetLastError());
+  return CYG_OK;
+}
+
+int cyg_pack_done(cyg_handle h, const int32_t* done, uint32_t* bits, void* stream) {
+  if (!h || !done || !bits) return fail(CYG_E_INVAL, "null argument");
+  DeviceGuard g(h->device);
+  const int threads = 256, blocks = (h->B + threads - 1) / threads;
+  cyg_pack_done_launch(blocks, threads, (cudaStream_t)stream, done, bits, h->B);
   h->launches++;
   CU(cudaGetLastError());
   return CYG_OK;

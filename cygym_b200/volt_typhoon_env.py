@@ -416,7 +416,8 @@ class Volt_Typhoon_CyberDefenseEnv:
     def _finish(self, raw, shaped, done, action, grouped, executed):
         v = self._venv
         # one device->host copy: rewards, done and the pre-evolve masks; the counters come from the cached state copy
-        out = torch.cat([v._out.view(torch.int32).reshape(-1), v.pre_masks().reshape(-1)]).cpu().numpy()
+        out = torch.cat([raw.view(torch.int32).reshape(-1), shaped.view(torch.int32).reshape(-1), done.view(torch.int32).reshape(-1),
+                         v.pre_masks().reshape(-1)]).cpu().numpy()
         self._host = None
         if int(self._snap()["scal"][K.S_FLAGS]) & K.FL_DET_PENDING:  # defender action 10 trained the detector (volt:945-962)
             seed = self.detector_fit_seed

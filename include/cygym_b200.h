@@ -307,6 +307,9 @@ int cyg_set_env_id_stride(cyg_handle h, int32_t run, int32_t stride);
  * cyg_unpack_actions expands B rows (device memory) into hdr [B][4] + mask [B][Wm] for cyg_step; it is one small launch
  * on `stream` and replaces nothing of the reference -- it is the decode of what volt_typhoon_env.py:876 unpacks. */
 int cyg_unpack_actions(cyg_handle h, const uint32_t* rows, uint32_t* hdr, uint32_t* mask, void* stream);
+/* The way back: the `done` flags of a step (cyg_step_out.done, [B] int32) as one bit per env -- bit b % 32 of word b / 32,
+ * ceil(B / 32) words -- so that a host-buffer step reads 8.1 bytes per env (raw, shaped, done bit) instead of 12. */
+int cyg_pack_done(cyg_handle h, const int32_t* done, uint32_t* bits, void* stream);
 
 /* Replaces randomize_compromise_and_ownership() (volt_typhoon_env.py:330-383); env_mask may be NULL. */
 int cyg_randomize(cyg_handle h, const uint8_t* env_mask, void* stream);

@@ -281,8 +281,10 @@ def test_step_host_matches_device_step():
         torch.cuda.synchronize()
         r = [x.clone() for x in a.step(ab)]
         rows_c.copy_(torch.from_numpy(compact_action_rows(ab.hdr.cpu(), ab.mask.cpu())))
-        raw, shaped, done = b.step_host(act=rows_c)
+        raw, shaped, bits = b.step_host(act=rows_c, packed_done=(t >= 2))   # t >= 2: done comes back as one bit per env
+        done = bits if t < 2 else torch.from_numpy(((bits.numpy().view(np.uint32)[np.arange(B) >> 5] >> (np.arange(B) & 31)) & 1).astype(np.int32))
         assert torch.equal(raw, r[0].cpu()) and torch.equal(shaped, r[1].cpu()) and torch.equal(done, r[2].cpu()), t
+        assert b.host_result_bytes(True) == 4 * (2 * B + (B + 31) // 32)
         h2, m2 = expand_action_rows(rows_c.numpy())
         assert np.array_equal(b._host["d_hdr"].cpu().numpy().view(np.uint32), h2) and np.array_equal(b._host["d_mask"].cpu().numpy().view(np.uint32), m2)
     ca, cb = a.export_state(), b.export_state()
