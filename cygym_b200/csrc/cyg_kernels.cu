@@ -791,9 +791,10 @@ struct GroupParams {
   int B, mode, role, n_types, noop;
 };
 #if defined(CYG_TU_W) && CYG_TU_W == 4 /* one copy: the kernel is not templated on the plane width */
-__global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
-  const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
-  if (b >= p.B) return;
+/* the groups of ONE env by one warp: lane g < G ends up with group g's device words (handed to `put` word by word) and its
+ * header (returned through h4) */
+template <typename Put>
+__device__ __forceinline__ void group_one_env(const GroupParams& p, int b, int lane, uint32_t* slot, uint32_t h4[4], Put put) {
   const Net& n = p.net;
   const int M = n.M, Wm = n.Wm, Wp = n.W;
   const uint32_t* pl = p.recs + (size_t)b * n.S + CYG_REC_PLANES;
@@ -808,12 +809,16 @@ __global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
     else if (p.role == 2) vis = ~pl[P_NYA * Wp + w] & pl[P_OWNED * Wp + w] & pl[P_KNOWN * Wp + w];
     const int ty = d < M ? p.types[(size_t)b * M + d] : -1;
     const bool on = d < M && ((vis >> lane) & 1u) && (!p.visible || p.visible[(size_t)b * M + d] != 0);
-    uint32_t mine = 0;
-    for (int g = 0; g < G; g++) { /* uniform */
-      const int t = g < p.noop ? g : g + 1;
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, on && ty == t);
-      if (lane == g) mine = m;
-    }
+    /* lanes with the same type find each other with ONE match (13 ballots + selects before: the kernel was bound by its
+     * instruction count, 60 us for 65 536 envs); the lowest lane of every type posts the set, lane g picks up its type's */
+    slot[lane] = 0u;
+    slot[lane + 32] = 0u;
+    __syncwarp();
+    const uint32_t same = __match_any_sync(0xFFFFFFFFu, on ? ty : -1);
+    if (on && ty >= 0 && ty < 64 && (same & ((1u << lane) - 1u)) == 0u) slot[ty] = same;
+    __syncwarp();
+    uint32_t mine = lane < G ? slot[t_mine] : 0u;
+    __syncwarp();
     if (lane < G) {
       if (t_mine == 11 || t_mine == 12) { /* single-device types: the chosen device if it is in the set, else (no choice given) the lowest */
         if (p.single) {
@@ -825,18 +830,35 @@ __global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
       }
       if (mine && first < 0) first = 32 * w + __ffs((int)mine) - 1;
       ndev += __popc(mine);
-      p.mask[((size_t)lane * p.B + b) * Wm + w] = mine;
+      put(w, mine);
     }
   }
-  if (lane < G) {
-    uint32_t* h = p.hdr + ((size_t)lane * p.B + b) * 4;
-    const int at = ndev > 0 ? t_mine : p.noop;
-    h[0] = (uint32_t)(at & 0xFF) | ((uint32_t)p.mode << 8) | (1u << 16);
-    h[1] = (uint32_t)(p.exp_idx ? p.exp_idx[b] : 0) & 0xFFu;
-    h[2] = (uint32_t)ndev;
-    h[3] = (uint32_t)(p.app_idx ? p.app_idx[b] : 0);
-  }
+  const int at = ndev > 0 ? t_mine : p.noop;
+  h4[0] = (uint32_t)(at & 0xFF) | ((uint32_t)p.mode << 8) | (1u << 16);
+  h4[1] = (uint32_t)(p.exp_idx ? p.exp_idx[b] : 0) & 0xFFu;
+  h4[2] = (uint32_t)ndev;
+  h4[3] = (uint32_t)(p.app_idx ? p.app_idx[b] : 0);
 }
+
+/* any plane width: one warp per env, every lane < G writes its group's words straight to [g][b] (4-byte pieces, one per
+ * group and word: fine for the few envs of a large network) */
+__global__ void cyg_group_kernel(const __grid_constant__ GroupParams p) {
+  const int b = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+  if (b >= p.B) return;
+  const int G = p.n_types - 1, Wm = p.net.Wm;
+  __shared__ uint32_t s_slot[4][64]; /* per warp: the device set of every type, one plane word at a time */
+  uint32_t h4[4];
+  uint32_t* const mrow = p.mask + ((size_t)lane * p.B + b) * Wm;
+  if (Wm == 4 && (((uintptr_t)p.mask) & 15) == 0) { /* the outputs are [g][b][..]: ONE 16-byte store per group instead of four 4-byte pieces */
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    group_one_env(p, b, lane, s_slot[(threadIdx.x >> 5) & 3], h4, [&](int w, uint32_t m) { m0 = w == 0 ? m : m0; m1 = w == 1 ? m : m1; m2 = w == 2 ? m : m2; m3 = w == 3 ? m : m3; });
+    if (lane < G) *reinterpret_cast<uint4*>(mrow) = make_uint4(m0, m1, m2, m3);
+  } else {
+    group_one_env(p, b, lane, s_slot[(threadIdx.x >> 5) & 3], h4, [&](int w, uint32_t m) { mrow[w] = m; });
+  }
+  if (lane < G) *reinterpret_cast<uint4*>(p.hdr + ((size_t)lane * p.B + b) * 4) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+}
+
 #endif
 
 /* cyg_unpack_actions: compact action rows [B][2 + Wm] (include/cygym_b200.h) -> hdr [B][4] + mask [B][Wm].  One thread
@@ -1376,6 +1398,7 @@ int cyg_group_actions(cyg_handle h, int32_t mode, int32_t role, const int32_t* p
   if (!h->state) return fail(CYG_E_INVAL, "cyg_bind() first");
   if (n_types < 2 || n_types > 33 || noop < 0 || noop >= n_types) return fail(CYG_E_INVAL, "n_types must be 2..33 and noop one of them");
   if (role < 0 || role > 2 || (mode != CYG_MODE_DEFENDER && mode != CYG_MODE_ATTACKER)) return fail(CYG_E_INVAL, "bad role / mode");
+  if (((uintptr_t)hdr) & 15) return fail(CYG_E_INVAL, "hdr must be 16-byte aligned");
   DeviceGuard g(h->device);
   GroupParams p = {h->net, h->state, per_dev_types, exp_idx, app_idx, visible, single_choice, hdr, mask, h->B, mode, role, n_types, noop};
   const int threads = 128, blocks = (int)(((size_t)h->B * 32 + threads - 1) / threads);
