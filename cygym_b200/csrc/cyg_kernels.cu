@@ -151,6 +151,29 @@ __device__ __forceinline__ void observe_rows_f(const Net& n, const uint32_t* rec
     const uint32_t vis = F == 4 ? (k & ~y & o) : (obs_mode == 1 ? (~y & o) : 0xFFFFFFFFu); /* rows outside are -1 */
     const int nelem = min(32, M - 32 * w) * F;
     float* row = out + (size_t)el * dim + 32 * w * F;
+    if ((((uintptr_t)row) & 7) == 0) { /* uniform */
+      /* pairs of floats: F is even, a device's row is (OS, version) (compromised, 0 | 1) [(known, not-yet-added)], so a
+       * lane produces the two fields of ONE pair of ONE device and stores 8 bytes -- half the rounds and a third of the
+       * instructions per float of the element-wise form below (which cost more warp instructions than the step itself) */
+      constexpr int P = F / 2; /* pairs per device */
+      const int npair = nelem >> 1;
+#pragma unroll
+      for (int t = 0; t < P; t++) {
+        const int pi = t * 32 + lane;
+        if (pi >= npair) continue;
+        const int sd = pi / P, fp = pi - sd * P, d = 32 * w + sd;
+        float2 v;
+        if (!((vis >> sd) & 1u)) { v.x = -1.f; v.y = -1.f; }
+        else if (fp == 0) { v.x = osv[d]; v.y = verv[d]; }
+        else if (fp == 1) {
+          v.x = (F == 6 && obs_mode == 1) ? -1.f : (float)((c >> sd) & 1u);
+          v.y = F == 4 ? 1.f : 0.f;
+        } else { v.x = (float)((k >> sd) & 1u); v.y = (float)((y >> sd) & 1u); }
+        reinterpret_cast<float2*>(row)[pi] = v;
+      }
+      if (F == 4 && w == 0 && lane < n.cfg.X) out[(size_t)el * dim + 4 * M + lane] = lane < n.cfg.n_exploits ? 1.f : 0.f;
+      continue;
+    }
 #pragma unroll
     for (int t = 0; t < F; t++) {
       const int e = t * 32 + lane;
