@@ -40,6 +40,8 @@ __device__ __forceinline__ uint32_t draw_at(const Rng& r, int site, uint32_t k) 
   return j == 0 ? o[0] : j == 1 ? o[1] : j == 2 ? o[2] : o[3];
 }
 
+template <bool V> struct HasX { static constexpr bool value = V; };
+
 template <int W>
 struct Coop {
   typedef Env<W, 1> E;
@@ -250,18 +252,26 @@ struct Coop {
         int tw = 0, mrun = 1;
         uint32_t nem = 0;
         bool had_att = false; /* some lane's pool of the current pass had edges removed (uniform) */
+        /* the fixed-point passes, compiled twice: for envs without extra edges (every env of a fresh network) nothing of the
+         * extra-edge bookkeeping is in the loop, for envs with extras all of it is */
+        auto passes = [&](auto has_x) {
+        constexpr bool HX = decltype(has_x)::value;
         for (;;) {
 #ifdef CYG_COUNT_ROUNDS
           e.dbg_rounds += 0x10000;
 #endif
           const int c0 = popc(x[0]), c1 = popc(x[1]), c2 = popc(x[2]), c3 = popc(x[3]);
-          const int tot = c0 + c1 + c2 + c3 + popc(imo) + popc(imi);
+          const int tot = c0 + c1 + c2 + c3 + (HX ? popc(imo) + popc(imi) : 0);
           nem = __ballot_sync(CYG_FULL, tot > 0);
           const uint32_t xr = __shfl_sync(CYG_FULL, xd, popc(nem & lanes_below(lane)));
           int nkey = -1, other = -1, ntw = 0, nm = 1;
           const int r = tot > 0 ? (int)below(xr, (uint32_t)tot) : 0;
           int sel = -1, passed = 0;
-          for (int j = 0; j < nx; j++) { /* uniform: does r land on an extra edge, how many extras sit in front of it */
+          /* only the extras that sit in SOME lane's pool matter (with the hub outside the window that is a third of them) */
+          uint32_t rel = HX ? __reduce_or_sync(CYG_FULL, imo | imi) : 0u;
+          while (rel) { /* uniform: does r land on an extra edge, how many extras sit in front of it */
+            const int j = __ffs((int)rel) - 1;
+            rel &= rel - 1u;
             const int po_j = __shfl_sync(CYG_FULL, xpo, j), pi_j = __shfl_sync(CYG_FULL, xpi, j);
             const uint32_t lo_j = __shfl_sync(CYG_FULL, lto, j), li_j = __shfl_sync(CYG_FULL, lti, j);
             const int ju = __shfl_sync(CYG_FULL, xu, j), jv = __shfl_sync(CYG_FULL, xv, j);
@@ -275,7 +285,7 @@ struct Coop {
             }
           }
           if (tot > 0) {
-            if (sel >= 0) {
+            if (HX && sel >= 0) {
               nkey = 0x10000 | sel;
             } else {
               const int rr = r - passed; /* word holding unit rr of the window, branch-free */
@@ -315,13 +325,14 @@ struct Coop {
             att &= ((lane >> k) & 1) ? bk : ~bk;
           }
           had_att = bv != 0;
-          x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2]; x[3] = x0[3]; imo = imo0; imi = imi0;
+          x[0] = x0[0]; x[1] = x0[1]; x[2] = x0[2]; x[3] = x0[3];
+          if (HX) { imo = imo0; imi = imi0; }
           while (__any_sync(CYG_FULL, att != 0)) {
             const int from = att ? (__ffs((int)att) - 1) : lane;
             const int kj = __shfl_sync(CYG_FULL, key, from);
             const int tj = __shfl_sync(CYG_FULL, tw, from), mj = __shfl_sync(CYG_FULL, mrun, from);
             if (att) {
-              if (kj & 0x10000) { imo &= ~(1u << (kj & 31)); imi &= ~(1u << (kj & 31)); }
+              if (HX && (kj & 0x10000)) { imo &= ~(1u << (kj & 31)); imi &= ~(1u << (kj & 31)); }
               else { /* the run [tj, tj + mj) of my window: at most one word boundary */
                 const int pp = tj - a0, sh = pp & 31;
                 const uint32_t m0 = lowmask(mj) << sh, m1 = sh + mj > 32 ? lowmask(mj) >> (32 - sh) : 0u;
@@ -332,6 +343,8 @@ struct Coop {
             }
           }
         }
+        };
+        if (nx) passes(HasX<true>{}); else passes(HasX<false>{}); /* uniform */
         /* commit: every lane's pick is final */
         const bool pick_x = key >= 0 && (key & 0x10000) != 0, pick_b = key >= 0 && !pick_x;
         if (pick_b) {
@@ -392,6 +405,9 @@ struct Coop {
       uint32_t kv[W];
 #pragma unroll
       for (int w = 0; w < W; w++) kv[w] = e.pl(P_KNOWN, w) & e.m_vuln(raw, w);
+      /* the rounds, compiled twice: without extra edges (every env of a fresh network) no candidate row of extras exists */
+      auto rounds = [&](auto has_x) {
+      constexpr bool HX = decltype(has_x)::value;
       int pos = 0;
       while (pos < ns) { /* uniform */
         const int idx = pos + lane;
@@ -400,7 +416,8 @@ struct Coop {
         uint32_t comp[W], xrow[W];
 #pragma unroll
         for (int w = 0; w < W; w++) { comp[w] = e.pl(P_COMP, w); xrow[w] = 0; }
-        if (nx > 32) {
+        if (!HX) {
+        } else if (nx > 32) {
           if (valid) e.extra_out_row(s, false, xrow);
         } else {
           for (int j = 0; j < nx; j++) { /* uniform */
@@ -413,7 +430,7 @@ struct Coop {
         }
         int cnt = 0, v = -1;
         bool rule3 = false;
-        if (valid) v = e.attack_source(s, comp, kv, has_blk, nx > 0 ? xrow : (const uint32_t*)nullptr, cnt, rule3);
+        if (valid) v = e.attack_source(s, comp, kv, has_blk, HX ? xrow : (const uint32_t*)nullptr, cnt, rule3);
         const uint32_t same = __match_any_sync(CYG_FULL, v >= 0 ? v : (0x1000 + lane));
         const bool conflict = valid && rule3 && (same & lanes_below(lane)) != 0;
         const uint32_t conf = __ballot_sync(CYG_FULL, conflict);
@@ -429,7 +446,7 @@ struct Coop {
           }
           const uint32_t tot = __shfl_sync(CYG_FULL, incl, 31), cap = (uint32_t)e.n->cfg.log_cap;
           const uint32_t end = log_base + tot;
-          if (nrec) e.log_source(s, v, has_blk, nx > 0 ? xrow : (const uint32_t*)nullptr, log_base + incl - nrec, end > cap ? end - cap : 0u);
+          if (nrec) e.log_source(s, v, has_blk, HX ? xrow : (const uint32_t*)nullptr, log_base + incl - nrec, end > cap ? end - cap : 0u);
           log_base = end;
         }
         if (valid && lane < c) {
@@ -442,6 +459,8 @@ struct Coop {
         pos += c;
         __syncwarp();
       }
+      };
+      if (nx) rounds(HasX<true>{}); else rounds(HasX<false>{}); /* uniform */
     }
     logs_add = __reduce_add_sync(CYG_FULL, logs_add);
     if (lane == 0) e.scal(CYG_S_LOGS) += logs_add;
