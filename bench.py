@@ -36,7 +36,7 @@ if ROOT not in sys.path:
 
 METRIC = "env-steps/sec at 64K envs x 100 devices"
 UNIT = "env-steps/s"
-PREHEAT = 8  # untimed launches before every timed region, whatever --warmup says
+PREHEAT = 64  # untimed launches before every timed region, whatever --warmup says: allocator, clocks, L2 and the env states (an episode a few hundred steps in steps differently from a fresh one) are then those of a long run
 
 
 def parse():
